@@ -1,0 +1,191 @@
+/*
+ * petal_b200.h -- C ABI of libpetal_b200.so, the B200-native (sm_100a) exact nearest-neighbour
+ * engine behind the petal-neighbors API.
+ *
+ * The reference (petabi/petal-neighbors v0.18.0) is a pure-Rust library with no FFI of its
+ * own; its public Rust API is the drop-in surface and this header is what a Rust `extern "C"`
+ * block (rust/petal-neighbors-b200/src/ffi.rs, shown in INTEGRATION.md) binds underneath it.
+ * Every entry point names the reference interface it replaces (file:line into the reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *   - every function returns a pn_status (int32_t); pn_last_error_message() gives the
+ *     thread-local detail string; no exception or panic crosses the ABI;
+ *   - `A` is f32 or f64 (the reference is generic over `A: Float`), one symbol per type;
+ *   - host-buffer calls (`pn_*_query_*`) copy queries H2D and results D2H themselves;
+ *     `_dev` calls take device pointers on the tree's device and enqueue on `stream`;
+ *   - indices are u64 at the boundary (Rust `usize`), u32 inside the engine (N < 2^32);
+ *   - k-NN results are ordered by (distance, index) ascending -- the reference's order for
+ *     distinct distances, with index as the tie-break (BASELINE.json north_star); rows are
+ *     padded with (UINT64_MAX, +inf) when k > n;
+ *   - distances are bit-identical to the reference's sequential non-FMA fold + sqrt
+ *     (src/distance.rs:26-35);
+ *   - there is no CPU fallback: a query on a machine without a usable CUDA device fails with
+ *     PN_CUDA.
+ * Threading: queries on one tree from several host threads are legal (the reference's
+ * `&self` queries, `Euclidean: Sync`, src/distance.rs:19); they serialise on an internal
+ * mutex.  create/destroy must not race with queries on the same handle.
+ */
+#ifndef PETAL_B200_H
+#define PETAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN_ABI_VERSION 1
+
+typedef enum pn_status {
+    PN_OK = 0,
+    PN_EMPTY = 1,          /* ArrayError::Empty,         src/lib.rs:12-13, src/ball_tree.rs:44-46 */
+    PN_NOT_CONTIGUOUS = 2, /* ArrayError::NotContiguous, src/lib.rs:14-15, src/ball_tree.rs:47-49 */
+    PN_BAD_ARG = 3,        /* null pointer, dtype/kind mismatch, n >= 2^32, bad option */
+    PN_CUDA = 4,           /* CUDA runtime error or no device (no CPU fallback) */
+    PN_NCCL = 5,           /* reserved: collectives are driven by the host language binding */
+    PN_OOM = 6             /* host or device allocation failed */
+} pn_status;
+
+typedef enum pn_tree_kind { PN_KIND_BALL = 0, PN_KIND_VP = 1 } pn_tree_kind;
+typedef enum pn_dtype { PN_F32 = 0, PN_F64 = 1 } pn_dtype;
+
+/* scan engine selection for k-NN */
+typedef enum pn_algo {
+    PN_ALGO_AUTO = 0,
+    PN_ALGO_SIMT = 1,  /* exact difference-form FP32/FP64 tiles on the CUDA cores */
+    PN_ALGO_TENSOR = 2 /* tcgen05 TF32 filter + exact rerank (f32, any d; AUTO picks it by d) */
+} pn_algo;
+
+#define PN_FLAG_HOST_ONLY 1u /* build + flatten on the host only (no device; queries fail with
+                                PN_CUDA).  For builder tests on machines without a GPU. */
+
+/* Engine knobs.  The reference has none; all are new.  Zero = default. */
+typedef struct pn_build_opts {
+    uint32_t struct_size; /* sizeof(pn_build_opts), for forward compatibility */
+    int32_t device;       /* CUDA device ordinal; -1 = current device */
+    uint32_t bucket_size; /* target points per leaf bucket (default 256, min 8) */
+    uint32_t algo;        /* pn_algo */
+    uint32_t host_threads; /* builder threads; 0 = hardware concurrency */
+    uint32_t flags;
+    /* Point sharding by subtree (multi-GPU, "points larger than one GPU's HBM"): keep only the
+     * points of subtree `shard_index` at depth `shard_depth` of the ball tree
+     * (src/ball_tree.rs:535-537 split rule).  Returned indices stay global.  0/0 = all. */
+    uint32_t shard_depth;
+    uint32_t shard_index;
+    uint32_t reserved[8];
+} pn_build_opts;
+
+typedef struct pn_tree pn_tree; /* opaque: flattened, device-resident tree */
+
+typedef struct pn_tree_info {
+    uint64_t n_points;     /* points held by this handle (shard-local) */
+    uint64_t n_points_total;
+    uint32_t dim, dim_padded;
+    uint32_t kind, dtype;
+    uint32_t n_levels;     /* cut level L: buckets are the reference's nodes at depth L */
+    uint32_t n_buckets, n_nodes;
+    uint32_t bucket_size_max;
+    int32_t device;
+    uint32_t algo;
+    uint64_t device_bytes;
+    double build_seconds;  /* host build + flatten + upload */
+} pn_tree_info;
+
+/* Work counters of the most recent query call. */
+typedef struct pn_counters {
+    uint64_t queries;
+    uint64_t pairs;          /* (query, point) distances evaluated by the scan kernels */
+    uint64_t filter_pairs;   /* (query, point) pairs seen by the tensor filter */
+    uint64_t rerank_pairs;   /* candidates re-evaluated exactly after the tensor filter */
+    uint64_t node_visits;    /* (query tile, node) visits of the traversal */
+    uint64_t kernel_launches;
+    double device_ms;        /* CUDA-event time of the device work of the call */
+    double scan_ms;          /* CUDA-event time of the dominant (scan/filter) kernel alone */
+    uint64_t h2d_bytes, d2h_bytes;
+} pn_counters;
+
+const char *pn_last_error_message(void);
+int32_t pn_abi_version(void);
+int32_t pn_device_count(int32_t *count);
+
+/* --- construction: BallTree::new / ::euclidean (src/ball_tree.rs:38-63, 367-373) and
+ * VantagePointTree::new / ::euclidean (src/vantage_point_tree.rs:31-72).  `points` is row-major
+ * with `row_stride` elements between rows and `col_stride` between the elements of a row
+ * (col_stride != 1 -> PN_NOT_CONTIGUOUS, the reference's row-0 check).  The buffer is borrowed
+ * for the duration of the call only.  `opts` may be NULL. */
+int32_t pn_balltree_create_f32(const float *points, size_t n, size_t d, size_t row_stride,
+                               size_t col_stride, const pn_build_opts *opts, pn_tree **out);
+int32_t pn_balltree_create_f64(const double *points, size_t n, size_t d, size_t row_stride,
+                               size_t col_stride, const pn_build_opts *opts, pn_tree **out);
+int32_t pn_vptree_create_f32(const float *points, size_t n, size_t d, size_t row_stride,
+                             size_t col_stride, const pn_build_opts *opts, pn_tree **out);
+int32_t pn_vptree_create_f64(const double *points, size_t n, size_t d, size_t row_stride,
+                             size_t col_stride, const pn_build_opts *opts, pn_tree **out);
+int32_t pn_tree_destroy(pn_tree *tree); /* Rust Drop */
+
+/* --- BallTree::query (src/ball_tree.rs:102-121), batched: `nq` queries, row stride
+ * `q_row_stride` elements; outputs are caller-allocated row-major nq x k.  k == 0 is a no-op
+ * (:106-108). */
+int32_t pn_balltree_query_f32(pn_tree *tree, const float *queries, size_t nq, size_t q_row_stride,
+                              size_t k, uint64_t *idx_out, float *dist_out);
+int32_t pn_balltree_query_f64(pn_tree *tree, const double *queries, size_t nq, size_t q_row_stride,
+                              size_t k, uint64_t *idx_out, double *dist_out);
+
+/* --- BallTree::query_nearest (src/ball_tree.rs:80-86), batched; outputs nq each. */
+int32_t pn_balltree_query_nearest_f32(pn_tree *tree, const float *queries, size_t nq,
+                                      size_t q_row_stride, uint64_t *idx_out, float *dist_out);
+int32_t pn_balltree_query_nearest_f64(pn_tree *tree, const double *queries, size_t nq,
+                                      size_t q_row_stride, uint64_t *idx_out, double *dist_out);
+
+/* --- BallTree::query_radius (src/ball_tree.rs:137-142), batched.  Result is CSR:
+ * offsets[nq + 1], indices[offsets[nq]] (strict `distance < r` on the bit-exact distance,
+ * :277; each query's indices ascending).  Both arrays are engine-allocated; release each with
+ * pn_free. */
+int32_t pn_balltree_query_radius_f32(pn_tree *tree, const float *queries, size_t nq,
+                                     size_t q_row_stride, float radius, uint64_t **offsets_out,
+                                     uint64_t **indices_out);
+int32_t pn_balltree_query_radius_f64(pn_tree *tree, const double *queries, size_t nq,
+                                     size_t q_row_stride, double radius, uint64_t **offsets_out,
+                                     uint64_t **indices_out);
+
+/* --- VantagePointTree::query_nearest (src/vantage_point_tree.rs:88-98), batched. */
+int32_t pn_vptree_query_nearest_f32(pn_tree *tree, const float *queries, size_t nq,
+                                    size_t q_row_stride, uint64_t *idx_out, float *dist_out);
+int32_t pn_vptree_query_nearest_f64(pn_tree *tree, const double *queries, size_t nq,
+                                    size_t q_row_stride, uint64_t *idx_out, double *dist_out);
+
+void pn_free(void *p);
+
+/* --- device-resident variants (queries and outputs already in HBM on the tree's device).
+ * Used by the bench's kernel-only leg and by multi-GPU drivers that all-gather per-shard
+ * results.  `stream` is a cudaStream_t (NULL = the tree's own stream); the call returns after
+ * enqueueing unless `sync` != 0.  The element type is the tree's dtype. */
+int32_t pn_tree_query_knn_dev(pn_tree *tree, const void *queries_dev, size_t nq,
+                              size_t q_row_stride, size_t k, uint64_t *idx_dev, void *dist_dev,
+                              void *stream, int32_t sync);
+
+/* K-way merge of `n_lists` per-shard sorted top-k lists (layout [list][nq][k]) by
+ * (distance, index): the step after the all-gather when points are sharded by subtree
+ * (no reference equivalent).  All pointers are device pointers on `device`. */
+int32_t pn_merge_topk_dev(uint32_t dtype, int32_t device, const uint64_t *idx_lists_dev,
+                          const void *dist_lists_dev, size_t n_lists, size_t nq, size_t k,
+                          uint64_t *idx_out_dev, void *dist_out_dev, void *stream, int32_t sync);
+
+/* --- introspection */
+int32_t pn_tree_get_info(const pn_tree *tree, pn_tree_info *info);
+int32_t pn_tree_get_counters(const pn_tree *tree, pn_counters *counters);
+
+/* Copy-out of the flattened layout (builder tests).  Any pointer may be
+ * NULL.  ids[n]: original index of the i-th point in bucket order; bucket_lo/hi[n_buckets];
+ * node_radius[n_nodes] (ball: radius, vp: threshold mu); node_center[n_nodes * dim_padded]
+ * (ball: centroid, vp: vantage point); points[n * dim_padded] in the tree's dtype. */
+int32_t pn_tree_get_layout(const pn_tree *tree, uint32_t *ids, uint32_t *bucket_lo,
+                           uint32_t *bucket_hi, void *node_radius, void *node_center,
+                           void *points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PETAL_B200_H */

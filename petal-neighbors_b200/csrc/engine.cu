@@ -1,0 +1,590 @@
+// engine.cu -- host side of libpetal_b200.so: tree handles, workspaces, kernel launches and the
+// C ABI declared in include/petal_b200.h.  No CPU fallback: every query entry point launches the
+// sm_100a kernels of kernels.cuh or fails with PN_CUDA.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/petal_b200.h"
+#include "flat_tree.hpp"
+#include "kernels.cuh"
+
+namespace petal {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(x)                                                                                          \
+    do {                                                                                               \
+        cudaError_t e_ = (x);                                                                          \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? PN_OOM : PN_CUDA,                            \
+                        std::string(#x) + ": " + cudaGetErrorString(e_));                              \
+    } while (0)
+#define TRY(x)                  \
+    do {                        \
+        int r_ = (x);           \
+        if (r_ != PN_OK) return r_; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return PN_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) { p = nullptr; return fail(PN_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+        cap = want;
+        return PN_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; (void)cudaGetLastError(); return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) { ok = false; (void)cudaGetLastError(); }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace petal
+
+using namespace petal;
+
+// The opaque handle.
+struct pn_tree {
+    virtual ~pn_tree() {}
+    pn_tree_info info{};
+    pn_counters counters{};
+    std::mutex mu;
+    bool host_only = false;
+    virtual int knn_host(const void* q, size_t nq, size_t stride, size_t k, uint64_t* idx, void* dist) = 0;
+    virtual int knn_dev(const void* q, size_t nq, size_t stride, size_t k, uint64_t* idx, void* dist,
+                        cudaStream_t st, bool sync) = 0;
+    virtual int radius_host(const void* q, size_t nq, size_t stride, double r, uint64_t** offs, uint64_t** idx) = 0;
+    virtual int layout(uint32_t* ids, uint32_t* blo, uint32_t* bhi, void* rad, void* cen, void* pts) = 0;
+};
+
+namespace petal {
+
+template <typename A>
+struct Engine final : pn_tree {
+    using V = typename VT<A>::V;
+    FlatTree<A> ft;  // host copy of the flattened tree (point rows dropped after upload)
+    int device = 0;
+    int n_sms = 148;
+    cudaStream_t stream = nullptr, last_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    DevBuf d_pts, d_ids, d_blo, d_bhi, d_centers, d_radii, d_vpids;
+    DevBuf w_qraw, w_q, w_home, w_hist, w_cursor, w_order, w_part_d, w_part_i, w_floor_d, w_floor_i,
+        w_counters, w_out_i, w_out_d, w_counts, w_offsets, w_hits;
+    DevTree<A> dt{};
+
+    ~Engine() override {
+        if (!host_only) {
+            DeviceGuard g(device);
+            for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &w_qraw, &w_q, &w_home,
+                              &w_hist, &w_cursor, &w_order, &w_part_d, &w_part_i, &w_floor_d, &w_floor_i, &w_counters,
+                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits})
+                b->release();
+            for (auto& e : ev) if (e) cudaEventDestroy(e);
+            if (stream) cudaStreamDestroy(stream);
+        }
+    }
+
+    int upload() {
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "no usable CUDA device (there is no CPU fallback)");
+        CU(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+        auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
+            TRY(b.ensure(bytes ? bytes : 16));
+            if (bytes) CU(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+            return PN_OK;
+        };
+        TRY(up(d_pts, ft.pts.data(), ft.pts.size() * sizeof(A)));
+        TRY(up(d_ids, ft.ids.data(), ft.ids.size() * 4));
+        TRY(up(d_blo, ft.bucket_lo.data(), ft.bucket_lo.size() * 4));
+        TRY(up(d_bhi, ft.bucket_hi.data(), ft.bucket_hi.size() * 4));
+        TRY(up(d_centers, ft.centers.data(), ft.centers.size() * sizeof(A)));
+        TRY(up(d_radii, ft.radii.data(), ft.radii.size() * sizeof(A)));
+        TRY(up(d_vpids, ft.vp_ids.data(), ft.vp_ids.size() * 4));
+        info.device_bytes = d_pts.cap + d_ids.cap + d_blo.cap + d_bhi.cap + d_centers.cap + d_radii.cap + d_vpids.cap;
+        std::vector<A>().swap(ft.pts);  // the device copy is the point store from here on
+        fill_dev_tree();
+        return PN_OK;
+    }
+
+    void fill_dev_tree() {
+        dt.pts = d_pts.as<V>(); dt.ids = d_ids.as<uint32_t>();
+        dt.bucket_lo = d_blo.as<uint32_t>(); dt.bucket_hi = d_bhi.as<uint32_t>();
+        dt.centers = d_centers.as<V>(); dt.radii = d_radii.as<A>(); dt.vp_ids = d_vpids.as<uint32_t>();
+        dt.n = (uint32_t)ft.n; dt.d = ft.d; dt.dpad = ft.dpad; dt.dv = ft.dpad / VT<A>::N;
+        dt.L = ft.L; dt.n_internal = ft.n_internal; dt.n_buckets = ft.n_buckets; dt.n_nodes = ft.n_nodes;
+        dt.kind = ft.kind;
+        const double u = sizeof(A) == 4 ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
+        dt.slack = (A)((2.0 * ft.d + 8.0) * u);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    template <int DVR, int K, int KIND>
+    int launch_knn_t(const KnnArgs<A>& a, dim3 grid, cudaStream_t st) {
+        size_t smem = TILE_BYTES + (DVR == 0 ? (size_t)TQ * ft.dpad * sizeof(A) : 0);
+        auto kern = knn_tile_kernel<A, DVR, K, KIND>;
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TQ, smem, st>>>(a);
+        CU(cudaGetLastError());
+        return PN_OK;
+    }
+    template <int K, int KIND>
+    int launch_knn_k(const KnnArgs<A>& a, dim3 grid, cudaStream_t st) {
+        switch (dt.dv) {
+            case 1: return launch_knn_t<1, K, KIND>(a, grid, st);
+            case 2: return launch_knn_t<2, K, KIND>(a, grid, st);
+            case 4: return launch_knn_t<4, K, KIND>(a, grid, st);
+            case 8: return launch_knn_t<8, K, KIND>(a, grid, st);
+            default: return launch_knn_t<0, K, KIND>(a, grid, st);
+        }
+    }
+    int launch_knn(const KnnArgs<A>& a, dim3 grid, cudaStream_t st, bool k1) {
+        if (ft.kind == 0) return k1 ? launch_knn_k<1, 0>(a, grid, st) : launch_knn_k<16, 0>(a, grid, st);
+        return k1 ? launch_knn_k<1, 1>(a, grid, st) : launch_knn_k<16, 1>(a, grid, st);
+    }
+
+    int use_stream(cudaStream_t st) {
+        if (last_stream && last_stream != st) CU(cudaStreamSynchronize(last_stream));
+        last_stream = st;
+        return PN_OK;
+    }
+
+    // queries (raw rows on the device) -> zero-padded rows + tile order
+    int stage_queries(const A* qraw, uint32_t nq, size_t stride, cudaStream_t st, bool sort) {
+        TRY(w_q.ensure((size_t)nq * ft.dpad * sizeof(A)));
+        const size_t tot = (size_t)nq * ft.dpad;
+        pad_queries_kernel<A><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(qraw, stride, nq, ft.d, ft.dpad, w_q.as<A>());
+        CU(cudaGetLastError());
+        ++counters.kernel_launches;
+        if (!sort) return PN_OK;
+        TRY(w_home.ensure((size_t)nq * 4));
+        TRY(w_order.ensure((size_t)nq * 4));
+        TRY(w_hist.ensure((size_t)ft.n_buckets * 4));
+        TRY(w_cursor.ensure((size_t)ft.n_buckets * 4));
+        CU(cudaMemsetAsync(w_hist.p, 0, (size_t)ft.n_buckets * 4, st));
+        home_bucket_kernel<A><<<(nq + 127) / 128, 128, 0, st>>>(dt, w_q.as<V>(), nq, w_home.as<uint32_t>(), w_hist.as<uint32_t>());
+        CU(cudaGetLastError());
+        exclusive_scan_kernel<<<1, 1024, 0, st>>>(w_hist.as<uint32_t>(), w_cursor.as<uint32_t>(), ft.n_buckets);
+        CU(cudaGetLastError());
+        scatter_order_kernel<<<(nq + 255) / 256, 256, 0, st>>>(w_home.as<uint32_t>(), w_cursor.as<uint32_t>(), nq, w_order.as<uint32_t>());
+        CU(cudaGetLastError());
+        counters.kernel_launches += 3;
+        return PN_OK;
+    }
+
+    // k-NN for nq queries whose raw rows are already on the device; results to device buffers
+    int knn_device(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st) {
+        const bool sort = ft.n_buckets > 1 && nq > (uint32_t)TQ;
+        TRY(stage_queries(qraw, nq, stride, st, sort));
+        const uint32_t tiles = (nq + TQ - 1) / TQ;
+        uint32_t sl = 0;
+        while (((uint64_t)tiles << sl) < 2ull * n_sms && sl < ft.L && (2u << sl) <= (uint32_t)MAX_LISTS) ++sl;
+        const uint32_t n_splits = 1u << sl;
+        const bool k1 = (k == 1);
+        const uint32_t KP = k1 ? 1 : 16;
+        const uint32_t n_pass = (k + KP - 1) / KP;
+        TRY(w_part_d.ensure((size_t)n_splits * nq * KP * sizeof(A)));
+        TRY(w_part_i.ensure((size_t)n_splits * nq * KP * 4));
+        TRY(w_counters.ensure(16));
+        if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * sizeof(A))); TRY(w_floor_i.ensure((size_t)nq * 4)); }
+        CU(cudaMemsetAsync(w_counters.p, 0, 16, st));
+        CU(cudaEventRecord(ev[2], st));
+        for (uint32_t p = 0; p < n_pass; ++p) {
+            const uint32_t kk = std::min(KP, k - p * KP);
+            KnnArgs<A> a{};
+            a.t = dt; a.q = w_q.as<V>(); a.qorder = sort ? w_order.as<uint32_t>() : nullptr;
+            a.nq = nq; a.k = kk; a.split_level = sl;
+            a.part_d = w_part_d.as<A>(); a.part_i = w_part_i.as<uint32_t>();
+            a.floor_d = p ? w_floor_d.as<A>() : nullptr; a.floor_i = p ? w_floor_i.as<uint32_t>() : nullptr;
+            a.counters = w_counters.as<unsigned long long>();
+            TRY(launch_knn(a, dim3(tiles, n_splits), st, k1));
+            merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
+                w_part_d.as<A>(), w_part_i.as<uint32_t>(), n_splits, nq, kk, idx_out, dist_out, k, p * KP,
+                n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr);
+            CU(cudaGetLastError());
+            counters.kernel_launches += 2;
+        }
+        CU(cudaEventRecord(ev[3], st));
+        return PN_OK;
+    }
+
+    int fetch_counters(cudaStream_t st, uint64_t nq) {
+        unsigned long long c[2] = {0, 0};
+        CU(cudaMemcpyAsync(c, w_counters.p, 16, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        counters.queries = nq;
+        counters.pairs = c[0];
+        counters.node_visits = c[1];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) counters.device_ms = ms; else (void)cudaGetLastError();
+        if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) counters.scan_ms = ms; else (void)cudaGetLastError();
+        return PN_OK;
+    }
+
+    int check_query_args(const void* q, size_t nq, size_t stride) {
+        if (host_only) return fail(PN_CUDA, "tree was built with PN_FLAG_HOST_ONLY: no device, and there is no CPU fallback");
+        if (nq && !q) return fail(PN_BAD_ARG, "queries is null");
+        if (nq >= (1ull << 32)) return fail(PN_BAD_ARG, "nq must be < 2^32 per call");
+        if (nq > 1 && stride < ft.d) return fail(PN_BAD_ARG, "q_row_stride < dimension");
+        return PN_OK;
+    }
+
+    int knn_host(const void* qv, size_t nq, size_t stride, size_t k, uint64_t* idx, void* distv) override {
+        TRY(check_query_args(qv, nq, stride));
+        if (k == 0 || nq == 0) return PN_OK;  // src/ball_tree.rs:106-108
+        if (!idx || !distv) return fail(PN_BAD_ARG, "output buffer is null");
+        std::lock_guard<std::mutex> lk(mu);
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        counters = pn_counters{};
+        const A* q = (const A*)qv;
+        A* dist = (A*)distv;
+        cudaStream_t st = stream;
+        TRY(use_stream(st));
+        // bounded device workspace: chunks of at most 2^20 queries
+        const size_t chunk = 1u << 20;
+        CU(cudaEventRecord(ev[0], st));
+        for (size_t q0 = 0; q0 < nq; q0 += chunk) {
+            const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
+            TRY(w_qraw.ensure((size_t)cq * ft.d * sizeof(A)));
+            TRY(w_out_i.ensure((size_t)cq * k * 8));
+            TRY(w_out_d.ensure((size_t)cq * k * sizeof(A)));
+            CU(cudaMemcpy2DAsync(w_qraw.p, ft.d * sizeof(A), q + q0 * stride, stride * sizeof(A), ft.d * sizeof(A), cq,
+                                 cudaMemcpyHostToDevice, st));
+            TRY(knn_device(w_qraw.as<A>(), cq, ft.d, (uint32_t)k, w_out_i.as<uint64_t>(), w_out_d.as<A>(), st));
+            CU(cudaMemcpyAsync(idx + q0 * k, w_out_i.p, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(dist + q0 * k, w_out_d.p, (size_t)cq * k * sizeof(A), cudaMemcpyDeviceToHost, st));
+            counters.h2d_bytes += (uint64_t)cq * ft.d * sizeof(A);
+            counters.d2h_bytes += (uint64_t)cq * k * (8 + sizeof(A));
+            if (q0 + chunk < nq) CU(cudaStreamSynchronize(st));  // workspace reuse
+        }
+        CU(cudaEventRecord(ev[1], st));
+        return fetch_counters(st, nq);
+    }
+
+    int knn_dev(const void* qv, size_t nq, size_t stride, size_t k, uint64_t* idx, void* distv, cudaStream_t st, bool sync) override {
+        TRY(check_query_args(qv, nq, stride));
+        if (k == 0 || nq == 0) return PN_OK;
+        if (!idx || !distv) return fail(PN_BAD_ARG, "output buffer is null");
+        std::lock_guard<std::mutex> lk(mu);
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        if (!st) st = stream;
+        TRY(use_stream(st));
+        counters = pn_counters{};
+        CU(cudaEventRecord(ev[0], st));
+        TRY(knn_device((const A*)qv, (uint32_t)nq, stride, (uint32_t)k, idx, (A*)distv, st));
+        CU(cudaEventRecord(ev[1], st));
+        if (sync) return fetch_counters(st, nq);
+        counters.queries = nq;
+        return PN_OK;
+    }
+
+    int radius_host(const void* qv, size_t nq, size_t stride, double rr, uint64_t** offs_out, uint64_t** idx_out) override {
+        TRY(check_query_args(qv, nq, stride));
+        if (ft.kind != 0) return fail(PN_BAD_ARG, "query_radius is a BallTree method (the reference VP tree has none)");
+        if (!offs_out || !idx_out) return fail(PN_BAD_ARG, "output pointer is null");
+        std::lock_guard<std::mutex> lk(mu);
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        counters = pn_counters{};
+        const A r = (A)rr;
+        const A* q = (const A*)qv;
+        cudaStream_t st = stream;
+        TRY(use_stream(st));
+        uint64_t* offs = (uint64_t*)malloc((nq + 1) * 8);
+        if (!offs) return fail(PN_OOM, "malloc offsets");
+        offs[0] = 0;
+        uint64_t* hit_buf = nullptr;
+        size_t hit_cap = 0, total = 0;
+        const size_t chunk = 1u << 20;
+        const uint32_t wpb = 8;
+        auto bail = [&](int rc) { free(offs); free(hit_buf); return rc; };
+        if (cudaEventRecord(ev[0], st) != cudaSuccess) return bail(fail(PN_CUDA, "cudaEventRecord"));
+#define CUB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(fail(PN_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_))); } while (0)
+#define TRYB(x) do { int r_ = (x); if (r_ != PN_OK) return bail(r_); } while (0)
+        TRYB(w_counters.ensure(16));
+        CUB(cudaMemsetAsync(w_counters.p, 0, 16, st));
+        for (size_t q0 = 0; q0 < nq; q0 += chunk) {
+            const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
+            TRYB(w_qraw.ensure((size_t)cq * ft.d * sizeof(A)));
+            CUB(cudaMemcpy2DAsync(w_qraw.p, ft.d * sizeof(A), q + q0 * stride, stride * sizeof(A), ft.d * sizeof(A), cq,
+                                  cudaMemcpyHostToDevice, st));
+            TRYB(stage_queries(w_qraw.as<A>(), cq, ft.d, st, false));
+            TRYB(w_counts.ensure((size_t)cq * 4));
+            TRYB(w_offsets.ensure((size_t)(cq + 1) * 8));
+            const unsigned blocks = (cq + wpb - 1) / wpb;
+            if (q0 == 0) CUB(cudaEventRecord(ev[2], st));
+            radius_kernel<A><<<blocks, wpb * 32, 0, st>>>(dt, w_q.as<V>(), cq, r, w_counts.as<uint32_t>(), nullptr, nullptr,
+                                                         w_counters.as<unsigned long long>());
+            CUB(cudaGetLastError());
+            offsets_scan_kernel<<<1, 1024, 0, st>>>(w_counts.as<uint32_t>(), w_offsets.as<uint64_t>(), cq);
+            CUB(cudaGetLastError());
+            CUB(cudaMemcpyAsync(offs + q0 + 1, w_offsets.as<uint64_t>() + 1, (size_t)cq * 8, cudaMemcpyDeviceToHost, st));
+            CUB(cudaStreamSynchronize(st));
+            const uint64_t ctotal = offs[q0 + cq];  // chunk-local total
+            TRYB(w_hits.ensure((ctotal ? ctotal : 1) * 8));
+            radius_kernel<A><<<blocks, wpb * 32, 0, st>>>(dt, w_q.as<V>(), cq, r, w_counts.as<uint32_t>(), w_offsets.as<uint64_t>(),
+                                                         w_hits.as<uint64_t>(), nullptr);
+            CUB(cudaGetLastError());
+            segment_sort_kernel<<<blocks, wpb * 32, 0, st>>>(w_offsets.as<uint64_t>(), w_hits.as<uint64_t>(), cq);
+            CUB(cudaGetLastError());
+            if (q0 + chunk >= nq) CUB(cudaEventRecord(ev[3], st));
+            counters.kernel_launches += 4;
+            if (total + ctotal > hit_cap) {
+                size_t ncap = std::max<size_t>(total + ctotal, hit_cap * 2);
+                uint64_t* nb = (uint64_t*)realloc(hit_buf, (ncap ? ncap : 1) * 8);
+                if (!nb) return bail(fail(PN_OOM, "realloc indices"));
+                hit_buf = nb; hit_cap = ncap;
+            }
+            if (ctotal) CUB(cudaMemcpyAsync(hit_buf + total, w_hits.p, ctotal * 8, cudaMemcpyDeviceToHost, st));
+            CUB(cudaStreamSynchronize(st));
+            for (uint32_t i = 1; i <= cq; ++i) offs[q0 + i] += total;  // chunk-local -> global offsets
+            total += ctotal;
+            counters.h2d_bytes += (uint64_t)cq * ft.d * sizeof(A);
+            counters.d2h_bytes += (uint64_t)cq * 8 + ctotal * 8;
+        }
+        if (nq == 0) { CUB(cudaEventRecord(ev[2], st)); CUB(cudaEventRecord(ev[3], st)); }
+        CUB(cudaEventRecord(ev[1], st));
+        if (!hit_buf) hit_buf = (uint64_t*)malloc(8);
+        TRYB(fetch_counters(st, nq));
+#undef CUB
+#undef TRYB
+        *offs_out = offs;
+        *idx_out = hit_buf;
+        return PN_OK;
+    }
+
+    int layout(uint32_t* ids, uint32_t* blo, uint32_t* bhi, void* rad, void* cen, void* pts) override {
+        if (ids) memcpy(ids, ft.ids.data(), ft.ids.size() * 4);
+        if (blo) memcpy(blo, ft.bucket_lo.data(), ft.bucket_lo.size() * 4);
+        if (bhi) memcpy(bhi, ft.bucket_hi.data(), ft.bucket_hi.size() * 4);
+        if (rad) memcpy(rad, ft.radii.data(), (size_t)ft.n_nodes * sizeof(A));
+        if (cen) memcpy(cen, ft.centers.data(), (size_t)ft.n_nodes * ft.dpad * sizeof(A));
+        if (pts) {
+            if (host_only) memcpy(pts, ft.pts.data(), ft.pts.size() * sizeof(A));
+            else {
+                DeviceGuard g(device);
+                CU(cudaMemcpy(pts, d_pts.p, (size_t)ft.n * ft.dpad * sizeof(A), cudaMemcpyDeviceToHost));
+            }
+        }
+        return PN_OK;
+    }
+};
+
+template <typename A>
+static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row_stride, size_t col_stride,
+                       const pn_build_opts* opts_in, pn_tree** out) {
+    if (!out) return fail(PN_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (n == 0) return fail(PN_EMPTY, "array is empty");                                         // src/ball_tree.rs:44-46
+    if (d > 1 && col_stride != 1) return fail(PN_NOT_CONTIGUOUS, "array is not contiguous in memory");  // :47-49
+    if (!points) return fail(PN_BAD_ARG, "points is null");
+    if (d == 0) return fail(PN_BAD_ARG, "points have zero columns");
+    if (n >= 0xFFFFFFFFull) return fail(PN_BAD_ARG, "n must be < 2^32 - 1 (u32 indices inside the engine)");
+    if (n > 1 && row_stride < d) return fail(PN_BAD_ARG, "row_stride < dimension");
+    pn_build_opts o{};
+    if (opts_in) memcpy(&o, opts_in, std::min<size_t>(sizeof(o), opts_in->struct_size ? opts_in->struct_size : sizeof(o)));
+    else o.device = -1;
+    const size_t dpad = (d + VT<A>::N - 1) / VT<A>::N * VT<A>::N;
+    if (dpad * sizeof(A) > 1024) return fail(PN_BAD_ARG, "dimension too large: a padded row must fit 1024 bytes (f32 d<=256, f64 d<=128)");
+    uint32_t bucket = o.bucket_size ? o.bucket_size : 256;
+    if (bucket < 8) bucket = 8;
+    uint32_t threads = o.host_threads ? o.host_threads : std::max(1u, std::thread::hardware_concurrency());
+    auto t0 = std::chrono::steady_clock::now();
+    std::unique_ptr<Engine<A>> e;
+    try {
+        e.reset(new Engine<A>());
+        if (kind == PN_KIND_BALL) {
+            BallBuilder<A> b(points, n, d, row_stride, threads);
+            std::vector<uint32_t> idx(n);
+            for (size_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
+            size_t lo = 0, hi = n;
+            if (o.shard_depth) {
+                if (o.shard_depth > 16 || o.shard_index >= (1u << o.shard_depth)) return fail(PN_BAD_ARG, "bad shard_depth / shard_index");
+                b.shard_range(idx, o.shard_depth, o.shard_index, lo, hi);
+                if (hi == lo) return fail(PN_EMPTY, "shard holds no points");
+            }
+            b.build(idx, lo, hi, bucket, e->ft);
+        } else {
+            if (o.shard_depth) return fail(PN_BAD_ARG, "subtree sharding is a ball-tree option");
+            VpBuilder<A> b(points, n, d, row_stride, threads);
+            b.build(bucket, e->ft);
+        }
+    } catch (const std::bad_alloc&) {
+        return fail(PN_OOM, "host allocation failed while building the tree");
+    }
+    FlatTree<A>& ft = e->ft;
+    e->host_only = (o.flags & PN_FLAG_HOST_ONLY) != 0;
+    pn_tree_info& inf = e->info;
+    inf.n_points = ft.n; inf.n_points_total = ft.n_total;
+    inf.dim = ft.d; inf.dim_padded = ft.dpad;
+    inf.kind = kind; inf.dtype = sizeof(A) == 4 ? PN_F32 : PN_F64;
+    inf.n_levels = ft.L; inf.n_buckets = ft.n_buckets; inf.n_nodes = ft.n_nodes;
+    inf.bucket_size_max = ft.bucket_max;
+    inf.algo = o.algo;
+    inf.device = -1;
+    if (!e->host_only) {
+        int dev = o.device;
+        if (dev < 0) {
+            if (cudaGetDevice(&dev) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return fail(PN_CUDA, "no CUDA device available (there is no CPU fallback)");
+            }
+        }
+        e->device = dev;
+        inf.device = dev;
+        TRY(e->upload());
+    }
+    inf.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *out = e.release();
+    return PN_OK;
+}
+
+template <typename A>
+static int merge_topk_dev(int device, const uint64_t* idx_lists, const A* dist_lists, size_t n_lists, size_t nq, size_t k,
+                          uint64_t* idx_out, A* dist_out, cudaStream_t st, bool sync) {
+    if (!idx_lists || !dist_lists || !idx_out || !dist_out) return fail(PN_BAD_ARG, "null pointer");
+    if (n_lists == 0 || n_lists > (size_t)MAX_LISTS) return fail(PN_BAD_ARG, "n_lists must be in 1..256");
+    if (k > 65535 || nq >= (1ull << 32)) return fail(PN_BAD_ARG, "k must be <= 65535 and nq < 2^32");
+    if (nq == 0 || k == 0) return PN_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+    merge_lists_kernel<A, uint64_t><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(dist_lists, idx_lists, (uint32_t)n_lists, (uint32_t)nq,
+                                                                          (uint32_t)k, idx_out, dist_out, (uint32_t)k, 0, nullptr, nullptr);
+    CU(cudaGetLastError());
+    if (sync) CU(cudaStreamSynchronize(st));
+    return PN_OK;
+}
+
+}  // namespace petal
+
+// ================================= C ABI ======================================================
+#define GUARD_BEGIN try {
+#define GUARD_END                                                              \
+    }                                                                          \
+    catch (const std::bad_alloc&) { return fail(PN_OOM, "host allocation failed"); } \
+    catch (const std::exception& ex) { return fail(PN_BAD_ARG, ex.what()); }  \
+    catch (...) { return fail(PN_BAD_ARG, "unknown error"); }
+
+static int check_tree(const pn_tree* t, uint32_t dtype, int kind) {
+    if (!t) return fail(PN_BAD_ARG, "tree is null");
+    if (t->info.dtype != dtype) return fail(PN_BAD_ARG, "element type of the call does not match the tree");
+    if (kind >= 0 && (int)t->info.kind != kind) return fail(PN_BAD_ARG, "tree kind does not match the call");
+    return PN_OK;
+}
+
+extern "C" {
+
+const char* pn_last_error_message(void) { return g_err.c_str(); }
+int32_t pn_abi_version(void) { return PN_ABI_VERSION; }
+int32_t pn_device_count(int32_t* count) {
+    if (!count) return fail(PN_BAD_ARG, "count is null");
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { (void)cudaGetLastError(); c = 0; }
+    *count = c;
+    return PN_OK;
+}
+
+int32_t pn_balltree_create_f32(const float* p, size_t n, size_t d, size_t rs, size_t cs, const pn_build_opts* o, pn_tree** out) {
+    GUARD_BEGIN return create_tree<float>(PN_KIND_BALL, p, n, d, rs, cs, o, out); GUARD_END
+}
+int32_t pn_balltree_create_f64(const double* p, size_t n, size_t d, size_t rs, size_t cs, const pn_build_opts* o, pn_tree** out) {
+    GUARD_BEGIN return create_tree<double>(PN_KIND_BALL, p, n, d, rs, cs, o, out); GUARD_END
+}
+int32_t pn_vptree_create_f32(const float* p, size_t n, size_t d, size_t rs, size_t cs, const pn_build_opts* o, pn_tree** out) {
+    GUARD_BEGIN return create_tree<float>(PN_KIND_VP, p, n, d, rs, cs, o, out); GUARD_END
+}
+int32_t pn_vptree_create_f64(const double* p, size_t n, size_t d, size_t rs, size_t cs, const pn_build_opts* o, pn_tree** out) {
+    GUARD_BEGIN return create_tree<double>(PN_KIND_VP, p, n, d, rs, cs, o, out); GUARD_END
+}
+int32_t pn_tree_destroy(pn_tree* t) {
+    GUARD_BEGIN delete t; return PN_OK; GUARD_END
+}
+
+int32_t pn_balltree_query_f32(pn_tree* t, const float* q, size_t nq, size_t qs, size_t k, uint64_t* io, float* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F32, PN_KIND_BALL)); return t->knn_host(q, nq, qs, k, io, dd); GUARD_END
+}
+int32_t pn_balltree_query_f64(pn_tree* t, const double* q, size_t nq, size_t qs, size_t k, uint64_t* io, double* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_BALL)); return t->knn_host(q, nq, qs, k, io, dd); GUARD_END
+}
+int32_t pn_balltree_query_nearest_f32(pn_tree* t, const float* q, size_t nq, size_t qs, uint64_t* io, float* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F32, PN_KIND_BALL)); return t->knn_host(q, nq, qs, 1, io, dd); GUARD_END
+}
+int32_t pn_balltree_query_nearest_f64(pn_tree* t, const double* q, size_t nq, size_t qs, uint64_t* io, double* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_BALL)); return t->knn_host(q, nq, qs, 1, io, dd); GUARD_END
+}
+int32_t pn_balltree_query_radius_f32(pn_tree* t, const float* q, size_t nq, size_t qs, float r, uint64_t** oo, uint64_t** io) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F32, PN_KIND_BALL)); return t->radius_host(q, nq, qs, (double)r, oo, io); GUARD_END
+}
+int32_t pn_balltree_query_radius_f64(pn_tree* t, const double* q, size_t nq, size_t qs, double r, uint64_t** oo, uint64_t** io) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_BALL)); return t->radius_host(q, nq, qs, r, oo, io); GUARD_END
+}
+int32_t pn_vptree_query_nearest_f32(pn_tree* t, const float* q, size_t nq, size_t qs, uint64_t* io, float* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F32, PN_KIND_VP)); return t->knn_host(q, nq, qs, 1, io, dd); GUARD_END
+}
+int32_t pn_vptree_query_nearest_f64(pn_tree* t, const double* q, size_t nq, size_t qs, uint64_t* io, double* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_VP)); return t->knn_host(q, nq, qs, 1, io, dd); GUARD_END
+}
+void pn_free(void* p) { free(p); }
+
+int32_t pn_tree_query_knn_dev(pn_tree* t, const void* q, size_t nq, size_t qs, size_t k, uint64_t* io, void* dd, void* stream, int32_t sync) {
+    GUARD_BEGIN
+    if (!t) return fail(PN_BAD_ARG, "tree is null");
+    return t->knn_dev(q, nq, qs, k, io, dd, (cudaStream_t)stream, sync != 0);
+    GUARD_END
+}
+int32_t pn_merge_topk_dev(uint32_t dtype, int32_t device, const uint64_t* il, const void* dl, size_t n_lists, size_t nq, size_t k,
+                          uint64_t* io, void* dd, void* stream, int32_t sync) {
+    GUARD_BEGIN
+    if (dtype == PN_F32) return merge_topk_dev<float>(device, il, (const float*)dl, n_lists, nq, k, io, (float*)dd, (cudaStream_t)stream, sync != 0);
+    if (dtype == PN_F64) return merge_topk_dev<double>(device, il, (const double*)dl, n_lists, nq, k, io, (double*)dd, (cudaStream_t)stream, sync != 0);
+    return fail(PN_BAD_ARG, "bad dtype");
+    GUARD_END
+}
+
+int32_t pn_tree_get_info(const pn_tree* t, pn_tree_info* info) {
+    if (!t || !info) return fail(PN_BAD_ARG, "null pointer");
+    *info = t->info;
+    return PN_OK;
+}
+int32_t pn_tree_get_counters(const pn_tree* t, pn_counters* c) {
+    if (!t || !c) return fail(PN_BAD_ARG, "null pointer");
+    *c = t->counters;
+    return PN_OK;
+}
+int32_t pn_tree_get_layout(const pn_tree* t, uint32_t* ids, uint32_t* blo, uint32_t* bhi, void* rad, void* cen, void* pts) {
+    GUARD_BEGIN
+    if (!t) return fail(PN_BAD_ARG, "tree is null");
+    return const_cast<pn_tree*>(t)->layout(ids, blo, bhi, rad, cen, pts);
+    GUARD_END
+}
+
+}  // extern "C"

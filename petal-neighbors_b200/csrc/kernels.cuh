@@ -1,0 +1,576 @@
+// kernels.cuh -- sm_100a device code of the exact k-NN / radius engine.
+//
+// Replaces, for batches of queries, the per-query recursion of the reference:
+//   knn_tile_kernel   : nearest_k_neighbors_in_subtree src/ball_tree.rs:203-243,
+//                       nearest_neighbor_in_subtree :149-196, search_node
+//                       src/vantage_point_tree.rs:100-130 (k = 1)
+//   radius_kernel     : neighbors_within_radius_in_subtree src/ball_tree.rs:250-294
+//   merge_lists_kernel: BinaryHeap::into_sorted_vec :117 for split scans / point shards
+// Every distance is Euclidean::distance (src/distance.rs:26-35) evaluated with explicit
+// round-to-nearest intrinsics in the reference's order (sub, mul, add per dimension, then
+// sqrt) so that it is bit-identical to the Rust fold: the compiler can neither contract the
+// multiply-add into an FMA nor reassociate the sum.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace petal {
+
+constexpr int TQ = 128;           // queries per CTA of the tile scan, one per thread
+constexpr int RP = 8;             // points per register tile (independent fold chains per thread)
+constexpr int TILE_BYTES = 16384; // shared-memory point tile
+constexpr int MAX_STACK = 40;     // traversal stack depth (tree depth <= 32)
+constexpr uint32_t NO_ID = 0xFFFFFFFFu;
+
+template <typename A> struct VT;
+template <> struct VT<float>  { using V = float4;  static constexpr int N = 4; };
+template <> struct VT<double> { using V = double2; static constexpr int N = 2; };
+
+// ---- exact IEEE arithmetic (never contracted, never reassociated) -------------------------
+__device__ __forceinline__ float  xsub(float a, float b)   { return __fsub_rn(a, b); }
+__device__ __forceinline__ float  xmul(float a, float b)   { return __fmul_rn(a, b); }
+__device__ __forceinline__ float  xadd(float a, float b)   { return __fadd_rn(a, b); }
+__device__ __forceinline__ float  xsqrt(float a)           { return __fsqrt_rn(a); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsqrt(double a)          { return __dsqrt_rn(a); }
+
+template <typename A> __device__ __forceinline__ A pos_inf();
+template <> __device__ __forceinline__ float  pos_inf<float>()  { return __int_as_float(0x7f800000); }
+template <> __device__ __forceinline__ double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// one vector step of the sequential fold: sum += (q_j - p_j)^2 for the 4 (2) dims of a V
+__device__ __forceinline__ float fold(float acc, const float4& q, const float4& p) {
+    float t;
+    t = xsub(q.x, p.x); acc = xadd(acc, xmul(t, t));
+    t = xsub(q.y, p.y); acc = xadd(acc, xmul(t, t));
+    t = xsub(q.z, p.z); acc = xadd(acc, xmul(t, t));
+    t = xsub(q.w, p.w); acc = xadd(acc, xmul(t, t));
+    return acc;
+}
+__device__ __forceinline__ double fold(double acc, const double2& q, const double2& p) {
+    double t;
+    t = xsub(q.x, p.x); acc = xadd(acc, xmul(t, t));
+    t = xsub(q.y, p.y); acc = xadd(acc, xmul(t, t));
+    return acc;
+}
+
+__device__ __forceinline__ float4  vzero(float)  { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ double2 vzero(double) { return make_double2(0., 0.); }
+
+// Conservative squared-domain acceptance threshold: any s with sqrt_rn(s) <= kth satisfies
+// s <= thresh2(kth).  (All comparisons of the reference are on sqrt'd distances; the
+// cheap squared test only filters, the exact test runs on the sqrt'd value.)
+__device__ __forceinline__ float  thresh2(float kth)  { return xadd(xmul(xmul(kth, kth), 1.00000095367431640625f), FLT_MIN); }
+__device__ __forceinline__ double thresh2(double kth) { return xadd(xmul(xmul(kth, kth), 1.0 + 1.7763568394002505e-15), DBL_MIN); }
+
+// ---- flattened tree as seen by the device --------------------------------------------------
+template <typename A>
+struct DevTree {
+    const typename VT<A>::V* pts;  // n x dpad, bucket order
+    const uint32_t* ids;           // n
+    const uint32_t* bucket_lo;
+    const uint32_t* bucket_hi;
+    const typename VT<A>::V* centers;  // n_nodes x dpad
+    const A* radii;                // ball: radius (-1 empty) ; vp: mu
+    const uint32_t* vp_ids;        // vp only
+    uint32_t n, d, dpad, dv;       // dv = dpad / VT<A>::N
+    uint32_t L, n_internal, n_buckets, n_nodes;
+    int kind;
+    A slack;                       // (2d + 8) * unit roundoff: relative slack of a triangle bound
+};
+
+// ---- per-thread running top-k in registers (Neighbor + BinaryHeap, src/ball_tree.rs:378-423,
+// :109, :219-225), kept sorted ascending by (distance, index) ---------------------------------
+template <typename A, int K>
+struct TopK {
+    A kd[K];
+    uint32_t ki[K];
+    A kth;          // current k-th best distance (+inf until k candidates were seen)
+    uint32_t kth_i;
+    A t2;           // thresh2(kth)
+    A fd;           // floor key for multi-pass k > K: only keys > (fd, fi) are accepted
+    uint32_t fi;
+    bool has_floor;
+
+    __device__ __forceinline__ void init(bool active) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) { kd[i] = pos_inf<A>(); ki[i] = NO_ID; }
+        kth = pos_inf<A>(); kth_i = NO_ID;
+        t2 = active ? pos_inf<A>() : A(-1);
+        has_floor = false; fd = A(0); fi = 0;
+    }
+    __device__ __forceinline__ void set_floor(A d, uint32_t i) { has_floor = true; fd = d; fi = i; }
+
+    // exact test + insertion on the sqrt'd distance
+    __device__ __forceinline__ void offer(A d, uint32_t id, uint32_t k) {
+        if (has_floor && !(d > fd || (d == fd && id > fi))) return;
+        if (!(d < kth || (d == kth && id < kth_i))) return;
+#pragma unroll
+        for (int i = 0; i < K; ++i) if (i == (int)k - 1) { kd[i] = d; ki[i] = id; }
+#pragma unroll
+        for (int i = K - 1; i > 0; --i) {
+            bool sw = (kd[i] < kd[i - 1]) || (kd[i] == kd[i - 1] && ki[i] < ki[i - 1]);
+            if (sw) {
+                A td = kd[i]; kd[i] = kd[i - 1]; kd[i - 1] = td;
+                uint32_t ti = ki[i]; ki[i] = ki[i - 1]; ki[i - 1] = ti;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) if (i == (int)k - 1) { kth = kd[i]; kth_i = ki[i]; }
+        t2 = thresh2(kth);
+    }
+    __device__ __forceinline__ void offer_sq(A s, uint32_t id, uint32_t k) { offer(xsqrt(s), id, k); }
+};
+
+// ---- block-wide counts of up to four predicates with ONE barrier ---------------------------
+struct VoteBuf { uint32_t v[2][TQ / 32][4]; };
+__device__ __forceinline__ void block_counts(VoteBuf& vb, int& parity, bool a, bool b, bool c, bool d,
+                                             int& na, int& nb, int& nc, int& nd) {
+    const unsigned full = 0xffffffffu;
+    unsigned ba = __ballot_sync(full, a), bb = __ballot_sync(full, b);
+    unsigned bc = __ballot_sync(full, c), bd = __ballot_sync(full, d);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        vb.v[parity][warp][0] = __popc(ba); vb.v[parity][warp][1] = __popc(bb);
+        vb.v[parity][warp][2] = __popc(bc); vb.v[parity][warp][3] = __popc(bd);
+    }
+    __syncthreads();
+    na = nb = nc = nd = 0;
+#pragma unroll
+    for (int w = 0; w < TQ / 32; ++w) {
+        na += vb.v[parity][w][0]; nb += vb.v[parity][w][1];
+        nc += vb.v[parity][w][2]; nd += vb.v[parity][w][3];
+    }
+    parity ^= 1;
+}
+
+template <typename A>
+struct KnnArgs {
+    DevTree<A> t;
+    const typename VT<A>::V* q;  // nq x dpad, zero padded
+    const uint32_t* qorder;      // sorted slot -> query id (tile coherence), may be null
+    uint32_t nq, k;
+    uint32_t split_level;        // grid.y = 2^split_level subtrees scanned independently
+    A* part_d;                   // [n_splits][nq][k]
+    uint32_t* part_i;
+    const A* floor_d;            // optional [nq] floor keys (multi-pass k > K)
+    const uint32_t* floor_i;
+    unsigned long long* counters;  // [0] pairs, [1] node visits
+};
+
+// ---- the tile scan: one CTA = 128 queries (one per thread), DFS over the flattened tree with
+// block-uniform control flow, buckets staged through shared memory with 16-byte loads, every
+// lane folding RP independent point distances per step -------------------------------------
+template <typename A, int DVR, int K, int KIND>
+__global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
+    using V = typename VT<A>::V;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V* ps = reinterpret_cast<V*>(smem_raw);
+    V* qs = reinterpret_cast<V*>(smem_raw + TILE_BYTES);  // generic-d only: [dv][TQ]
+    __shared__ VoteBuf votes;
+    __shared__ unsigned long long s_pairs, s_visits;
+
+    const DevTree<A>& t = a.t;
+    const int tid = threadIdx.x;
+    const uint32_t slot = blockIdx.x * TQ + tid;
+    const bool active = slot < a.nq;
+    const uint32_t qid = active ? (a.qorder ? a.qorder[slot] : slot) : 0;
+    const int DV = DVR > 0 ? DVR : (int)t.dv;
+    const uint32_t k = a.k;
+    if (tid == 0) { s_pairs = 0; s_visits = 0; }
+
+    V qreg[DVR > 0 ? DVR : 1];
+    if (DVR > 0) {
+#pragma unroll
+        for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc)
+            qreg[jc] = active ? a.q[(size_t)qid * DV + jc] : vzero(A(0));
+    } else {
+        for (int jc = 0; jc < DV; ++jc) qs[jc * TQ + tid] = active ? a.q[(size_t)qid * DV + jc] : vzero(A(0));
+    }
+    __syncthreads();
+
+    TopK<A, K> topk;
+    topk.init(active);
+    if (a.floor_d && active) topk.set_floor(a.floor_d[qid], a.floor_i[qid]);
+
+    unsigned long long my_pairs = 0, my_visits = 0;
+    int parity = 0;
+
+    // squared fold distance from this thread's query to a row of `centers` / `pts` in global memory
+    auto dist_to = [&](const V* row) -> A {
+        A acc = A(0);
+        if (DVR > 0) {
+#pragma unroll
+            for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc) acc = fold(acc, qreg[jc], __ldg(row + jc));
+        } else {
+            for (int jc = 0; jc < DV; ++jc) acc = fold(acc, qs[jc * TQ + tid], __ldg(row + jc));
+        }
+        return xsqrt(acc);
+    };
+
+    // leaf loops src/ball_tree.rs:162-173, 217-226: all points of bucket b against all 128 queries
+    const int TP = max(RP, (int)(TILE_BYTES / (t.dpad * sizeof(A))) / RP * RP);
+    auto scan_bucket = [&](uint32_t b, bool need) {
+        const uint32_t lo = t.bucket_lo[b], hi = t.bucket_hi[b];
+        const bool warp_need = __any_sync(0xffffffffu, need);
+        for (uint32_t p0 = lo; p0 < hi; p0 += TP) {
+            const int np = min((int)(hi - p0), TP);
+            __syncthreads();
+            const V* src = t.pts + (size_t)p0 * DV;
+            for (int i = tid; i < np * DV; i += TQ) ps[i] = __ldg(src + i);
+            __syncthreads();
+            if (!warp_need) continue;
+            if (active) my_pairs += np;
+            for (int pp = 0; pp < np; pp += RP) {
+                A acc[RP];
+#pragma unroll
+                for (int r = 0; r < RP; ++r) acc[r] = A(0);
+                if (DVR > 0) {
+#pragma unroll
+                    for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc) {
+#pragma unroll
+                        for (int r = 0; r < RP; ++r) acc[r] = fold(acc[r], qreg[jc], ps[(pp + r) * DVR + jc]);
+                    }
+                } else {
+                    for (int jc = 0; jc < DV; ++jc) {
+                        const V qv = qs[jc * TQ + tid];
+#pragma unroll
+                        for (int r = 0; r < RP; ++r) acc[r] = fold(acc[r], qv, ps[(pp + r) * DV + jc]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    if (pp + r < np && acc[r] <= topk.t2)
+                        topk.offer_sq(acc[r], __ldg(t.ids + p0 + pp + r), k);
+                }
+            }
+        }
+    };
+
+    uint32_t stack[MAX_STACK];
+    int sp = 0;
+    const uint32_t root = ((1u << a.split_level) - 1u) + blockIdx.y;
+
+    if (KIND == 0) {
+        // ---- ball tree: prune a node for a query iff its conservative lower bound
+        // cd - R - slack*(cd+R) exceeds the query's current k-th distance (:212, strict) ----
+        stack[sp++] = root;
+        while (sp) {
+            const uint32_t node = stack[--sp];
+            ++my_visits;
+            if (node >= t.n_internal) {
+                const A R = t.radii[node];
+                if (R < A(0)) continue;  // empty
+                const A cd = dist_to(t.centers + (size_t)node * DV);
+                const A lb = xsub(xsub(cd, R), xmul(t.slack, xadd(cd, R)));
+                const bool need = active && !(lb > topk.kth);
+                if (!__syncthreads_or(need)) continue;
+                scan_bucket(node - t.n_internal, need);
+            } else {
+                const uint32_t c1 = 2 * node + 1, c2 = c1 + 1;
+                const A R1 = t.radii[c1], R2 = t.radii[c2];
+                A lb1 = pos_inf<A>(), lb2 = pos_inf<A>();
+                if (!(R1 < A(0))) { const A cd = dist_to(t.centers + (size_t)c1 * DV); lb1 = xsub(xsub(cd, R1), xmul(t.slack, xadd(cd, R1))); }
+                if (!(R2 < A(0))) { const A cd = dist_to(t.centers + (size_t)c2 * DV); lb2 = xsub(xsub(cd, R2), xmul(t.slack, xadd(cd, R2))); }
+                const bool need1 = active && !(R1 < A(0)) && !(lb1 > topk.kth);
+                const bool need2 = active && !(R2 < A(0)) && !(lb2 > topk.kth);
+                int n1, n2, npref, nany;
+                block_counts(votes, parity, need1, need2, (need1 || need2) && (lb1 < lb2), need1 || need2, n1, n2, npref, nany);
+                // nearer child first (:232-236), decided by the tile's majority
+                const bool first1 = 2 * npref >= nany;
+                const uint32_t first = first1 ? c1 : c2, second = first1 ? c2 : c1;
+                const int nfirst = first1 ? n1 : n2, nsecond = first1 ? n2 : n1;
+                if (nsecond) stack[sp++] = second;
+                if (nfirst) stack[sp++] = first;
+            }
+        }
+    } else {
+        // ---- vantage-point tree (search_node, src/vantage_point_tree.rs:100-130): the bound of a
+        // subtree is the max over its ancestors of |d(q,vp) - mu| on the far/near side ----
+        A lbs[MAX_STACK];
+        if (a.split_level > 0 && blockIdx.y == 0) {
+            // vantage points above the split level belong to no split's subtree
+            for (uint32_t node = 0; node < ((1u << a.split_level) - 1u); ++node) {
+                const A dq = dist_to(t.centers + (size_t)node * DV);
+                if (active) topk.offer(dq, t.vp_ids[node], k);
+            }
+        }
+        stack[sp] = root; lbs[sp] = A(0); ++sp;
+        while (sp) {
+            --sp;
+            const uint32_t node = stack[sp];
+            const A lb = lbs[sp];
+            ++my_visits;
+            const bool need = active && !(lb > topk.kth);
+            if (node >= t.n_internal) {
+                if (!__syncthreads_or(need)) continue;
+                scan_bucket(node - t.n_internal, need);
+            } else {
+                const A mu = t.radii[node];
+                const A dq = dist_to(t.centers + (size_t)node * DV);
+                if (need) topk.offer(dq, t.vp_ids[node], k);  // the vantage point is a data point (:106-109)
+                const A s = xmul(t.slack, xadd(dq, mu));
+                const A lbn = fmax(lb, xsub(xsub(dq, mu), s));   // near side: d(p,vp) <= mu
+                const A lbf = fmax(lb, xsub(xsub(mu, dq), s));   // far side:  d(p,vp) >= mu
+                const bool needn = active && !(lbn > topk.kth);
+                const bool needf = active && !(lbf > topk.kth);
+                int nn, nf, npref, nany;
+                block_counts(votes, parity, needn, needf, (needn || needf) && (dq < mu), needn || needf, nn, nf, npref, nany);
+                const bool near_first = 2 * npref >= nany;  // :111 `distance < radius` -> near first
+                const uint32_t cn = 2 * node + 1, cf = cn + 1;
+                if (near_first) {
+                    if (nf) { stack[sp] = cf; lbs[sp] = lbf; ++sp; }
+                    if (nn) { stack[sp] = cn; lbs[sp] = lbn; ++sp; }
+                } else {
+                    if (nn) { stack[sp] = cn; lbs[sp] = lbn; ++sp; }
+                    if (nf) { stack[sp] = cf; lbs[sp] = lbf; ++sp; }
+                }
+            }
+        }
+    }
+
+    if (active) {
+        const size_t base = ((size_t)blockIdx.y * a.nq + qid) * k;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            if (i < (int)k) { a.part_d[base + i] = topk.kd[i]; a.part_i[base + i] = topk.ki[i]; }
+        }
+    }
+    if (a.counters) {
+        atomicAdd(&s_pairs, my_pairs);
+        if (tid == 0) s_visits = my_visits;
+        __syncthreads();
+        if (tid == 0) { atomicAdd(&a.counters[0], s_pairs); atomicAdd(&a.counters[1], s_visits); }
+    }
+}
+
+// ---- k-way merge of sorted (distance, index) lists: split scans of one GPU, or the gathered
+// per-shard lists of several GPUs (K7 in SURVEY.md 2).  One thread per query. ---------------
+constexpr int MAX_LISTS = 256;
+template <typename A, typename I>
+__global__ void merge_lists_kernel(const A* __restrict__ in_d, const I* __restrict__ in_i, uint32_t n_lists,
+                                   uint32_t nq, uint32_t k, uint64_t* __restrict__ out_i, A* __restrict__ out_d,
+                                   uint32_t out_stride, uint32_t out_off, A* floor_d, uint32_t* floor_i) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const I none = (I)~(I)0;
+    A last_d = pos_inf<A>();
+    uint64_t last_i = ~0ull;
+    if (n_lists == 1) {
+        for (uint32_t i = 0; i < k; ++i) {
+            const A d = in_d[(size_t)q * k + i];
+            const I id = in_i[(size_t)q * k + i];
+            out_d[(size_t)q * out_stride + out_off + i] = d;
+            out_i[(size_t)q * out_stride + out_off + i] = id == none ? ~0ull : (uint64_t)id;
+            last_d = d; last_i = id == none ? ~0ull : (uint64_t)id;
+        }
+    } else {
+        uint16_t head[MAX_LISTS];
+        for (uint32_t l = 0; l < n_lists; ++l) head[l] = 0;
+        for (uint32_t i = 0; i < k; ++i) {
+            A bd = pos_inf<A>();
+            uint64_t bi = ~0ull;
+            int bl = -1;
+            for (uint32_t l = 0; l < n_lists; ++l) {
+                if (head[l] >= k) continue;
+                const size_t at = ((size_t)l * nq + q) * k + head[l];
+                const I id = in_i[at];
+                if (id == none) continue;
+                const A d = in_d[at];
+                if (bl < 0 || d < bd || (d == bd && (uint64_t)id < bi)) { bd = d; bi = (uint64_t)id; bl = (int)l; }
+            }
+            if (bl >= 0) ++head[bl];
+            out_d[(size_t)q * out_stride + out_off + i] = bd;
+            out_i[(size_t)q * out_stride + out_off + i] = bi;
+            last_d = bd; last_i = bi;
+        }
+    }
+    if (floor_d && k > 0) { floor_d[q] = last_d; floor_i[q] = last_i == ~0ull ? NO_ID : (uint32_t)last_i; }
+}
+
+// ---- query staging ----------------------------------------------------------------------------
+template <typename A>
+__global__ void pad_queries_kernel(const A* __restrict__ q, size_t q_stride, uint32_t nq, uint32_t d, uint32_t dpad,
+                                   A* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nq * dpad) return;
+    const uint32_t r = (uint32_t)(i / dpad), c = (uint32_t)(i % dpad);
+    out[i] = c < d ? q[(size_t)r * q_stride + c] : A(0);
+}
+
+// home bucket of each query: greedy descent (nearer centroid / near-far side of mu).  Only used
+// to sort queries so that the 128 queries of a tile visit the same buckets.
+template <typename A>
+__global__ void home_bucket_kernel(const DevTree<A> t, const typename VT<A>::V* __restrict__ q, uint32_t nq,
+                                   uint32_t* __restrict__ home, uint32_t* __restrict__ hist) {
+    using V = typename VT<A>::V;
+    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const V* qr = q + (size_t)qi * t.dv;
+    auto dist_to = [&](const V* row) {
+        A acc = A(0);
+        for (uint32_t jc = 0; jc < t.dv; ++jc) acc = fold(acc, qr[jc], __ldg(row + jc));
+        return acc;
+    };
+    uint32_t node = 0;
+    while (node < t.n_internal) {
+        const uint32_t c1 = 2 * node + 1, c2 = c1 + 1;
+        if (t.kind == 0) {
+            const A R1 = t.radii[c1], R2 = t.radii[c2];
+            if (R1 < A(0)) { node = c2; continue; }
+            if (R2 < A(0)) { node = c1; continue; }
+            node = dist_to(t.centers + (size_t)c1 * t.dv) <= dist_to(t.centers + (size_t)c2 * t.dv) ? c1 : c2;
+        } else {
+            const A mu = t.radii[node];
+            node = xsqrt(dist_to(t.centers + (size_t)node * t.dv)) < mu ? c1 : c2;
+        }
+    }
+    const uint32_t b = node - t.n_internal;
+    home[qi] = b;
+    atomicAdd(&hist[b], 1u);
+}
+
+// exclusive scan of n uint32 counters by a single block (n <= a few million)
+__global__ void exclusive_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n) {
+    __shared__ uint32_t sums[1024];
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t chunk = (n + nt - 1) / nt;
+    const uint32_t b = min(n, tid * chunk), e = min(n, b + chunk);
+    uint32_t s = 0;
+    for (uint32_t i = b; i < e; ++i) s += in[i];
+    sums[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < nt; ++i) { uint32_t v = sums[i]; sums[i] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t run = sums[tid];
+    for (uint32_t i = b; i < e; ++i) { uint32_t v = in[i]; out[i] = run; run += v; }
+}
+
+__global__ void scatter_order_kernel(const uint32_t* __restrict__ home, uint32_t* __restrict__ cursor, uint32_t nq,
+                                     uint32_t* __restrict__ qorder) {
+    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const uint32_t pos = atomicAdd(&cursor[home[qi]], 1u);
+    qorder[pos] = qi;
+}
+
+// ---- radius search: one warp per query, lanes over the points of a bucket, hits compacted with
+// __ballot_sync + popc prefix (neighbors_within_radius_in_subtree, src/ball_tree.rs:250-294).
+// Contract: index i is reported iff the bit-exact distance is < r (strict, :277).
+// A node is skipped when its conservative lower bound is >= r and taken whole, without per-point
+// tests (:271-273), when its conservative upper bound is < r.  Pass 1 (out == null) counts,
+// pass 2 writes at offsets[q]. ---------------------------------------------------------------
+template <typename A>
+__global__ void radius_kernel(const DevTree<A> t, const typename VT<A>::V* __restrict__ q, uint32_t nq, A r,
+                              uint32_t* __restrict__ counts, const uint64_t* __restrict__ offsets,
+                              uint64_t* __restrict__ out, unsigned long long* counters) {
+    using V = typename VT<A>::V;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint32_t qi = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const V* qr = q + (size_t)qi * t.dv;
+    auto dist_to = [&](const V* row) {
+        A acc = A(0);
+        for (uint32_t jc = 0; jc < t.dv; ++jc) acc = fold(acc, __ldg(qr + jc), __ldg(row + jc));
+        return xsqrt(acc);
+    };
+    uint64_t base = out ? offsets[qi] : 0;
+    uint32_t count = 0;
+    unsigned long long pairs = 0;
+    uint32_t stack[MAX_STACK];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        const uint32_t node = stack[--sp];
+        const A R = t.radii[node];
+        if (R < A(0)) continue;
+        const A cd = dist_to(t.centers + (size_t)node * t.dv);  // warp-uniform
+        const A s = xmul(t.slack, xadd(cd, R));
+        const A lb = xsub(xsub(cd, R), s), ub = xadd(xadd(cd, R), s);
+        if (lb >= r) continue;
+        // leaf-bucket span of this node in the implicit complete tree
+        uint32_t first = node, last = node;
+        while (first < t.n_internal) { first = 2 * first + 1; last = 2 * last + 2; }
+        const uint32_t lo = t.bucket_lo[first - t.n_internal], hi = t.bucket_hi[last - t.n_internal];
+        if (ub < r) {  // whole node inside the ball
+            if (out) for (uint32_t p = lo + lane; p < hi; p += 32) out[base + count + (p - lo)] = t.ids[p];
+            count += hi - lo;
+        } else if (node >= t.n_internal) {
+            for (uint32_t p0 = lo; p0 < hi; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                bool hit = false;
+                if (p < hi) hit = dist_to(t.pts + (size_t)p * t.dv) < r;
+                const unsigned m = __ballot_sync(full, hit);
+                if (out && hit) out[base + count + __popc(m & ((1u << lane) - 1u))] = t.ids[p];
+                count += __popc(m);
+            }
+            pairs += hi - lo;
+        } else {
+            stack[sp++] = 2 * node + 1;  // :284-285
+            stack[sp++] = 2 * node + 2;
+        }
+    }
+    if (!out && lane == 0) counts[qi] = count;
+    if (counters && lane == 0 && !out) atomicAdd(&counters[0], pairs);
+}
+
+// u32 counts -> u64 exclusive offsets (single block)
+__global__ void offsets_scan_kernel(const uint32_t* __restrict__ counts, uint64_t* __restrict__ offsets, uint32_t n) {
+    __shared__ unsigned long long sums[1024];
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t chunk = (n + nt - 1) / nt;
+    const uint32_t b = min(n, tid * chunk), e = min(n, b + chunk);
+    unsigned long long s = 0;
+    for (uint32_t i = b; i < e; ++i) s += counts[i];
+    sums[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (uint32_t i = 0; i < nt; ++i) { unsigned long long v = sums[i]; sums[i] = run; run += v; }
+        offsets[n] = run;
+    }
+    __syncthreads();
+    unsigned long long run = sums[tid];
+    for (uint32_t i = b; i < e; ++i) { unsigned long long v = counts[i]; offsets[i] = run; run += v; }
+}
+
+// ascending sort of each query's hit list: one warp per segment, bitonic network over the
+// segment padded to a power of two with +inf keys (the reference's order is unspecified DFS
+// order and its tests sort before comparing, src/ball_tree.rs:667, 777)
+__global__ void segment_sort_kernel(const uint64_t* __restrict__ offsets, uint64_t* __restrict__ vals, uint32_t nq) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const uint64_t lo = offsets[qi];
+    const uint32_t n = (uint32_t)(offsets[qi + 1] - lo);
+    if (n < 2) return;
+    uint64_t* v = vals + lo;
+    uint32_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    // all-ascending form of the bitonic network (first step of each phase mirrors, i ^ (size-1)):
+    // every compare-exchange moves the smaller key down, so the virtual +inf keys at >= n never move
+    auto cmpx = [&](uint32_t i, uint32_t j) {
+        if (j > i && j < n) {
+            const uint64_t x = v[i], y = v[j];
+            if (x > y) { v[i] = y; v[j] = x; }
+        }
+    };
+    for (uint32_t size = 2; size <= np2; size <<= 1) {
+        for (uint32_t i = lane; i < np2; i += 32) cmpx(i, i ^ (size - 1));
+        __syncwarp();
+        for (uint32_t stride = size >> 2; stride > 0; stride >>= 1) {
+            for (uint32_t i = lane; i < np2; i += 32) cmpx(i, i ^ stride);
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace petal
