@@ -150,7 +150,7 @@ struct Engine final : pn_tree {
     int launch_knn_t(const KnnArgs<A>& a, dim3 grid, cudaStream_t st) {
         size_t smem = TILE_BYTES + (DVR == 0 ? (size_t)TQ * ft.dpad * sizeof(A) : 0);
         auto kern = knn_tile_kernel<A, DVR, K, KIND>;
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, TQ, smem, st>>>(a);
         CU(cudaGetLastError());
         return PN_OK;
