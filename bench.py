@@ -223,7 +223,8 @@ def main():
                                  host_threads=max(1, ncpu // max(world, 1)))
     info = tree.info()
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # explicit (non-default) stream: handle 0 would mean "the tree's own stream"
+    torch.cuda.set_stream(stream)
     q_dev = torch.from_numpy(Q).cuda()
     idx_dev = torch.empty((nq, k), dtype=torch.int64, device="cuda")
     dist_dev = torch.empty((nq, k), dtype=tdtype, device="cuda")
