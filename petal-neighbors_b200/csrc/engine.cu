@@ -12,6 +12,7 @@
 #include "../../include/petal_b200.h"
 #include "flat_tree.hpp"
 #include "kernels.cuh"
+#include "tc_filter.cuh"
 
 namespace petal {
 
@@ -97,13 +98,20 @@ struct Engine final : pn_tree {
     DevBuf w_qraw, w_q, w_home, w_hist, w_cursor, w_order, w_part_d, w_part_i, w_floor_d, w_floor_i,
         w_counters, w_out_i, w_out_d, w_counts, w_offsets, w_hits;
     DevTree<A> dt{};
+    // tensor path (f32 only): augmented TF32 operands, see tc_filter.cuh
+    DevBuf d_baug, d_center, w_aaug, w_qmargin;
+    bool tensor_ready = false, last_used_tensor = false;
+    uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
+    float pmax = 0.f;      // max |p - center|
+    uint32_t algo = PN_ALGO_AUTO;
+    alignas(64) CUtensorMap map_b;
 
     ~Engine() override {
         if (!host_only) {
             DeviceGuard g(device);
             for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &w_qraw, &w_q, &w_home,
                               &w_hist, &w_cursor, &w_order, &w_part_d, &w_part_i, &w_floor_d, &w_floor_i, &w_counters,
-                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits})
+                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             if (stream) cudaStreamDestroy(stream);
@@ -129,8 +137,9 @@ struct Engine final : pn_tree {
         TRY(up(d_radii, ft.radii.data(), ft.radii.size() * sizeof(A)));
         TRY(up(d_vpids, ft.vp_ids.data(), ft.vp_ids.size() * 4));
         info.device_bytes = d_pts.cap + d_ids.cap + d_blo.cap + d_bhi.cap + d_centers.cap + d_radii.cap + d_vpids.cap;
-        std::vector<A>().swap(ft.pts);  // the device copy is the point store from here on
         fill_dev_tree();
+        TRY(prepare_tensor());
+        std::vector<A>().swap(ft.pts);  // the device copy is the point store from here on
         return PN_OK;
     }
 
@@ -170,6 +179,135 @@ struct Engine final : pn_tree {
         return k1 ? launch_knn_k<1, 1>(a, grid, st) : launch_knn_k<16, 1>(a, grid, st);
     }
 
+
+    // ------------------------------------------------------------------------------------------
+    // tensor path set-up (f32, d >= 8 worth of contraction): centred, augmented B operand + its TMA map
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn encode_fn() {
+        static EncodeTiledFn fn = [] {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
+            return (EncodeTiledFn)p;
+        }();
+        return fn;
+    }
+    int make_map(CUtensorMap* m, void* base, uint64_t rows) {
+        EncodeTiledFn fn = encode_fn();
+        if (!fn) return fail(PN_CUDA, "cuTensorMapEncodeTiled entry point not found");
+        cuuint64_t dims[2] = {kp, rows};
+        cuuint64_t strides[1] = {(cuuint64_t)kp * 4};
+        cuuint32_t box[2] = {(cuuint32_t)tc::KC, (cuuint32_t)tc::BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(PN_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+        return PN_OK;
+    }
+    bool tensor_eligible() const { return sizeof(A) == 4 && algo != PN_ALGO_SIMT && (algo == PN_ALGO_TENSOR || ft.d >= 16); }
+    int prepare_tensor() {
+        if constexpr (sizeof(A) == 4) {
+            if (!tensor_eligible()) return PN_OK;
+            kp = (ft.d + 4 + tc::KC - 1) / tc::KC * tc::KC;
+            // centre = mean of the stored points (double accumulation on the host)
+            std::vector<double> mean(ft.dpad, 0.0);
+            for (size_t i = 0; i < ft.n; ++i)
+                for (uint32_t j = 0; j < ft.d; ++j) mean[j] += (double)ft.pts[i * ft.dpad + j];
+            std::vector<float> c(ft.dpad, 0.f);
+            for (uint32_t j = 0; j < ft.d; ++j) c[j] = (float)(mean[j] / (double)ft.n);
+            TRY(d_center.ensure(ft.dpad * 4));
+            CU(cudaMemcpy(d_center.p, c.data(), ft.dpad * 4, cudaMemcpyHostToDevice));
+            TRY(d_baug.ensure((size_t)ft.n * kp * 4));
+            TRY(w_counters.ensure(32));
+            CU(cudaMemset(w_counters.p, 0, 32));
+            tc::build_baug_kernel<<<(unsigned)((ft.n + 127) / 128), 128, 0, stream>>>(d_pts.as<float>(), d_center.as<float>(), (uint32_t)ft.n, ft.d,
+                                                                                     ft.dpad, kp, d_baug.as<float>(), w_counters.as<unsigned int>());
+            CU(cudaGetLastError());
+            unsigned int bits = 0;
+            CU(cudaMemcpyAsync(&bits, w_counters.p, 4, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            memcpy(&pmax, &bits, 4);
+            TRY(make_map(&map_b, d_baug.p, ft.n));
+            info.device_bytes += d_baug.cap;
+            tensor_ready = true;
+        }
+        return PN_OK;
+    }
+
+    template <int DVR, int K, int MT>
+    int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
+        const size_t smem = 1024 + (size_t)(MT * fa.nkc + fa.stages) * tc::CHUNK_BYTES + 256;
+        auto kern = tc::knn_filter_kernel<DVR, K, MT>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (fa.nq + MT * tc::BM - 1) / (MT * tc::BM);
+        kern<<<grid, (4 * MT + 2) * 32, smem, st>>>(map_a, map_b, fa);
+        CU(cudaGetLastError());
+        return PN_OK;
+    }
+    template <int K>
+    int launch_filter_k(const CUtensorMap& map_a, tc::FilterArgs& fa, cudaStream_t st) {
+        const int mt = fa.nkc <= 3 ? 2 : 1;
+        const size_t budget = 220 * 1024;
+        fa.stages = (uint32_t)std::min<size_t>(8, (budget - 1280 - (size_t)mt * fa.nkc * tc::CHUNK_BYTES) / tc::CHUNK_BYTES);
+        if (mt == 2) {
+            if (dt.dv == 4) return launch_filter_t<4, K, 2>(map_a, fa, st);
+            if (dt.dv == 8) return launch_filter_t<8, K, 2>(map_a, fa, st);
+            return launch_filter_t<0, K, 2>(map_a, fa, st);
+        }
+        return launch_filter_t<0, K, 1>(map_a, fa, st);
+    }
+
+    // tensor k-NN: same contract as knn_device
+    int knn_device_tensor(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st) {
+        if constexpr (sizeof(A) == 4) {
+            TRY(stage_queries(qraw, nq, stride, st, false));
+            TRY(w_aaug.ensure((size_t)nq * kp * 4));
+            TRY(w_qmargin.ensure((size_t)nq * 4));
+            const bool k1 = (k == 1);
+            const uint32_t KP = k1 ? 1 : 16;
+            const uint32_t n_pass = (k + KP - 1) / KP;
+            TRY(w_part_d.ensure((size_t)nq * KP * 4));
+            TRY(w_part_i.ensure((size_t)nq * KP * 4));
+            TRY(w_counters.ensure(32));
+            if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * 4)); TRY(w_floor_i.ensure((size_t)nq * 4)); }
+            CU(cudaMemsetAsync(w_counters.p, 0, 32, st));
+            tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(w_q.as<float>(), d_center.as<float>(), nq, ft.d, ft.dpad, kp, pmax,
+                                                                    w_aaug.as<float>(), w_qmargin.as<float>());
+            CU(cudaGetLastError());
+            ++counters.kernel_launches;
+            alignas(64) CUtensorMap map_a;
+            TRY(make_map(&map_a, w_aaug.p, nq));
+            CU(cudaEventRecord(ev[2], st));
+            for (uint32_t p = 0; p < n_pass; ++p) {
+                const uint32_t kk = std::min(KP, k - p * KP);
+                tc::FilterArgs fa{};
+                fa.t = *reinterpret_cast<DevTree<float>*>(&dt);
+                fa.q = w_q.as<float4>(); fa.q_margin = w_qmargin.as<float>();
+                fa.nq = nq; fa.k = kk;
+                fa.n_tiles = (uint32_t)((ft.n + tc::BN - 1) / tc::BN);
+                fa.nkc = kp / tc::KC;
+                fa.t2_scale = 1.0f + (float)(ft.d + 4) * 1.1920928955078125e-07f;
+                fa.part_d = w_part_d.as<float>(); fa.part_i = w_part_i.as<uint32_t>();
+                fa.floor_d = p ? w_floor_d.as<float>() : nullptr; fa.floor_i = p ? w_floor_i.as<uint32_t>() : nullptr;
+                fa.counters = w_counters.as<unsigned long long>();
+                TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
+                merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
+                    w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, nq, kk, idx_out, dist_out, k, p * KP,
+                    n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr);
+                CU(cudaGetLastError());
+                counters.kernel_launches += 2;
+                counters.filter_pairs += (uint64_t)ft.n * nq;
+            }
+            CU(cudaEventRecord(ev[3], st));
+            return PN_OK;
+        } else {
+            (void)qraw; (void)nq; (void)stride; (void)k; (void)idx_out; (void)dist_out; (void)st;
+            return fail(PN_BAD_ARG, "the tensor path is f32 only");
+        }
+    }
+
     int use_stream(cudaStream_t st) {
         if (last_stream && last_stream != st) CU(cudaStreamSynchronize(last_stream));
         last_stream = st;
@@ -201,6 +339,8 @@ struct Engine final : pn_tree {
 
     // k-NN for nq queries whose raw rows are already on the device; results to device buffers
     int knn_device(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st) {
+        last_used_tensor = tensor_ready && (algo == PN_ALGO_TENSOR || nq >= 2048);
+        if (last_used_tensor) return knn_device_tensor(qraw, nq, stride, k, idx_out, dist_out, st);
         const bool sort = ft.n_buckets > 1 && nq > (uint32_t)TQ;
         TRY(stage_queries(qraw, nq, stride, st, sort));
         const uint32_t tiles = (nq + TQ - 1) / TQ;
@@ -212,9 +352,9 @@ struct Engine final : pn_tree {
         const uint32_t n_pass = (k + KP - 1) / KP;
         TRY(w_part_d.ensure((size_t)n_splits * nq * KP * sizeof(A)));
         TRY(w_part_i.ensure((size_t)n_splits * nq * KP * 4));
-        TRY(w_counters.ensure(16));
+        TRY(w_counters.ensure(32));
         if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * sizeof(A))); TRY(w_floor_i.ensure((size_t)nq * 4)); }
-        CU(cudaMemsetAsync(w_counters.p, 0, 16, st));
+        CU(cudaMemsetAsync(w_counters.p, 0, 32, st));
         CU(cudaEventRecord(ev[2], st));
         for (uint32_t p = 0; p < n_pass; ++p) {
             const uint32_t kk = std::min(KP, k - p * KP);
@@ -236,12 +376,13 @@ struct Engine final : pn_tree {
     }
 
     int fetch_counters(cudaStream_t st, uint64_t nq) {
-        unsigned long long c[2] = {0, 0};
-        CU(cudaMemcpyAsync(c, w_counters.p, 16, cudaMemcpyDeviceToHost, st));
+        unsigned long long c[4] = {0, 0, 0, 0};
+        CU(cudaMemcpyAsync(c, w_counters.p, 32, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         counters.queries = nq;
-        counters.pairs = c[0];
+        counters.pairs = last_used_tensor ? counters.filter_pairs : c[0];
         counters.node_visits = c[1];
+        counters.rerank_pairs = c[2];
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) counters.device_ms = ms; else (void)cudaGetLastError();
         if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) counters.scan_ms = ms; else (void)cudaGetLastError();
@@ -330,8 +471,9 @@ struct Engine final : pn_tree {
         if (cudaEventRecord(ev[0], st) != cudaSuccess) return bail(fail(PN_CUDA, "cudaEventRecord"));
 #define CUB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(fail(PN_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_))); } while (0)
 #define TRYB(x) do { int r_ = (x); if (r_ != PN_OK) return bail(r_); } while (0)
-        TRYB(w_counters.ensure(16));
-        CUB(cudaMemsetAsync(w_counters.p, 0, 16, st));
+        last_used_tensor = false;
+        TRYB(w_counters.ensure(32));
+        CUB(cudaMemsetAsync(w_counters.p, 0, 32, st));
         for (size_t q0 = 0; q0 < nq; q0 += chunk) {
             const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
             TRYB(w_qraw.ensure((size_t)cq * ft.d * sizeof(A)));
@@ -461,6 +603,7 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
         }
         e->device = dev;
         inf.device = dev;
+        e->algo = o.algo;
         TRY(e->upload());
     }
     inf.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -1,0 +1,103 @@
+"""Parity of the tensor path (tcgen05 TF32 filter + exact rerank, csrc/tc_filter.cuh) against the
+oracle: the filter may only ever ADD candidates, the rerank is the exact fold, so indices must be
+identical (ties by index) and distances bit-identical, exactly as for the SIMT path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pn():
+    import petal_neighbors_b200 as pn
+    return pn
+
+
+def bits(a):
+    return a.view(np.uint32)
+
+
+def check(pn, oracle, pts, Q, k, **opts):
+    bt = pn.BallTree.euclidean(pts, algo=pn.PN_ALGO_TENSOR, **opts)
+    idx, dist = bt.query_batch(Q, k)
+    oi, od = oracle.brute_knn(pts, Q, k)
+    bad = np.argwhere(idx != oi.astype(np.uint64))
+    assert bad.size == 0, f"index mismatch at {bad[:5]} got {idx[tuple(bad[0])]} want {oi[tuple(bad[0])]}"
+    assert np.array_equal(bits(dist), bits(od)), "distances are not bit-identical"
+    c = bt.counters()
+    assert c["filter_pairs"] == pts.shape[0] * Q.shape[0] * max(1, -(-k // 16))
+    assert c["rerank_pairs"] >= min(k, pts.shape[0]) * Q.shape[0] // 2
+    return bt, c
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (1000, 16, 300, 10),       # DVR=4, MT=2, one K chunk
+    (128, 16, 256, 10),        # exactly one tile
+    (5000, 16, 1000, 1),       # K=1 kernel
+    (4097, 20, 513, 16),       # DVR=8
+    (3000, 32, 257, 10),       # d = 32 -> Kp = 64, two K chunks
+    (6000, 64, 300, 10),       # generic query path, three K chunks, MT=2
+    (4000, 100, 200, 10),      # Kp = 128 -> MT=1
+    (3000, 128, 130, 10),      # Kp = 160, five K chunks
+    (2000, 3, 100, 10),        # forced tensor at tiny d
+    (3000, 16, 200, 40),       # multi-pass k > 16
+    (50, 16, 10, 10),          # n < one tile
+    (7, 16, 3, 10),            # k > n: padded rows
+    (20000, 16, 5000, 10),
+])
+def test_tensor_knn_random(pn, oracle, n, d, nq, k):
+    from petal_neighbors_b200 import synth
+    pts = synth.uniform(n, d, 51 + n + d, np.float32)
+    Q = synth.uniform(nq, d, 52 + n + d, np.float32)
+    check(pn, oracle, pts, Q, k)
+
+
+def test_tensor_ties_and_duplicates(pn, oracle):
+    rng = np.random.default_rng(17)
+    pts = rng.integers(0, 4, size=(5000, 16)).astype(np.float32)
+    Q = rng.integers(0, 4, size=(300, 16)).astype(np.float32)
+    for k in (1, 10, 16):
+        check(pn, oracle, pts, Q, k)
+    pts = np.ones((1000, 16), np.float32)
+    check(pn, oracle, pts, pts[:50] + np.float32(0.5), 10)
+    check(pn, oracle, pts, pts[:50], 10)        # all distances exactly zero
+
+
+def test_tensor_clustered_offset_and_far_queries(pn, oracle):
+    """Data far from the origin (centring matters), tight clusters (tiny distances vs large norms),
+    and queries far outside the data (large |q'|: the margin grows, the answer must not change)."""
+    from petal_neighbors_b200 import synth
+    pts = synth.gaussian_mixture(8000, 32, 5, n_centers=16, sigma=0.01, dtype=np.float32) + np.float32(100.0)
+    Q = synth.gaussian_mixture(400, 32, 6, n_centers=16, sigma=0.01, dtype=np.float32) + np.float32(100.0)
+    check(pn, oracle, pts, Q, 10)
+    Qfar = Q * np.float32(3.0)
+    check(pn, oracle, pts, Qfar, 5)
+    pts2 = synth.uniform(4000, 16, 1, np.float32) * np.float32(1e-3) + np.float32(7.0)
+    check(pn, oracle, pts2, pts2[:300], 10)     # self-queries: first neighbour at distance 0
+
+
+def test_tensor_auto_selection(pn, oracle):
+    from petal_neighbors_b200 import synth
+    pts = synth.uniform(30000, 16, 2, np.float32)
+    Q = synth.uniform(4096, 16, 3, np.float32)
+    bt = pn.BallTree.euclidean(pts)             # AUTO: f32, d >= 16, nq >= 2048 -> tensor
+    idx, dist = bt.query_batch(Q, 10)
+    assert bt.counters()["filter_pairs"] == 30000 * 4096
+    oi, od = oracle.brute_knn(pts, Q, 10)
+    assert np.array_equal(idx, oi.astype(np.uint64)) and np.array_equal(bits(dist), bits(od))
+    idx, dist = bt.query_batch(Q[:100], 10)     # small batch -> pruned SIMT scan
+    assert bt.counters()["filter_pairs"] == 0
+    assert np.array_equal(idx, oi[:100].astype(np.uint64))
+    bs = pn.BallTree.euclidean(pts, algo=pn.PN_ALGO_SIMT)
+    idx2, dist2 = bs.query_batch(Q, 10)
+    assert bs.counters()["filter_pairs"] == 0 and np.array_equal(idx2, oi.astype(np.uint64))
+
+
+def test_tensor_vp_tree(pn, oracle):
+    from petal_neighbors_b200 import synth
+    pts = synth.gaussian_mixture(20000, 64, 5, n_centers=32, dtype=np.float32)
+    Q = synth.gaussian_mixture(3000, 64, 6, n_centers=32, dtype=np.float32)
+    vp = pn.VantagePointTree.euclidean(pts, algo=pn.PN_ALGO_TENSOR)
+    vi, vd = vp.query_nearest_batch(Q)
+    oi, od = oracle.brute_knn(pts, Q, 1)
+    assert np.array_equal(vi, oi[:, 0].astype(np.uint64)) and np.array_equal(bits(vd), bits(od[:, 0]))
