@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--bucket", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--queries", type=int, default=0, help="override queries per GPU (profiling runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -212,6 +213,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = args.workload
+    if args.queries:
+        w = list(WORKLOADS[wl]); w[2] = args.queries; w[6] += f" [REDUCED to {args.queries} queries: profiling run, not a bench line]"
+        WORKLOADS[wl] = tuple(w)
     n, d, nq, k, dtype, gen, label = WORKLOADS[wl]
     s = np.dtype(dtype).itemsize
     tdtype = torch.float32 if dtype == np.float32 else torch.float64

@@ -238,7 +238,7 @@ struct Engine final : pn_tree {
 
     template <int DVR, int K, int MT>
     int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
-        const size_t smem = 1024 + (size_t)(MT * fa.nkc + fa.stages) * tc::CHUNK_BYTES + 256;
+        const size_t smem = 1024 + (size_t)(MT * fa.nkc + fa.stages) * tc::CHUNK_BYTES + 512 + (size_t)4 * MT * (64 * 4 + 64);
         auto kern = tc::knn_filter_kernel<DVR, K, MT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (fa.nq + MT * tc::BM - 1) / (MT * tc::BM);
@@ -250,7 +250,7 @@ struct Engine final : pn_tree {
     int launch_filter_k(const CUtensorMap& map_a, tc::FilterArgs& fa, cudaStream_t st) {
         const int mt = fa.nkc <= 3 ? 2 : 1;
         const size_t budget = 220 * 1024;
-        fa.stages = (uint32_t)std::min<size_t>(8, (budget - 1280 - (size_t)mt * fa.nkc * tc::CHUNK_BYTES) / tc::CHUNK_BYTES);
+        fa.stages = (uint32_t)std::min<size_t>(8, (budget - 4608 - (size_t)mt * fa.nkc * tc::CHUNK_BYTES) / tc::CHUNK_BYTES);
         if (mt == 2) {
             if (dt.dv == 4) return launch_filter_t<4, K, 2>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 2>(map_a, fa, st);

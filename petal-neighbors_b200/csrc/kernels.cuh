@@ -83,46 +83,55 @@ struct DevTree {
 };
 
 // ---- per-thread running top-k in registers (Neighbor + BinaryHeap, src/ball_tree.rs:378-423,
-// :109, :219-225), kept sorted ascending by (distance, index) ---------------------------------
+// :109, :219-225), kept sorted ascending by (distance, index).  The list always has K slots; for
+// k < K the first K-k slots hold (-inf, 0) sentinels that nothing can displace, so the current
+// k-th best is ALWAYS slot K-1 and every register index is static (a runtime slot index would
+// push the arrays to local memory).  Results are slots [K-k, K). ------------------------------
 template <typename A, int K>
 struct TopK {
     A kd[K];
     uint32_t ki[K];
-    A kth;          // current k-th best distance (+inf until k candidates were seen)
-    uint32_t kth_i;
-    A t2;           // thresh2(kth)
+    A t2;           // thresh2(kth): squared-domain acceptance filter
     A fd;           // floor key for multi-pass k > K: only keys > (fd, fi) are accepted
     uint32_t fi;
     bool has_floor;
 
-    __device__ __forceinline__ void init(bool active) {
+    __device__ __forceinline__ A kth() const { return kd[K - 1]; }
+
+    __device__ __forceinline__ void init(bool active, uint32_t k) {
 #pragma unroll
-        for (int i = 0; i < K; ++i) { kd[i] = pos_inf<A>(); ki[i] = NO_ID; }
-        kth = pos_inf<A>(); kth_i = NO_ID;
+        for (int i = 0; i < K; ++i) {
+            const bool real = i >= K - (int)k;
+            kd[i] = real ? pos_inf<A>() : -pos_inf<A>();
+            ki[i] = real ? NO_ID : 0u;
+        }
         t2 = active ? pos_inf<A>() : A(-1);
         has_floor = false; fd = A(0); fi = 0;
     }
     __device__ __forceinline__ void set_floor(A d, uint32_t i) { has_floor = true; fd = d; fi = i; }
 
     // exact test + insertion on the sqrt'd distance
-    __device__ __forceinline__ void offer(A d, uint32_t id, uint32_t k) {
+    __device__ __forceinline__ void offer(A d, uint32_t id) {
         if (has_floor && !(d > fd || (d == fd && id > fi))) return;
-        if (!(d < kth || (d == kth && id < kth_i))) return;
-#pragma unroll
-        for (int i = 0; i < K; ++i) if (i == (int)k - 1) { kd[i] = d; ki[i] = id; }
+        if (!(d < kd[K - 1] || (d == kd[K - 1] && id < ki[K - 1]))) return;
+        kd[K - 1] = d; ki[K - 1] = id;
 #pragma unroll
         for (int i = K - 1; i > 0; --i) {
-            bool sw = (kd[i] < kd[i - 1]) || (kd[i] == kd[i - 1] && ki[i] < ki[i - 1]);
-            if (sw) {
-                A td = kd[i]; kd[i] = kd[i - 1]; kd[i - 1] = td;
-                uint32_t ti = ki[i]; ki[i] = ki[i - 1]; ki[i - 1] = ti;
-            }
+            const bool sw = (kd[i] < kd[i - 1]) || (kd[i] == kd[i - 1] && ki[i] < ki[i - 1]);
+            const A lo_d = sw ? kd[i] : kd[i - 1], hi_d = sw ? kd[i - 1] : kd[i];
+            const uint32_t lo_i = sw ? ki[i] : ki[i - 1], hi_i = sw ? ki[i - 1] : ki[i];
+            kd[i - 1] = lo_d; kd[i] = hi_d; ki[i - 1] = lo_i; ki[i] = hi_i;
         }
-#pragma unroll
-        for (int i = 0; i < K; ++i) if (i == (int)k - 1) { kth = kd[i]; kth_i = ki[i]; }
-        t2 = thresh2(kth);
+        t2 = thresh2(kd[K - 1]);
     }
-    __device__ __forceinline__ void offer_sq(A s, uint32_t id, uint32_t k) { offer(xsqrt(s), id, k); }
+    __device__ __forceinline__ void offer_sq(A s, uint32_t id) { offer(xsqrt(s), id); }
+
+    // results: slot K-k+i -> out[i]
+    __device__ __forceinline__ void store(A* out_d, uint32_t* out_i, uint32_t k) const {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+            if (i >= K - (int)k) { out_d[i - (K - (int)k)] = kd[i]; out_i[i - (K - (int)k)] = ki[i]; }
+    }
 };
 
 // ---- block-wide counts of up to four predicates with ONE barrier ---------------------------
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
     __syncthreads();
 
     TopK<A, K> topk;
-    topk.init(active);
+    topk.init(active, k);
     if (a.floor_d && active) topk.set_floor(a.floor_d[qid], a.floor_i[qid]);
 
     unsigned long long my_pairs = 0, my_visits = 0;
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
 #pragma unroll
                 for (int r = 0; r < RP; ++r) {
                     if (pp + r < np && acc[r] <= topk.t2)
-                        topk.offer_sq(acc[r], __ldg(t.ids + p0 + pp + r), k);
+                        topk.offer_sq(acc[r], __ldg(t.ids + p0 + pp + r));
                 }
             }
         }
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
                 if (R < A(0)) continue;  // empty
                 const A cd = dist_to(t.centers + (size_t)node * DV);
                 const A lb = xsub(xsub(cd, R), xmul(t.slack, xadd(cd, R)));
-                const bool need = active && !(lb > topk.kth);
+                const bool need = active && !(lb > topk.kth());
                 if (!__syncthreads_or(need)) continue;
                 scan_bucket(node - t.n_internal, need);
             } else {
@@ -275,8 +284,8 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
                 A lb1 = pos_inf<A>(), lb2 = pos_inf<A>();
                 if (!(R1 < A(0))) { const A cd = dist_to(t.centers + (size_t)c1 * DV); lb1 = xsub(xsub(cd, R1), xmul(t.slack, xadd(cd, R1))); }
                 if (!(R2 < A(0))) { const A cd = dist_to(t.centers + (size_t)c2 * DV); lb2 = xsub(xsub(cd, R2), xmul(t.slack, xadd(cd, R2))); }
-                const bool need1 = active && !(R1 < A(0)) && !(lb1 > topk.kth);
-                const bool need2 = active && !(R2 < A(0)) && !(lb2 > topk.kth);
+                const bool need1 = active && !(R1 < A(0)) && !(lb1 > topk.kth());
+                const bool need2 = active && !(R2 < A(0)) && !(lb2 > topk.kth());
                 int n1, n2, npref, nany;
                 block_counts(votes, parity, need1, need2, (need1 || need2) && (lb1 < lb2), need1 || need2, n1, n2, npref, nany);
                 // nearer child first (:232-236), decided by the tile's majority
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
             // vantage points above the split level belong to no split's subtree
             for (uint32_t node = 0; node < ((1u << a.split_level) - 1u); ++node) {
                 const A dq = dist_to(t.centers + (size_t)node * DV);
-                if (active) topk.offer(dq, t.vp_ids[node], k);
+                if (active) topk.offer(dq, t.vp_ids[node]);
             }
         }
         stack[sp] = root; lbs[sp] = A(0); ++sp;
@@ -304,19 +313,19 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
             const uint32_t node = stack[sp];
             const A lb = lbs[sp];
             ++my_visits;
-            const bool need = active && !(lb > topk.kth);
+            const bool need = active && !(lb > topk.kth());
             if (node >= t.n_internal) {
                 if (!__syncthreads_or(need)) continue;
                 scan_bucket(node - t.n_internal, need);
             } else {
                 const A mu = t.radii[node];
                 const A dq = dist_to(t.centers + (size_t)node * DV);
-                if (need) topk.offer(dq, t.vp_ids[node], k);  // the vantage point is a data point (:106-109)
+                if (need) topk.offer(dq, t.vp_ids[node]);  // the vantage point is a data point (:106-109)
                 const A s = xmul(t.slack, xadd(dq, mu));
                 const A lbn = fmax(lb, xsub(xsub(dq, mu), s));   // near side: d(p,vp) <= mu
                 const A lbf = fmax(lb, xsub(xsub(mu, dq), s));   // far side:  d(p,vp) >= mu
-                const bool needn = active && !(lbn > topk.kth);
-                const bool needf = active && !(lbf > topk.kth);
+                const bool needn = active && !(lbn > topk.kth());
+                const bool needf = active && !(lbf > topk.kth());
                 int nn, nf, npref, nany;
                 block_counts(votes, parity, needn, needf, (needn || needf) && (dq < mu), needn || needf, nn, nf, npref, nany);
                 const bool near_first = 2 * npref >= nany;  // :111 `distance < radius` -> near first
@@ -334,10 +343,7 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
 
     if (active) {
         const size_t base = ((size_t)blockIdx.y * a.nq + qid) * k;
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            if (i < (int)k) { a.part_d[base + i] = topk.kd[i]; a.part_i[base + i] = topk.ki[i]; }
-        }
+        topk.store(a.part_d + base, a.part_i + base, k);
     }
     if (a.counters) {
         atomicAdd(&s_pairs, my_pairs);

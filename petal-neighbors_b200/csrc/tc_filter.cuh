@@ -188,6 +188,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t* tempty_bar = tfull_bar + NUM_ACC;      // [NUM_ACC]
     uint64_t* a_bar = tempty_bar + NUM_ACC;          // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
+    uint32_t* qbuf = tmem_slot + 4;  // per epilogue warp: 64 x u32 point rows, then 64 x u8 owner lanes
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int EPI_WARPS = 4 * MT;
@@ -260,24 +261,59 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else {
         // ================= epilogue: one query row per thread =================
+        // Filter hits are not evaluated in place (a divergent chain of dependent L2 round trips
+        // that would hold the accumulator stage hostage for the whole CTA): they are pushed to a
+        // per-warp queue with ballot compaction and drained 32 at a time, the 32 lanes evaluating
+        // 32 exact distances in parallel and handing each result to the lane that owns the query.
         const int mt = warp >> 2, quad = warp & 3;
-        const uint32_t qrow = row_base + mt * BM + quad * 32 + lane;
+        const uint32_t wrow0 = row_base + mt * BM + quad * 32;  // first query row of this warp
+        const uint32_t qrow = wrow0 + lane;
         const bool active = qrow < a.nq;
         const DevTree<float>& t = a.t;
         const int DV = DVR > 0 ? DVR : (int)t.dv;
-        float4 qreg[DVR > 0 ? DVR : 1];
-        if (DVR > 0) {
-#pragma unroll
-            for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc) qreg[jc] = active ? a.q[(size_t)qrow * DV + jc] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        uint32_t* q_prow = qbuf + warp * 64;
+        unsigned char* q_owner = reinterpret_cast<unsigned char*>(qbuf + EPI_WARPS * 64) + warp * 64;
         TopK<float, K> topk;
-        topk.init(active);
+        topk.init(active, a.k);
         if (a.floor_d && active) topk.set_floor(a.floor_d[qrow], a.floor_i[qrow]);
         const float margin = active ? a.q_margin[qrow] : 0.f;
         const float t2s = a.t2_scale;
-        const float ninf = -pos_inf<float>();
-        float theta = active ? pos_inf<float>() : ninf;
+        float theta = active ? pos_inf<float>() : -pos_inf<float>();
+        const unsigned full = 0xffffffffu;
+        const unsigned lt_mask = (1u << lane) - 1u;
         unsigned long long hits = 0;
+        int qn = 0;  // queue fill, warp-uniform
+
+        // exact evaluation of queue entries [0, cnt), cnt <= 32 (warp-uniform)
+        auto drain = [&](int cnt) {
+            float s = pos_inf<float>();
+            uint32_t id = NO_ID;
+            int o = 0;
+            if (lane < cnt) {
+                o = q_owner[lane];
+                const uint32_t prow = q_prow[lane];
+                const float4* qr = a.q + (size_t)(wrow0 + o) * DV;
+                const float4* pr = t.pts + (size_t)prow * DV;
+                float acc = 0.f;
+                if (DVR > 0) {
+#pragma unroll
+                    for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc) acc = fold(acc, __ldg(qr + jc), __ldg(pr + jc));
+                } else {
+                    for (int jc = 0; jc < DV; ++jc) acc = fold(acc, __ldg(qr + jc), __ldg(pr + jc));
+                }
+                s = acc;
+                id = __ldg(t.ids + prow);
+            }
+            for (int e = 0; e < cnt; ++e) {
+                const float se = __shfl_sync(full, s, e);
+                const uint32_t ide = __shfl_sync(full, id, e);
+                const int oe = __shfl_sync(full, o, e);
+                if (lane == oe && se <= topk.t2) {
+                    topk.offer_sq(se, ide);
+                    theta = xadd(xmul(topk.t2, t2s), margin);
+                }
+            }
+        };
 
         for (uint32_t j = 0; j < a.n_tiles; ++j) {
             const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
@@ -295,28 +331,37 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     m2 = fminf(m2, fminf(v[i + 4], v[i + 5])); m3 = fminf(m3, fminf(v[i + 6], v[i + 7]));
                 }
                 const float m = fminf(fminf(m0, m1), fminf(m2, m3));
-                if (m <= theta) {
+                if (__any_sync(full, m <= theta)) {
                     uint32_t bits = 0;
+                    if (m <= theta) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) bits |= (v[i] <= theta ? 1u : 0u) << i;
-                    while (bits) {
-                        const int i = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const uint32_t prow = j * BN + cc * 32 + i;
-                        if (prow >= t.n) continue;  // zero-filled rows past the last point
-                        ++hits;
-                        const float4* pr = t.pts + (size_t)prow * DV;
-                        float acc = 0.f;
-                        if (DVR > 0) {
-#pragma unroll
-                            for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc) acc = fold(acc, qreg[jc], __ldg(pr + jc));
-                        } else {
-                            const float4* qr = a.q + (size_t)qrow * DV;
-                            for (int jc = 0; jc < DV; ++jc) acc = fold(acc, __ldg(qr + jc), __ldg(pr + jc));
+                        for (int i = 0; i < 32; ++i) bits |= (v[i] <= theta ? 1u : 0u) << i;
+                        const int valid = (int)t.n - (int)(j * BN + cc * 32);  // rows past the last point are zero-filled
+                        if (valid < 32) bits &= valid > 0 ? ((1u << valid) - 1u) : 0u;
+                    }
+                    for (;;) {
+                        const bool has = bits != 0;
+                        const unsigned mask = __ballot_sync(full, has);
+                        if (!mask) break;
+                        if (has) {
+                            const int i = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const int slot = qn + __popc(mask & lt_mask);
+                            q_prow[slot] = j * BN + cc * 32 + i;
+                            q_owner[slot] = (unsigned char)lane;
                         }
-                        if (acc <= topk.t2) {
-                            topk.offer_sq(acc, __ldg(t.ids + prow), a.k);
-                            theta = xadd(xmul(topk.t2, t2s), margin);
+                        qn += __popc(mask);
+                        hits += __popc(mask);
+                        __syncwarp();
+                        if (qn >= 32) {
+                            drain(32);
+                            const int rest = qn - 32;  // < 32
+                            uint32_t tp = 0; unsigned char to = 0;
+                            if (lane < rest) { tp = q_prow[32 + lane]; to = q_owner[32 + lane]; }
+                            __syncwarp();
+                            if (lane < rest) { q_prow[lane] = tp; q_owner[lane] = to; }
+                            __syncwarp();
+                            qn = rest;
                         }
                     }
                 }
@@ -324,17 +369,14 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (qn >= 16) { drain(qn); qn = 0; __syncwarp(); }
         }
+        if (qn > 0) { drain(qn); qn = 0; }
         if (active) {
             const size_t base = (size_t)qrow * a.k;
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-                if (i < (int)a.k) { a.part_d[base + i] = topk.kd[i]; a.part_i[base + i] = topk.ki[i]; }
+            topk.store(a.part_d + base, a.part_i + base, a.k);
         }
-        if (a.counters) {
-            for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
-            if (lane == 0) atomicAdd(&a.counters[2], hits);
-        }
+        if (a.counters && lane == 0) atomicAdd(&a.counters[2], hits);
     }
 
     tc_fence_before();
