@@ -102,7 +102,8 @@ struct Engine final : pn_tree {
     DevBuf d_baug, d_center, w_aaug, w_qmargin;
     bool tensor_ready = false, last_used_tensor = false;
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
-    float pmax = 0.f;      // max |p - center|
+    float pmax = 0.f;      // max |s (p - center)|
+    float tscale = 1.f;    // s: power of two bringing the centred coordinates into [-1, 1]
     uint32_t algo = PN_ALGO_AUTO;
     alignas(64) CUtensorMap map_b;
 
@@ -194,15 +195,15 @@ struct Engine final : pn_tree {
         }();
         return fn;
     }
-    int make_map(CUtensorMap* m, void* base, uint64_t rows) {
+    int make_map(CUtensorMap* m, void* base, uint64_t rows, uint32_t box_rows) {
         EncodeTiledFn fn = encode_fn();
         if (!fn) return fail(PN_CUDA, "cuTensorMapEncodeTiled entry point not found");
         cuuint64_t dims[2] = {kp, rows};
-        cuuint64_t strides[1] = {(cuuint64_t)kp * 4};
-        cuuint32_t box[2] = {(cuuint32_t)tc::KC, (cuuint32_t)tc::BN};
+        cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+        cuuint32_t box[2] = {(cuuint32_t)tc::KC, (cuuint32_t)box_rows};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(PN_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
         return PN_OK;
     }
@@ -210,26 +211,32 @@ struct Engine final : pn_tree {
     int prepare_tensor() {
         if constexpr (sizeof(A) == 4) {
             if (!tensor_eligible()) return PN_OK;
-            kp = (ft.d + 4 + tc::KC - 1) / tc::KC * tc::KC;
+            kp = (ft.d + tc::NSLOT + tc::KC - 1) / tc::KC * tc::KC;
             // centre = mean of the stored points (double accumulation on the host)
             std::vector<double> mean(ft.dpad, 0.0);
             for (size_t i = 0; i < ft.n; ++i)
                 for (uint32_t j = 0; j < ft.d; ++j) mean[j] += (double)ft.pts[i * ft.dpad + j];
             std::vector<float> c(ft.dpad, 0.f);
             for (uint32_t j = 0; j < ft.d; ++j) c[j] = (float)(mean[j] / (double)ft.n);
+            float maxabs = 0.f;
+            for (size_t i = 0; i < ft.n; ++i)
+                for (uint32_t j = 0; j < ft.d; ++j) maxabs = std::max(maxabs, std::fabs(ft.pts[i * ft.dpad + j] - c[j]));
+            int ex = 0;
+            if (maxabs > 0.f && std::isfinite(maxabs)) { std::frexp(maxabs, &ex); }  // maxabs = m 2^ex, m in [0.5, 1)
+            tscale = std::ldexp(1.0f, -ex);
             TRY(d_center.ensure(ft.dpad * 4));
             CU(cudaMemcpy(d_center.p, c.data(), ft.dpad * 4, cudaMemcpyHostToDevice));
-            TRY(d_baug.ensure((size_t)ft.n * kp * 4));
+            TRY(d_baug.ensure((size_t)ft.n * kp * 2));
             TRY(w_counters.ensure(32));
             CU(cudaMemset(w_counters.p, 0, 32));
-            tc::build_baug_kernel<<<(unsigned)((ft.n + 127) / 128), 128, 0, stream>>>(d_pts.as<float>(), d_center.as<float>(), (uint32_t)ft.n, ft.d,
-                                                                                     ft.dpad, kp, d_baug.as<float>(), w_counters.as<unsigned int>());
+            tc::build_baug_kernel<<<(unsigned)((ft.n + 127) / 128), 128, 0, stream>>>(d_pts.as<float>(), d_center.as<float>(), tscale, (uint32_t)ft.n, ft.d,
+                                                                                     ft.dpad, kp, d_baug.as<__half>(), w_counters.as<unsigned int>());
             CU(cudaGetLastError());
             unsigned int bits = 0;
             CU(cudaMemcpyAsync(&bits, w_counters.p, 4, cudaMemcpyDeviceToHost, stream));
             CU(cudaStreamSynchronize(stream));
             memcpy(&pmax, &bits, 4);
-            TRY(make_map(&map_b, d_baug.p, ft.n));
+            TRY(make_map(&map_b, d_baug.p, ft.n, tc::BN));
             info.device_bytes += d_baug.cap;
             tensor_ready = true;
         }
@@ -238,19 +245,20 @@ struct Engine final : pn_tree {
 
     template <int DVR, int K, int MT>
     int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
-        const size_t smem = 1024 + (size_t)(MT * fa.nkc + fa.stages) * tc::CHUNK_BYTES + 512 + (size_t)4 * MT * (64 * 4 + 64);
+        const size_t smem = 1024 + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES + 1024 + (size_t)4 * MT * 144 * 4;
         auto kern = tc::knn_filter_kernel<DVR, K, MT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (fa.nq + MT * tc::BM - 1) / (MT * tc::BM);
-        kern<<<grid, (4 * MT + 2) * 32, smem, st>>>(map_a, map_b, fa);
+        kern<<<grid, (5 * MT + 1) * 32, smem, st>>>(map_a, map_b, fa);
         CU(cudaGetLastError());
         return PN_OK;
     }
     template <int K>
     int launch_filter_k(const CUtensorMap& map_a, tc::FilterArgs& fa, cudaStream_t st) {
-        const int mt = fa.nkc <= 3 ? 2 : 1;
+        const int mt = fa.nkc <= 6 ? 2 : 1;
         const size_t budget = 220 * 1024;
-        fa.stages = (uint32_t)std::min<size_t>(8, (budget - 4608 - (size_t)mt * fa.nkc * tc::CHUNK_BYTES) / tc::CHUNK_BYTES);
+        fa.gs = fa.nkc == 1 ? 4 : (fa.nkc == 2 ? 2 : 1);
+        fa.stages = (uint32_t)std::min<size_t>(fa.gs > 1 ? 4 : 12, (budget - 7168 - (size_t)mt * fa.nkc * tc::A_CHUNK_BYTES) / (tc::CHUNK_BYTES * fa.gs));
         if (mt == 2) {
             if (dt.dv == 4) return launch_filter_t<4, K, 2>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 2>(map_a, fa, st);
@@ -263,7 +271,7 @@ struct Engine final : pn_tree {
     int knn_device_tensor(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st) {
         if constexpr (sizeof(A) == 4) {
             TRY(stage_queries(qraw, nq, stride, st, false));
-            TRY(w_aaug.ensure((size_t)nq * kp * 4));
+            TRY(w_aaug.ensure((size_t)nq * kp * 2));
             TRY(w_qmargin.ensure((size_t)nq * 4));
             const bool k1 = (k == 1);
             const uint32_t KP = k1 ? 1 : 16;
@@ -273,12 +281,12 @@ struct Engine final : pn_tree {
             TRY(w_counters.ensure(32));
             if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * 4)); TRY(w_floor_i.ensure((size_t)nq * 4)); }
             CU(cudaMemsetAsync(w_counters.p, 0, 32, st));
-            tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(w_q.as<float>(), d_center.as<float>(), nq, ft.d, ft.dpad, kp, pmax,
-                                                                    w_aaug.as<float>(), w_qmargin.as<float>());
+            tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(w_q.as<float>(), d_center.as<float>(), tscale, nq, ft.d, ft.dpad, kp, pmax,
+                                                                    w_aaug.as<__half>(), w_qmargin.as<float>());
             CU(cudaGetLastError());
             ++counters.kernel_launches;
             alignas(64) CUtensorMap map_a;
-            TRY(make_map(&map_a, w_aaug.p, nq));
+            TRY(make_map(&map_a, w_aaug.p, nq, tc::BM));
             CU(cudaEventRecord(ev[2], st));
             for (uint32_t p = 0; p < n_pass; ++p) {
                 const uint32_t kk = std::min(KP, k - p * KP);
@@ -288,7 +296,7 @@ struct Engine final : pn_tree {
                 fa.nq = nq; fa.k = kk;
                 fa.n_tiles = (uint32_t)((ft.n + tc::BN - 1) / tc::BN);
                 fa.nkc = kp / tc::KC;
-                fa.t2_scale = 1.0f + (float)(ft.d + 4) * 1.1920928955078125e-07f;
+                fa.t2_scale = tscale * tscale * (1.0f + (float)(ft.d + 4) * 1.1920928955078125e-07f);
                 fa.part_d = w_part_d.as<float>(); fa.part_i = w_part_i.as<uint32_t>();
                 fa.floor_d = p ? w_floor_d.as<float>() : nullptr; fa.floor_i = p ? w_floor_i.as<uint32_t>() : nullptr;
                 fa.counters = w_counters.as<unsigned long long>();
