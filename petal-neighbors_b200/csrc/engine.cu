@@ -99,7 +99,7 @@ struct Engine final : pn_tree {
         w_counters, w_out_i, w_out_d, w_counts, w_offsets, w_hits;
     DevTree<A> dt{};
     // tensor path (f32 only): augmented TF32 operands, see tc_filter.cuh
-    DevBuf d_baug, d_center, w_aaug, w_qmargin;
+    DevBuf d_baug, d_center, d_tile_pmax, w_aaug, w_qmargin;
     bool tensor_ready = false, last_used_tensor = false;
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
     float pmax = 0.f;      // max |s (p - center)|
@@ -112,7 +112,7 @@ struct Engine final : pn_tree {
             DeviceGuard g(device);
             for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &w_qraw, &w_q, &w_home,
                               &w_hist, &w_cursor, &w_order, &w_part_d, &w_part_i, &w_floor_d, &w_floor_i, &w_counters,
-                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin})
+                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &d_tile_pmax, &w_aaug, &w_qmargin})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             if (stream) cudaStreamDestroy(stream);
@@ -229,8 +229,12 @@ struct Engine final : pn_tree {
             TRY(d_baug.ensure((size_t)ft.n * kp * 2));
             TRY(w_counters.ensure(32));
             CU(cudaMemset(w_counters.p, 0, 32));
+            const size_t n_tiles = (ft.n + tc::BN - 1) / tc::BN;
+            TRY(d_tile_pmax.ensure(n_tiles * 4));
+            CU(cudaMemset(d_tile_pmax.p, 0, n_tiles * 4));
             tc::build_baug_kernel<<<(unsigned)((ft.n + 127) / 128), 128, 0, stream>>>(d_pts.as<float>(), d_center.as<float>(), tscale, (uint32_t)ft.n, ft.d,
-                                                                                     ft.dpad, kp, d_baug.as<__half>(), w_counters.as<unsigned int>());
+                                                                                     ft.dpad, kp, d_baug.as<__half>(), w_counters.as<unsigned int>(),
+                                                                                     d_tile_pmax.as<unsigned int>());
             CU(cudaGetLastError());
             unsigned int bits = 0;
             CU(cudaMemcpyAsync(&bits, w_counters.p, 4, cudaMemcpyDeviceToHost, stream));
@@ -293,6 +297,9 @@ struct Engine final : pn_tree {
                 tc::FilterArgs fa{};
                 fa.t = *reinterpret_cast<DevTree<float>*>(&dt);
                 fa.q = w_q.as<float4>(); fa.q_margin = w_qmargin.as<float>();
+                fa.tile_pmax = d_tile_pmax.as<float>();
+                fa.kq = (float)(kp + 8) * 4.76837158203125e-07f;
+                fa.sqd = 6.2e-05f * std::sqrt((float)ft.d);
                 fa.nq = nq; fa.k = kk;
                 fa.n_tiles = (uint32_t)((ft.n + tc::BN - 1) / tc::BN);
                 fa.nkc = kp / tc::KC;

@@ -145,7 +145,10 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 struct FilterArgs {
     DevTree<float> t;
     const float4* q;       // nq x dpad exact zero-padded queries (rerank)
-    const float* q_margin; // nq: E_q
+    const float* q_margin; // nq: scaled norm |q'| (+inf when outside the fp16 range)
+    const float* tile_pmax; // n_tiles: max |p'| over the points of each B tile
+    float kq;              // (Kp + 8) 2^-21
+    float sqd;             // 2^-14 sqrt(d)
     uint32_t nq, k;
     uint32_t n_tiles;      // ceil(n / BN)
     uint32_t nkc;          // K chunks (Kp / 32)
@@ -170,7 +173,8 @@ __device__ __forceinline__ void split3_f16(float x, __half& h1, __half& h2, __ha
 
 // B operand: one fp16 row per stored point (bucket order).  pmax_bits receives max |p'| (float bits).
 __global__ void build_baug_kernel(const float* __restrict__ pts, const float* __restrict__ center, float scale, uint32_t n,
-                                  uint32_t d, uint32_t dpad, uint32_t kp, __half* __restrict__ baug, unsigned int* pmax_bits) {
+                                  uint32_t d, uint32_t dpad, uint32_t kp, __half* __restrict__ baug, unsigned int* pmax_bits,
+                                  unsigned int* tile_pmax_bits) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = pts + (size_t)i * dpad;
@@ -186,7 +190,9 @@ __global__ void build_baug_kernel(const float* __restrict__ pts, const float* __
     split3_f16(nrm, h1, h2, h3);
     const __half one = __float2half_rn(1.f);
     o[kp - 6] = one; o[kp - 5] = one; o[kp - 4] = one; o[kp - 3] = h1; o[kp - 2] = h2; o[kp - 1] = h3;
-    atomicMax(pmax_bits, __float_as_uint(sqrtf(nrm) * 1.000001f));
+    const unsigned int nb = __float_as_uint(sqrtf(nrm) * 1.000001f);
+    atomicMax(pmax_bits, nb);
+    atomicMax(tile_pmax_bits + i / BN, nb);
 }
 
 // A operand + per-query margin E_q (scaled units)
@@ -210,10 +216,8 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
     split3_f16(in_range ? nrm : 0.f, h1, h2, h3);
     const __half one = __float2half_rn(1.f);
     o[kp - 6] = h1; o[kp - 5] = h2; o[kp - 4] = h3; o[kp - 3] = one; o[kp - 2] = one; o[kp - 1] = one;
-    const float s = qn + pmax;
-    const float e = 1.01f * 0.001953125f * qn * pmax + 6.2e-05f * sqrtf((float)d) * (qn + 2.f * pmax) +
-                    (float)(kp + 8) * 4.76837158203125e-07f * s * s;
-    q_margin[i] = in_range ? e : pos_inf<float>();
+    (void)pmax;
+    q_margin[i] = in_range ? qn : pos_inf<float>();
 }
 
 template <int DVR, int K, int MT>
@@ -333,7 +337,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         TopK<float, K> topk;
         topk.init(active, a.k);
         if (a.floor_d && active) topk.set_floor(a.floor_d[qrow], a.floor_i[qrow]);
-        const float margin = active ? a.q_margin[qrow] : 0.f;
+        const float qnorm = active ? a.q_margin[qrow] : 0.f;  // scaled |q'|
+        float margin = 0.f;                                   // E_q for the current tile
         const float t2s = a.t2_scale;
         float theta = active ? pos_inf<float>() : -pos_inf<float>();
         const unsigned full = 0xffffffffu;
@@ -385,21 +390,25 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
         // threshold test of 32 accumulator columns [col0, col0+32) of tile j; hits go to the queue
         auto scan32 = [&](const uint32_t (&r)[32], uint32_t j, int col0) {
-            float m0 = fminf(__uint_as_float(r[0]), __uint_as_float(r[1])), m1 = fminf(__uint_as_float(r[2]), __uint_as_float(r[3]));
-            float m2 = fminf(__uint_as_float(r[4]), __uint_as_float(r[5])), m3 = fminf(__uint_as_float(r[6]), __uint_as_float(r[7]));
+            // block minima over 4 blocks of 8 consecutive columns; only blocks that pass are searched
+            float mb[4];
 #pragma unroll
-            for (int i = 8; i < 32; i += 8) {
-                m0 = fminf(m0, fminf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
-                m1 = fminf(m1, fminf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
-                m2 = fminf(m2, fminf(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5])));
-                m3 = fminf(m3, fminf(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7])));
+            for (int b = 0; b < 4; ++b) {
+                const float x0 = fminf(__uint_as_float(r[8 * b]), fminf(__uint_as_float(r[8 * b + 1]), __uint_as_float(r[8 * b + 2])));
+                const float x1 = fminf(__uint_as_float(r[8 * b + 3]), fminf(__uint_as_float(r[8 * b + 4]), __uint_as_float(r[8 * b + 5])));
+                mb[b] = fminf(fminf(x0, x1), fminf(__uint_as_float(r[8 * b + 6]), __uint_as_float(r[8 * b + 7])));
             }
-            const float m = fminf(fminf(m0, m1), fminf(m2, m3));
+            const float m = fminf(fminf(mb[0], mb[1]), fminf(mb[2], mb[3]));
             if (!__any_sync(full, m <= theta)) return;
             uint32_t bits = 0;
             if (m <= theta) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) bits |= (__uint_as_float(r[i]) <= theta ? 1u : 0u) << i;
+                for (int b = 0; b < 4; ++b) {
+                    if (mb[b] <= theta) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) bits |= (__uint_as_float(r[8 * b + i]) <= theta ? 1u : 0u) << (8 * b + i);
+                    }
+                }
                 const int valid = (int)t.n - (int)(j * BN + col0);  // rows past the last point are zero-filled
                 if (valid < 32) bits &= valid > 0 ? ((1u << valid) - 1u) : 0u;
             }
@@ -441,6 +450,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (uint32_t j = 0; j < a.n_tiles; ++j) {
             const uint32_t as = j % NUM_ACC;
             const uint32_t taddr = tmem_base + lane_off + (as * MT + mt) * BN;
+            {   // rounding margin for this tile: E_q with the tile's own bound on |p'|
+                const float pm = __ldg(a.tile_pmax + j), sn = qnorm + pm;
+                margin = 1.01f * 0.001953125f * qnorm * pm + a.sqd * (qnorm + 2.f * pm) + a.kq * sn * sn;
+                if (active) theta = xadd(xmul(topk.t2, t2s), margin);
+            }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 uint32_t (&cur)[32] = (g & 1) ? rb : ra;
