@@ -312,7 +312,8 @@ def main():
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get(wl)
+                ent = json.load(open(prof)).get(wl if ctr["filter_pairs"] else wl + "_simt")
+                traffic = float(ent["bytes_per_launch"]) * nq / float(ent["queries"])  # scaled to this launch size
             except Exception:
                 traffic = None
         out = {
@@ -332,7 +333,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                          "traffic": traffic, "peak_source": f"of {which}",
-                         "kernel": "knn scan (tile kernel + merge), CUDA events inside the engine, per step",
+                         "kernel": ("tc::knn_filter_kernel (tcgen05 FP16 filter + exact rerank)" if ctr["filter_pairs"] else "knn_tile_kernel (exact SIMT scan)") + " + merge, CUDA events inside the engine, per step",
+                         "rerank_pairs": int(ctr["rerank_pairs"]),
                          "kernel_ms": scan_ms, "algorithmic_bytes": b_alg, "pairs": int(pairs),
                          "pairs_over_NQ": pairs / (float(n) * nq),
                          "tensor_frac_if_counted": tc_ach / tf32_peak, "tf32_peak_assumed_tflops": tf32_peak},
