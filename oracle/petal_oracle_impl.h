@@ -559,7 +559,7 @@ void FN(orc_brute_knn)(const REAL *points, size_t n, size_t d, size_t stride, co
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #endif
     (void)n_threads;
-#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
     for (long long qi = 0; qi < (long long)nq; ++qi) {
         size_t *bi = out_i + (size_t)qi * k;
         REAL *bd = out_d + (size_t)qi * k;
@@ -586,7 +586,7 @@ void FN(orc_brute_radius)(const REAL *points, size_t n, size_t d, size_t stride,
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #endif
     (void)n_threads;
-#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
     for (long long qi = 0; qi < (long long)nq; ++qi) {
         size_t c = 0;
         for (size_t i = 0; i < n; ++i) {
@@ -616,7 +616,7 @@ unsigned long long FN(orc_balltree_query_batch)(const FN(orc_balltree) *t, const
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #endif
     (void)n_threads;
-#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads) reduction(+ : total)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads) reduction(+ : total)
     for (long long qi = 0; qi < (long long)nq; ++qi) {
         unsigned long long nd = 0;
         size_t len = FN(orc_balltree_query)(t, q + (size_t)qi * q_stride, k, out_i + (size_t)qi * k,
@@ -637,7 +637,7 @@ unsigned long long FN(orc_vptree_query_nearest_batch)(const FN(orc_vptree) *t, c
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #endif
     (void)n_threads;
-#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads) reduction(+ : total)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads) reduction(+ : total)
     for (long long qi = 0; qi < (long long)nq; ++qi) {
         unsigned long long nd = 0;
         FN(orc_vptree_query_nearest)(t, q + (size_t)qi * q_stride, &out_i[qi], &out_d[qi], &nd);
@@ -656,7 +656,7 @@ void FN(orc_balltree_query_radius_batch)(const FN(orc_balltree) *t, const REAL *
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #endif
     (void)n_threads;
-#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
     for (long long qi = 0; qi < (long long)nq; ++qi) {
         size_t *res = NULL;
         size_t len = FN(orc_balltree_query_radius)(t, q + (size_t)qi * q_stride, r, &res);
