@@ -55,7 +55,7 @@ typedef enum pn_dtype { PN_F32 = 0, PN_F64 = 1 } pn_dtype;
 typedef enum pn_algo {
     PN_ALGO_AUTO = 0,
     PN_ALGO_SIMT = 1,  /* exact difference-form FP32/FP64 tiles on the CUDA cores */
-    PN_ALGO_TENSOR = 2 /* tcgen05 TF32 filter + exact rerank (f32, any d; AUTO picks it by d) */
+    PN_ALGO_TENSOR = 2 /* tcgen05 FP16 filter + exact rerank (f32 input; AUTO: d >= 16, batches >= 2048) */
 } pn_algo;
 
 #define PN_FLAG_HOST_ONLY 1u /* build + flatten on the host only (no device; queries fail with
@@ -155,6 +155,16 @@ int32_t pn_vptree_query_nearest_f32(pn_tree *tree, const float *queries, size_t 
                                     size_t q_row_stride, uint64_t *idx_out, float *dist_out);
 int32_t pn_vptree_query_nearest_f64(pn_tree *tree, const double *queries, size_t nq,
                                     size_t q_row_stride, uint64_t *idx_out, double *dist_out);
+
+/* --- all-points self-query: every stored point is a query (the reference bench's loop,
+ * benches/ball_tree.rs:53-59, and the k-NN-graph shape of downstream clustering).  Row i of the
+ * n x k outputs is the answer for points[i]; the point itself is its own first neighbour
+ * (distance 0, lowest index among exact duplicates).  No query upload: the stored, bucket-ordered
+ * points are the query tiles. */
+int32_t pn_balltree_query_self_f32(pn_tree *tree, size_t k, uint64_t *idx_out, float *dist_out);
+int32_t pn_balltree_query_self_f64(pn_tree *tree, size_t k, uint64_t *idx_out, double *dist_out);
+int32_t pn_tree_query_self_dev(pn_tree *tree, size_t k, uint64_t *idx_dev, void *dist_dev, void *stream,
+                               int32_t sync);
 
 void pn_free(void *p);
 

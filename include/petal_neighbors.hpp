@@ -74,6 +74,7 @@ template <> struct Abi<float> {
     static constexpr auto nearest = pn_balltree_query_nearest_f32;
     static constexpr auto radius = pn_balltree_query_radius_f32;
     static constexpr auto vp_nearest = pn_vptree_query_nearest_f32;
+    static constexpr auto self = pn_balltree_query_self_f32;
 };
 template <> struct Abi<double> {
     static constexpr auto ball_create = pn_balltree_create_f64;
@@ -82,6 +83,7 @@ template <> struct Abi<double> {
     static constexpr auto nearest = pn_balltree_query_nearest_f64;
     static constexpr auto radius = pn_balltree_query_radius_f64;
     static constexpr auto vp_nearest = pn_vptree_query_nearest_f64;
+    static constexpr auto self = pn_balltree_query_self_f64;
 };
 }  // namespace detail
 
@@ -129,6 +131,8 @@ template <typename A> class BallTree {
         pn_free(po); pn_free(pi);
         return {offs, ind};
     }
+    // every stored point as a query (benches/ball_tree.rs:53-59): row-major n x k outputs
+    void query_self(size_t k, uint64_t* idx_out, A* dist_out) const { detail::check(detail::Abi<A>::self(h_, k, idx_out, dist_out)); }
     size_t num_points() const { return n_; }
     pn_tree* handle() const { return h_; }
 

@@ -200,6 +200,16 @@ class BallTree(_Tree):
         m = min(int(k), self.num_points())
         return idx[0, :m].astype(np.uintp), dist[0, :m]
 
+    def query_self(self, k: int):
+        """Every stored point as a query (benches/ball_tree.rs:53-59): (indices[n, k], distances[n, k])."""
+        n = self.num_points()
+        idx = np.empty((n, k), np.uint64)
+        dist = np.empty((n, k), self.dtype)
+        if k:
+            fn = getattr(_ffi.lib(), f"pn_balltree_query_self_{self._sfx}")
+            _check(fn(self._h, k, idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
+
     def query_nearest_batch(self, Q):
         idx, dist = self._knn("pn_balltree_query_nearest", Q, 1)
         return idx[:, 0], dist[:, 0]

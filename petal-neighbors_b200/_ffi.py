@@ -23,6 +23,7 @@ EXPORTS = [
     "pn_balltree_query_nearest_f32", "pn_balltree_query_nearest_f64",
     "pn_balltree_query_radius_f32", "pn_balltree_query_radius_f64",
     "pn_vptree_query_nearest_f32", "pn_vptree_query_nearest_f64",
+    "pn_balltree_query_self_f32", "pn_balltree_query_self_f64", "pn_tree_query_self_dev",
     "pn_free", "pn_tree_query_knn_dev", "pn_merge_topk_dev",
     "pn_tree_get_info", "pn_tree_get_counters", "pn_tree_get_layout",
 ]
@@ -83,6 +84,9 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_int32
             f.argtypes = [vp, vp, sz, sz, vp, vp]
+        f = getattr(L, f"pn_balltree_query_self_{sfx}")
+        f.restype = C.c_int32
+        f.argtypes = [vp, sz, vp, vp]
         f = getattr(L, f"pn_balltree_query_radius_{sfx}")
         f.restype = C.c_int32
         f.argtypes = [vp, vp, sz, sz, real, C.POINTER(u64p), C.POINTER(u64p)]
@@ -92,6 +96,8 @@ def lib():
     L.pn_free.restype = None
     L.pn_tree_query_knn_dev.restype = C.c_int32
     L.pn_tree_query_knn_dev.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, C.c_int32]
+    L.pn_tree_query_self_dev.restype = C.c_int32
+    L.pn_tree_query_self_dev.argtypes = [vp, sz, vp, vp, vp, C.c_int32]
     L.pn_merge_topk_dev.restype = C.c_int32
     L.pn_merge_topk_dev.argtypes = [C.c_uint32, C.c_int32, vp, vp, sz, sz, sz, vp, vp, vp, C.c_int32]
     L.pn_tree_get_info.restype = C.c_int32

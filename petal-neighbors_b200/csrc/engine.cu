@@ -81,6 +81,7 @@ struct pn_tree {
     virtual int knn_dev(const void* q, size_t nq, size_t stride, size_t k, uint64_t* idx, void* dist,
                         cudaStream_t st, bool sync) = 0;
     virtual int radius_host(const void* q, size_t nq, size_t stride, double r, uint64_t** offs, uint64_t** idx) = 0;
+    virtual int knn_self(size_t k, uint64_t* idx, void* dist, bool dev, cudaStream_t st, bool sync) = 0;
     virtual int layout(uint32_t* ids, uint32_t* blo, uint32_t* bhi, void* rad, void* cen, void* pts) = 0;
 };
 
@@ -272,9 +273,11 @@ struct Engine final : pn_tree {
     }
 
     // tensor k-NN: same contract as knn_device
-    int knn_device_tensor(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st) {
+    int knn_device_tensor(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st,
+                          bool self_query = false) {
         if constexpr (sizeof(A) == 4) {
-            TRY(stage_queries(qraw, nq, stride, st, false));
+            if (!self_query) TRY(stage_queries(qraw, nq, stride, st, false));
+            const float* qpad = self_query ? d_pts.as<float>() : w_q.as<float>();
             TRY(w_aaug.ensure((size_t)nq * kp * 2));
             TRY(w_qmargin.ensure((size_t)nq * 4));
             const bool k1 = (k == 1);
@@ -285,7 +288,7 @@ struct Engine final : pn_tree {
             TRY(w_counters.ensure(32));
             if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * 4)); TRY(w_floor_i.ensure((size_t)nq * 4)); }
             CU(cudaMemsetAsync(w_counters.p, 0, 32, st));
-            tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(w_q.as<float>(), d_center.as<float>(), tscale, nq, ft.d, ft.dpad, kp, pmax,
+            tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(qpad, d_center.as<float>(), tscale, nq, ft.d, ft.dpad, kp, pmax,
                                                                     w_aaug.as<__half>(), w_qmargin.as<float>());
             CU(cudaGetLastError());
             ++counters.kernel_launches;
@@ -296,7 +299,7 @@ struct Engine final : pn_tree {
                 const uint32_t kk = std::min(KP, k - p * KP);
                 tc::FilterArgs fa{};
                 fa.t = *reinterpret_cast<DevTree<float>*>(&dt);
-                fa.q = w_q.as<float4>(); fa.q_margin = w_qmargin.as<float>();
+                fa.q = reinterpret_cast<const float4*>(qpad); fa.q_margin = w_qmargin.as<float>();
                 fa.tile_pmax = d_tile_pmax.as<float>();
                 fa.kq = (float)(kp + 8) * 4.76837158203125e-07f;
                 fa.sqd = 6.2e-05f * std::sqrt((float)ft.d);
@@ -310,7 +313,8 @@ struct Engine final : pn_tree {
                 TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
                 merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
                     w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, nq, kk, idx_out, dist_out, k, p * KP,
-                    n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr);
+                    n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr,
+                    self_query ? d_ids.as<uint32_t>() : nullptr);
                 CU(cudaGetLastError());
                 counters.kernel_launches += 2;
                 counters.filter_pairs += (uint64_t)ft.n * nq;
@@ -318,7 +322,7 @@ struct Engine final : pn_tree {
             CU(cudaEventRecord(ev[3], st));
             return PN_OK;
         } else {
-            (void)qraw; (void)nq; (void)stride; (void)k; (void)idx_out; (void)dist_out; (void)st;
+            (void)qraw; (void)nq; (void)stride; (void)k; (void)idx_out; (void)dist_out; (void)st; (void)self_query;
             return fail(PN_BAD_ARG, "the tensor path is f32 only");
         }
     }
@@ -353,11 +357,14 @@ struct Engine final : pn_tree {
     }
 
     // k-NN for nq queries whose raw rows are already on the device; results to device buffers
-    int knn_device(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st) {
+    // self_query: the queries are the stored points themselves, already padded, resident and in bucket
+    // order (perfect tile coherence); results are written to the ORIGINAL row of each point
+    int knn_device(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st,
+                   bool self_query = false) {
         last_used_tensor = tensor_ready && (algo == PN_ALGO_TENSOR || nq >= 2048);
-        if (last_used_tensor) return knn_device_tensor(qraw, nq, stride, k, idx_out, dist_out, st);
-        const bool sort = ft.n_buckets > 1 && nq > (uint32_t)TQ;
-        TRY(stage_queries(qraw, nq, stride, st, sort));
+        if (last_used_tensor) return knn_device_tensor(qraw, nq, stride, k, idx_out, dist_out, st, self_query);
+        const bool sort = !self_query && ft.n_buckets > 1 && nq > (uint32_t)TQ;
+        if (!self_query) TRY(stage_queries(qraw, nq, stride, st, sort));
         const uint32_t tiles = (nq + TQ - 1) / TQ;
         uint32_t sl = 0;
         while (((uint64_t)tiles << sl) < 2ull * n_sms && sl < ft.L && (2u << sl) <= (uint32_t)MAX_LISTS) ++sl;
@@ -374,7 +381,7 @@ struct Engine final : pn_tree {
         for (uint32_t p = 0; p < n_pass; ++p) {
             const uint32_t kk = std::min(KP, k - p * KP);
             KnnArgs<A> a{};
-            a.t = dt; a.q = w_q.as<V>(); a.qorder = sort ? w_order.as<uint32_t>() : nullptr;
+            a.t = dt; a.q = self_query ? d_pts.as<V>() : w_q.as<V>(); a.qorder = sort ? w_order.as<uint32_t>() : nullptr;
             a.nq = nq; a.k = kk; a.split_level = sl;
             a.part_d = w_part_d.as<A>(); a.part_i = w_part_i.as<uint32_t>();
             a.floor_d = p ? w_floor_d.as<A>() : nullptr; a.floor_i = p ? w_floor_i.as<uint32_t>() : nullptr;
@@ -382,7 +389,8 @@ struct Engine final : pn_tree {
             TRY(launch_knn(a, dim3(tiles, n_splits), st, k1));
             merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
                 w_part_d.as<A>(), w_part_i.as<uint32_t>(), n_splits, nq, kk, idx_out, dist_out, k, p * KP,
-                n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr);
+                n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr,
+                self_query ? d_ids.as<uint32_t>() : nullptr);
             CU(cudaGetLastError());
             counters.kernel_launches += 2;
         }
@@ -459,6 +467,38 @@ struct Engine final : pn_tree {
         TRY(knn_device((const A*)qv, (uint32_t)nq, stride, (uint32_t)k, idx, (A*)distv, st));
         CU(cudaEventRecord(ev[1], st));
         if (sync) return fetch_counters(st, nq);
+        counters.queries = nq;
+        return PN_OK;
+    }
+
+    // every stored point is a query (benches/ball_tree.rs:53-59): no H2D at all
+    int knn_self(size_t k, uint64_t* idx, void* distv, bool dev, cudaStream_t st, bool sync) override {
+        if (host_only) return fail(PN_CUDA, "tree was built with PN_FLAG_HOST_ONLY: no device, and there is no CPU fallback");
+        if (ft.n != ft.n_total) return fail(PN_BAD_ARG, "self-query needs the whole point set in this handle (not a shard)");
+        if (k == 0) return PN_OK;
+        if (!idx || !distv) return fail(PN_BAD_ARG, "output buffer is null");
+        std::lock_guard<std::mutex> lk(mu);
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        if (!st || !dev) st = stream;
+        TRY(use_stream(st));
+        counters = pn_counters{};
+        const uint32_t nq = (uint32_t)ft.n;
+        uint64_t* oi = idx; A* od = (A*)distv;
+        if (!dev) {
+            TRY(w_out_i.ensure((size_t)nq * k * 8));
+            TRY(w_out_d.ensure((size_t)nq * k * sizeof(A)));
+            oi = w_out_i.as<uint64_t>(); od = w_out_d.as<A>();
+        }
+        CU(cudaEventRecord(ev[0], st));
+        TRY(knn_device(d_pts.as<A>(), nq, ft.dpad, (uint32_t)k, oi, od, st, true));
+        if (!dev) {
+            CU(cudaMemcpyAsync(idx, oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(distv, od, (size_t)nq * k * sizeof(A), cudaMemcpyDeviceToHost, st));
+            counters.d2h_bytes = (uint64_t)nq * k * (8 + sizeof(A));
+        }
+        CU(cudaEventRecord(ev[1], st));
+        if (sync || !dev) return fetch_counters(st, nq);
         counters.queries = nq;
         return PN_OK;
     }
@@ -710,6 +750,18 @@ int32_t pn_vptree_query_nearest_f32(pn_tree* t, const float* q, size_t nq, size_
 }
 int32_t pn_vptree_query_nearest_f64(pn_tree* t, const double* q, size_t nq, size_t qs, uint64_t* io, double* dd) {
     GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_VP)); return t->knn_host(q, nq, qs, 1, io, dd); GUARD_END
+}
+int32_t pn_balltree_query_self_f32(pn_tree* t, size_t k, uint64_t* io, float* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F32, PN_KIND_BALL)); return t->knn_self(k, io, dd, false, nullptr, true); GUARD_END
+}
+int32_t pn_balltree_query_self_f64(pn_tree* t, size_t k, uint64_t* io, double* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_BALL)); return t->knn_self(k, io, dd, false, nullptr, true); GUARD_END
+}
+int32_t pn_tree_query_self_dev(pn_tree* t, size_t k, uint64_t* io, void* dd, void* stream, int32_t sync) {
+    GUARD_BEGIN
+    if (!t) return fail(PN_BAD_ARG, "tree is null");
+    return t->knn_self(k, io, dd, true, (cudaStream_t)stream, sync != 0);
+    GUARD_END
 }
 void pn_free(void* p) { free(p); }
 

@@ -359,9 +359,11 @@ constexpr int MAX_LISTS = 256;
 template <typename A, typename I>
 __global__ void merge_lists_kernel(const A* __restrict__ in_d, const I* __restrict__ in_i, uint32_t n_lists,
                                    uint32_t nq, uint32_t k, uint64_t* __restrict__ out_i, A* __restrict__ out_d,
-                                   uint32_t out_stride, uint32_t out_off, A* floor_d, uint32_t* floor_i) {
+                                   uint32_t out_stride, uint32_t out_off, A* floor_d, uint32_t* floor_i,
+                                   const uint32_t* __restrict__ row_map = nullptr) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    const size_t orow = row_map ? row_map[q] : q;  // self-query: results go to the original row of stored point q
     const I none = (I)~(I)0;
     A last_d = pos_inf<A>();
     uint64_t last_i = ~0ull;
@@ -369,8 +371,8 @@ __global__ void merge_lists_kernel(const A* __restrict__ in_d, const I* __restri
         for (uint32_t i = 0; i < k; ++i) {
             const A d = in_d[(size_t)q * k + i];
             const I id = in_i[(size_t)q * k + i];
-            out_d[(size_t)q * out_stride + out_off + i] = d;
-            out_i[(size_t)q * out_stride + out_off + i] = id == none ? ~0ull : (uint64_t)id;
+            out_d[orow * out_stride + out_off + i] = d;
+            out_i[orow * out_stride + out_off + i] = id == none ? ~0ull : (uint64_t)id;
             last_d = d; last_i = id == none ? ~0ull : (uint64_t)id;
         }
     } else {
@@ -389,8 +391,8 @@ __global__ void merge_lists_kernel(const A* __restrict__ in_d, const I* __restri
                 if (bl < 0 || d < bd || (d == bd && (uint64_t)id < bi)) { bd = d; bi = (uint64_t)id; bl = (int)l; }
             }
             if (bl >= 0) ++head[bl];
-            out_d[(size_t)q * out_stride + out_off + i] = bd;
-            out_i[(size_t)q * out_stride + out_off + i] = bi;
+            out_d[orow * out_stride + out_off + i] = bd;
+            out_i[orow * out_stride + out_off + i] = bi;
             last_d = bd; last_i = bi;
         }
     }

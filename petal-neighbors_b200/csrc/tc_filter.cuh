@@ -160,7 +160,6 @@ struct FilterArgs {
     const float* floor_d;
     const uint32_t* floor_i;
     unsigned long long* counters;  // [2] filter hits (elements passed to the exact rerank)
-    uint32_t dbg;                  // experiment switches (PN_TC_DEBUG): 1 no epilogue scan, 2 no MMA, 4 no TMEM load
 };
 
 // three-piece fp16 split of a non-negative fp32 value (residual < 2^-30 x in the normal range)

@@ -156,6 +156,17 @@ impl<'a, A: Element> BallTree<'a, A, Euclidean> {
         }
     }
 
+    /// Every stored point as a query (the loop of the reference's bench, benches/ball_tree.rs:53-59).
+    pub fn query_self(&self, k: usize) -> (Array2<usize>, Array2<A>) {
+        let mut idx = vec![0u64; self.n * k];
+        let mut dist = vec![A::zero(); self.n * k];
+        check(unsafe { A::ball_self(self.handle.0, k, idx.as_mut_ptr(), dist.as_mut_ptr()) });
+        (
+            Array2::from_shape_vec((self.n, k), idx.into_iter().map(|i| i as usize).collect()).unwrap(),
+            Array2::from_shape_vec((self.n, k), dist).unwrap(),
+        )
+    }
+
     /// reference src/ball_tree.rs:351-353
     pub fn num_points(&self) -> usize {
         self.n

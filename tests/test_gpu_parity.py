@@ -271,3 +271,21 @@ def test_config2_full_size_properties(pn, oracle):
     sample = np.arange(0, nq, 401)[:400]
     oi, od = oracle.brute_knn(pts, Q[sample], k)
     assert_knn_equal(idx[sample], dist[sample], oi, od)
+
+
+@pytest.mark.parametrize("dtype,n,d,k,algo", [
+    (np.float64, 10000, 3, 10, 0), (np.float32, 5000, 16, 10, 1), (np.float32, 6000, 16, 10, 2),
+    (np.float32, 3000, 5, 20, 0), (np.float32, 300, 2, 1, 0), (np.float32, 4100, 64, 5, 2),
+])
+def test_self_query(pn, oracle, dtype, n, d, k, algo):
+    """pn_balltree_query_self: every stored point is a query (benches/ball_tree.rs:53-59); row i is the
+    answer for points[i] regardless of the bucket order the engine stores the points in."""
+    from petal_neighbors_b200 import synth
+    pts = synth.uniform(n, d, 91 + n, dtype)
+    pts[n // 2] = pts[n // 3]                      # an exact duplicate: tie at distance 0 broken by index
+    bt = pn.BallTree.euclidean(pts, algo=algo, bucket_size=64)
+    idx, dist = bt.query_self(k)
+    oi, od = oracle.brute_knn(pts, pts, k)
+    assert_knn_equal(idx, dist, oi, od)
+    assert np.all(dist[:, 0] == 0)
+    assert bt.counters()["h2d_bytes"] == 0
