@@ -111,7 +111,13 @@ def _strides(points):
 
 
 def max_threads() -> int:
-    return int(lib().orc_max_threads())
+    """Host threads the baseline may use: the CPUs this process may run on.  (Not
+    omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, which would silently make the
+    'all cores' baseline single-threaded; the batch drivers pass num_threads explicitly.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def distance(x1, x2):
