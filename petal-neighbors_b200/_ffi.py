@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpetal_b200.so")
+LIB_PATH = os.environ.get("PN_B200_LIB") or os.path.join(_HERE, "lib", "libpetal_b200.so")  # PN_B200_LIB: diagnostic builds
 
 PN_OK, PN_EMPTY, PN_NOT_CONTIGUOUS, PN_BAD_ARG, PN_CUDA, PN_NCCL, PN_OOM = range(7)
 PN_KIND_BALL, PN_KIND_VP = 0, 1

@@ -100,7 +100,7 @@ struct Engine final : pn_tree {
         w_counters, w_out_i, w_out_d, w_counts, w_offsets, w_hits;
     DevTree<A> dt{};
     // tensor path (f32 only): augmented TF32 operands, see tc_filter.cuh
-    DevBuf d_baug, d_center, d_tile_pmax, w_aaug, w_qmargin;
+    DevBuf d_baug, d_center, w_aaug, w_qmargin;
     bool tensor_ready = false, last_used_tensor = false;
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
     float pmax = 0.f;      // max |s (p - center)|
@@ -113,7 +113,7 @@ struct Engine final : pn_tree {
             DeviceGuard g(device);
             for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &w_qraw, &w_q, &w_home,
                               &w_hist, &w_cursor, &w_order, &w_part_d, &w_part_i, &w_floor_d, &w_floor_i, &w_counters,
-                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &d_tile_pmax, &w_aaug, &w_qmargin})
+                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             if (stream) cudaStreamDestroy(stream);
@@ -228,14 +228,10 @@ struct Engine final : pn_tree {
             TRY(d_center.ensure(ft.dpad * 4));
             CU(cudaMemcpy(d_center.p, c.data(), ft.dpad * 4, cudaMemcpyHostToDevice));
             TRY(d_baug.ensure((size_t)ft.n * kp * 2));
-            TRY(w_counters.ensure(32));
-            CU(cudaMemset(w_counters.p, 0, 32));
-            const size_t n_tiles = (ft.n + tc::BN - 1) / tc::BN;
-            TRY(d_tile_pmax.ensure(n_tiles * 4));
-            CU(cudaMemset(d_tile_pmax.p, 0, n_tiles * 4));
+            TRY(w_counters.ensure(256));
+            CU(cudaMemset(w_counters.p, 0, 256));
             tc::build_baug_kernel<<<(unsigned)((ft.n + 127) / 128), 128, 0, stream>>>(d_pts.as<float>(), d_center.as<float>(), tscale, (uint32_t)ft.n, ft.d,
-                                                                                     ft.dpad, kp, d_baug.as<__half>(), w_counters.as<unsigned int>(),
-                                                                                     d_tile_pmax.as<unsigned int>());
+                                                                                     ft.dpad, kp, d_baug.as<__half>(), w_counters.as<unsigned int>());
             CU(cudaGetLastError());
             unsigned int bits = 0;
             CU(cudaMemcpyAsync(&bits, w_counters.p, 4, cudaMemcpyDeviceToHost, stream));
@@ -250,7 +246,7 @@ struct Engine final : pn_tree {
 
     template <int DVR, int K, int MT>
     int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
-        const size_t smem = 1024 + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES + 1024 + (size_t)4 * MT * 144 * 4;
+        const size_t smem = 1024 + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES + 1024 + (size_t)4 * MT * 144 * 4 + (size_t)4 * MT * K * 32 * 8;
         auto kern = tc::knn_filter_kernel<DVR, K, MT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (fa.nq + MT * tc::BM - 1) / (MT * tc::BM);
@@ -263,7 +259,7 @@ struct Engine final : pn_tree {
         const int mt = fa.nkc <= 6 ? 2 : 1;
         const size_t budget = 220 * 1024;
         fa.gs = fa.nkc == 1 ? 4 : (fa.nkc == 2 ? 2 : 1);
-        fa.stages = (uint32_t)std::min<size_t>(fa.gs > 1 ? 4 : 12, (budget - 7168 - (size_t)mt * fa.nkc * tc::A_CHUNK_BYTES) / (tc::CHUNK_BYTES * fa.gs));
+        fa.stages = (uint32_t)std::min<size_t>(fa.gs > 1 ? 4 : 12, (budget - 7168 - (size_t)4 * mt * K * 32 * 8 - (size_t)mt * fa.nkc * tc::A_CHUNK_BYTES) / (tc::CHUNK_BYTES * fa.gs));
         if (mt == 2) {
             if (dt.dv == 4) return launch_filter_t<4, K, 2>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 2>(map_a, fa, st);
@@ -285,9 +281,9 @@ struct Engine final : pn_tree {
             const uint32_t n_pass = (k + KP - 1) / KP;
             TRY(w_part_d.ensure((size_t)nq * KP * 4));
             TRY(w_part_i.ensure((size_t)nq * KP * 4));
-            TRY(w_counters.ensure(32));
+            TRY(w_counters.ensure(256));
             if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * 4)); TRY(w_floor_i.ensure((size_t)nq * 4)); }
-            CU(cudaMemsetAsync(w_counters.p, 0, 32, st));
+            CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
             tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(qpad, d_center.as<float>(), tscale, nq, ft.d, ft.dpad, kp, pmax,
                                                                     w_aaug.as<__half>(), w_qmargin.as<float>());
             CU(cudaGetLastError());
@@ -300,9 +296,6 @@ struct Engine final : pn_tree {
                 tc::FilterArgs fa{};
                 fa.t = *reinterpret_cast<DevTree<float>*>(&dt);
                 fa.q = reinterpret_cast<const float4*>(qpad); fa.q_margin = w_qmargin.as<float>();
-                fa.tile_pmax = d_tile_pmax.as<float>();
-                fa.kq = (float)(kp + 8) * 4.76837158203125e-07f;
-                fa.sqd = 6.2e-05f * std::sqrt((float)ft.d);
                 fa.nq = nq; fa.k = kk;
                 fa.n_tiles = (uint32_t)((ft.n + tc::BN - 1) / tc::BN);
                 fa.nkc = kp / tc::KC;
@@ -402,6 +395,15 @@ struct Engine final : pn_tree {
         unsigned long long c[4] = {0, 0, 0, 0};
         CU(cudaMemcpyAsync(c, w_counters.p, 32, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+#ifdef PN_TC_PROFILE
+        if (last_used_tensor && w_counters.cap >= 256) {
+            unsigned long long pc[20];
+            CU(cudaMemcpy(pc, (char*)w_counters.p + 64, sizeof(pc), cudaMemcpyDeviceToHost));
+            const double tiles = (double)((ft.n + tc::BN - 1) / tc::BN) * (double)((nq + 255) / 256);
+            fprintf(stderr, "[tc profile] cycles/tile  MMA thread: wait tempty %.0f | wait full %.0f | issue+commit %.0f   epilogue warp: wait tfull %.0f | TMEM read-out %.0f | scan+push %.0f | drain+margin %.0f\n",
+                    pc[0] / tiles, pc[1] / tiles, pc[2] / tiles, pc[6] / tiles, pc[7] / tiles, pc[8] / tiles, pc[9] / tiles);
+        }
+#endif
         counters.queries = nq;
         counters.pairs = last_used_tensor ? counters.filter_pairs : c[0];
         counters.node_visits = c[1];

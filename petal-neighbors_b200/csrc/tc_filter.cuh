@@ -40,6 +40,17 @@
 namespace petal {
 namespace tc {
 
+// -DPN_TC_PROFILE: per-role cycle accounting into counters[8..] (diagnostic builds only)
+#ifdef PN_TC_PROFILE
+#define PROF_DECL long long pt_ = clock64(), pc_[6] = {0, 0, 0, 0, 0, 0}
+#define PROF_ADD(i) do { long long n_ = clock64(); pc_[i] += n_ - pt_; pt_ = n_; } while (0)
+#define PROF_FLUSH(base) do { for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&a.counters[8 + (base) + i_], (unsigned long long)pc_[i_]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_ADD(i)
+#define PROF_FLUSH(base)
+#endif
+
 constexpr int BM = 128;            // queries per accumulator tile (TMEM lanes)
 constexpr int BN = 128;            // points per B tile (TMEM columns per accumulator stage)
 constexpr int KC = 32;             // fp16 elements per K chunk = one 64-byte swizzle row
@@ -59,31 +70,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Blocking wait.  The suspend-time hint lets the hardware put the waiting thread to sleep until the
+// phase completes (wake-up ~60 cycles) instead of re-issuing try_wait in a tight loop: the spinning
+// producer / MMA-issuer lanes share schedulers with epilogue warps and, being the highest warp ids,
+// would otherwise win arbitration and starve them.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// wait with back-off: many warps polling one barrier in a tight loop steal issue slots and barrier-unit
-// bandwidth from the TMA / MMA threads
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
-    uint32_t done;
-    for (;;) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P1;\n\t"
-            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (done) break;
-        if (ns) __nanosleep(ns);
-    }
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile(
@@ -142,13 +142,49 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                  : "memory");
 }
 
+// Per-thread running top-k kept in SHARED memory ([slot][lane], conflict-free): it is only touched
+// when the hit queue is drained, and keeping it out of the register file lets the epilogue hold a
+// whole 128-column accumulator stage in registers instead.  Same (distance, index) order and floor
+// semantics as TopK in kernels.cuh; only kth / thresh2 live in registers.
+struct SmemTopK {
+    float* sd;       // [k][32] distances of this warp, this lane's column = lane
+    uint32_t* si;    // [k][32]
+    float kth, t2, fd;
+    uint32_t kth_i, fi, k;
+    bool has_floor;
+    __device__ __forceinline__ void init(float* d, uint32_t* i, int lane, uint32_t k_, bool active) {
+        sd = d + lane; si = i + lane; k = k_;
+        for (uint32_t s = 0; s < k; ++s) { sd[s * 32] = pos_inf<float>(); si[s * 32] = NO_ID; }
+        kth = pos_inf<float>(); kth_i = NO_ID;
+        t2 = active ? pos_inf<float>() : -1.f;
+        has_floor = false; fd = 0.f; fi = 0;
+    }
+    __device__ __forceinline__ void set_floor(float d, uint32_t i) { has_floor = true; fd = d; fi = i; }
+    __device__ __forceinline__ void offer_sq(float s, uint32_t id) {
+        const float d = xsqrt(s);
+        if (has_floor && !(d > fd || (d == fd && id > fi))) return;
+        if (!(d < kth || (d == kth && id < kth_i))) return;
+        uint32_t p = k - 1;  // sorted insertion from the tail
+        while (p > 0) {
+            const float pd = sd[(p - 1) * 32];
+            const uint32_t pi = si[(p - 1) * 32];
+            if (!(d < pd || (d == pd && id < pi))) break;
+            sd[p * 32] = pd; si[p * 32] = pi;
+            --p;
+        }
+        sd[p * 32] = d; si[p * 32] = id;
+        kth = sd[(k - 1) * 32]; kth_i = si[(k - 1) * 32];
+        t2 = thresh2(kth);
+    }
+    __device__ __forceinline__ void store(float* out_d, uint32_t* out_i) const {
+        for (uint32_t s = 0; s < k; ++s) { out_d[s] = sd[s * 32]; out_i[s] = si[s * 32]; }
+    }
+};
+
 struct FilterArgs {
     DevTree<float> t;
     const float4* q;       // nq x dpad exact zero-padded queries (rerank)
-    const float* q_margin; // nq: scaled norm |q'| (+inf when outside the fp16 range)
-    const float* tile_pmax; // n_tiles: max |p'| over the points of each B tile
-    float kq;              // (Kp + 8) 2^-21
-    float sqd;             // 2^-14 sqrt(d)
+    const float* q_margin; // nq: E_q in scaled units (+inf when the query leaves the fp16 range)
     uint32_t nq, k;
     uint32_t n_tiles;      // ceil(n / BN)
     uint32_t nkc;          // K chunks (Kp / 32)
@@ -172,8 +208,7 @@ __device__ __forceinline__ void split3_f16(float x, __half& h1, __half& h2, __ha
 
 // B operand: one fp16 row per stored point (bucket order).  pmax_bits receives max |p'| (float bits).
 __global__ void build_baug_kernel(const float* __restrict__ pts, const float* __restrict__ center, float scale, uint32_t n,
-                                  uint32_t d, uint32_t dpad, uint32_t kp, __half* __restrict__ baug, unsigned int* pmax_bits,
-                                  unsigned int* tile_pmax_bits) {
+                                  uint32_t d, uint32_t dpad, uint32_t kp, __half* __restrict__ baug, unsigned int* pmax_bits) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = pts + (size_t)i * dpad;
@@ -189,9 +224,7 @@ __global__ void build_baug_kernel(const float* __restrict__ pts, const float* __
     split3_f16(nrm, h1, h2, h3);
     const __half one = __float2half_rn(1.f);
     o[kp - 6] = one; o[kp - 5] = one; o[kp - 4] = one; o[kp - 3] = h1; o[kp - 2] = h2; o[kp - 1] = h3;
-    const unsigned int nb = __float_as_uint(sqrtf(nrm) * 1.000001f);
-    atomicMax(pmax_bits, nb);
-    atomicMax(tile_pmax_bits + i / BN, nb);
+    atomicMax(pmax_bits, __float_as_uint(sqrtf(nrm) * 1.000001f));
 }
 
 // A operand + per-query margin E_q (scaled units)
@@ -215,8 +248,10 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
     split3_f16(in_range ? nrm : 0.f, h1, h2, h3);
     const __half one = __float2half_rn(1.f);
     o[kp - 6] = h1; o[kp - 5] = h2; o[kp - 4] = h3; o[kp - 3] = one; o[kp - 2] = one; o[kp - 1] = one;
-    (void)pmax;
-    q_margin[i] = in_range ? qn : pos_inf<float>();
+    const float sn = qn + pmax;
+    const float e = 1.01f * 0.001953125f * qn * pmax + 6.2e-05f * sqrtf((float)d) * (qn + 2.f * pmax) +
+                    (float)(kp + 8) * 4.76837158203125e-07f * sn * sn;
+    q_margin[i] = in_range ? e : pos_inf<float>();
 }
 
 template <int DVR, int K, int MT>
@@ -236,6 +271,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
     uint32_t* qbuf = tmem_slot + 4;  // per epilogue warp: QWORDS x u32 of queue / hand-over scratch
     constexpr int QWORDS = 144;
+    float* tk_d = reinterpret_cast<float*>(qbuf + 4 * MT * QWORDS);   // [EPI_WARPS][K][32]
+    uint32_t* tk_i = reinterpret_cast<uint32_t*>(tk_d + 4 * MT * K * 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int EPI_WARPS = 4 * MT;
@@ -294,10 +331,12 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t total = a.n_tiles * a.nkc;
             mbar_wait(a_bar, 0);
             uint32_t it = 0;
+            PROF_DECL;
             for (uint32_t j = 0; j < a.n_tiles; ++j) {
                 const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
                 mbar_wait(&tempty_bar[as * MT + mt], aph ^ 1u);  // this subtile's accumulator stage has been read out
                 tc_fence_after();
+                PROF_ADD(0);
                 const uint32_t d_tmem = tmem_base + (as * MT + mt) * BN;
                 for (uint32_t c = 0; c < a.nkc; ++c, ++it) {
                     const uint32_t g = it / a.gs, gi = it % a.gs, s = g % a.stages;
@@ -305,6 +344,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         mbar_wait(&full_bar[s], (g / a.stages) & 1u);
                         tc_fence_after();
                     }
+                    PROF_ADD(1);
                     // descriptors advance in 16-byte units: +2 per K step of 16 fp16, whole chunks per slot
                     const uint64_t bd = b_desc0 + (uint64_t)((s * a.gs + gi) * (CHUNK_BYTES >> 4));
                     const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
@@ -314,7 +354,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (gi + 1 == a.gs || it + 1 == total) tc_commit(&empty_bar[s]);  // group consumed by this subtile
                 }
                 tc_commit(&tfull_bar[as * MT + mt]);  // this subtile's accumulator is complete
+                PROF_ADD(2);
             }
+            if (mt == 0) PROF_FLUSH(0);
         }
     } else {
         // ================= epilogue: one query row per thread =================
@@ -333,11 +375,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         unsigned char* q_owner = reinterpret_cast<unsigned char*>(q_prow + 64);
         float* x_s = reinterpret_cast<float*>(q_prow + 80);
         uint32_t* x_id = q_prow + 112;
-        TopK<float, K> topk;
-        topk.init(active, a.k);
+        SmemTopK topk;
+        topk.init(tk_d + warp * (K * 32), tk_i + warp * (K * 32), lane, a.k, active);
         if (a.floor_d && active) topk.set_floor(a.floor_d[qrow], a.floor_i[qrow]);
-        const float qnorm = active ? a.q_margin[qrow] : 0.f;  // scaled |q'|
-        float margin = 0.f;                                   // E_q for the current tile
+        const float margin = active ? a.q_margin[qrow] : 0.f;  // E_q (scaled units)
         const float t2s = a.t2_scale;
         float theta = active ? pos_inf<float>() : -pos_inf<float>();
         const unsigned full = 0xffffffffu;
@@ -419,8 +460,12 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const int i = __ffs(bits) - 1;
                     bits &= bits - 1;
                     const int slot = qn + __popc(mask & lt_mask);
-                    q_prow[slot] = j * BN + col0 + i;
+                    const uint32_t prow = j * BN + col0 + i;
+                    q_prow[slot] = prow;
                     q_owner[slot] = (unsigned char)lane;
+                    // the exact rerank happens tiles later: start pulling the candidate's row and id now
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.pts + (size_t)prow * DV));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.ids + prow));
                 }
                 qn += __popc(mask);
                 hits += __popc(mask);
@@ -438,49 +483,39 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         };
 
-        // software pipeline over the 32-column groups of all tiles: while group g is tested, group
-        // g+1 (of this tile, or the first group of the next tile) is already on its way from TMEM
-        uint32_t ra[32], rb[32];
+        // The whole 128-column accumulator stage is pulled into registers at once and released
+        // BEFORE it is tested: with only two stages in TMEM the MMA -> read-out -> release loop of a
+        // stage is the critical path, so nothing but the TMEM loads may sit inside it.
         constexpr int G = BN / 32;
+        uint32_t r[G][32];
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        mbar_wait(&tfull_bar[mt], 0);
-        tc_fence_after();
-        tmem_ld32_issue(tmem_base + lane_off + mt * BN, ra);
+        PROF_DECL;
         for (uint32_t j = 0; j < a.n_tiles; ++j) {
-            const uint32_t as = j % NUM_ACC;
+            const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
+            PROF_ADD(3);
+            mbar_wait(&tfull_bar[as * MT + mt], aph);
+            tc_fence_after();
+            PROF_ADD(0);
             const uint32_t taddr = tmem_base + lane_off + (as * MT + mt) * BN;
-            {   // rounding margin for this tile: E_q with the tile's own bound on |p'|
-                const float pm = __ldg(a.tile_pmax + j), sn = qnorm + pm;
-                margin = 1.01f * 0.001953125f * qnorm * pm + a.sqd * (qnorm + 2.f * pm) + a.kq * sn * sn;
-                if (active) theta = xadd(xmul(topk.t2, t2s), margin);
-            }
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                uint32_t (&cur)[32] = (g & 1) ? rb : ra;
-                uint32_t (&nxt)[32] = (g & 1) ? ra : rb;
-                tmem_ld_wait(cur);
-                if (g + 1 < G) {
-                    tmem_ld32_issue(taddr + (g + 1) * 32, nxt);
-                } else {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);  // the stage is free once it is in registers
-                    if (j + 1 < a.n_tiles) {
-                        const uint32_t as1 = (j + 1) % NUM_ACC, aph1 = ((j + 1) / NUM_ACC) & 1u;
-                        mbar_wait(&tfull_bar[as1 * MT + mt], aph1);
-                        tc_fence_after();
-                        tmem_ld32_issue(tmem_base + lane_off + (as1 * MT + mt) * BN, nxt);
-                    }
-                }
-                scan32(cur, j, g * 32);
-            }
+            for (int g = 0; g < G; ++g) tmem_ld32_issue(taddr + g * 32, r[g]);
+#pragma unroll
+            for (int g = 0; g < G; ++g) tmem_ld_wait(r[g]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
+            PROF_ADD(1);
+#pragma unroll
+            for (int g = 0; g < G; ++g) scan32(r[g], j, g * 32);
+            PROF_ADD(2);
             // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
-            if (((j & 15u) == 15u) && qn > 0) { drain(qn); qn = 0; __syncwarp(); }
+            if (((j & 31u) == 31u) && qn > 0) { drain(qn); qn = 0; __syncwarp(); }
         }
+        if (warp == 0 && lane == 0) PROF_FLUSH(6);
         if (qn > 0) { drain(qn); qn = 0; }
         if (active) {
             const size_t base = (size_t)qrow * a.k;
-            topk.store(a.part_d + base, a.part_i + base, a.k);
+            topk.store(a.part_d + base, a.part_i + base);
         }
         if (a.counters && lane == 0) atomicAdd(&a.counters[2], hits);
     }
