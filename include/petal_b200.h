@@ -166,6 +166,12 @@ int32_t pn_balltree_query_self_f64(pn_tree *tree, size_t k, uint64_t *idx_out, d
 int32_t pn_tree_query_self_dev(pn_tree *tree, size_t k, uint64_t *idx_dev, void *dist_dev, void *stream,
                                int32_t sync);
 
+/* --- distance::pairwise with the Euclidean metric (src/distance.rs:58-74): dense symmetric n x n
+ * matrix of exact distances, zero diagonal; `out` is caller-allocated row-major n x n host memory.
+ * (A "next" row of the scope table: not on the tree path, same bit-exact fold.) */
+int32_t pn_pairwise_f32(int32_t device, const float *x, size_t n, size_t d, size_t row_stride, float *out);
+int32_t pn_pairwise_f64(int32_t device, const double *x, size_t n, size_t d, size_t row_stride, double *out);
+
 void pn_free(void *p);
 
 /* --- device-resident variants (queries and outputs already in HBM on the tree's device).

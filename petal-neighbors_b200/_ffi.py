@@ -24,6 +24,7 @@ EXPORTS = [
     "pn_balltree_query_radius_f32", "pn_balltree_query_radius_f64",
     "pn_vptree_query_nearest_f32", "pn_vptree_query_nearest_f64",
     "pn_balltree_query_self_f32", "pn_balltree_query_self_f64", "pn_tree_query_self_dev",
+    "pn_pairwise_f32", "pn_pairwise_f64",
     "pn_free", "pn_tree_query_knn_dev", "pn_merge_topk_dev",
     "pn_tree_get_info", "pn_tree_get_counters", "pn_tree_get_layout",
 ]
@@ -84,6 +85,9 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_int32
             f.argtypes = [vp, vp, sz, sz, vp, vp]
+        f = getattr(L, f"pn_pairwise_{sfx}")
+        f.restype = C.c_int32
+        f.argtypes = [C.c_int32, vp, sz, sz, sz, vp]
         f = getattr(L, f"pn_balltree_query_self_{sfx}")
         f.restype = C.c_int32
         f.argtypes = [vp, sz, vp, vp]

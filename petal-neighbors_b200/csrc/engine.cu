@@ -159,7 +159,7 @@ struct Engine final : pn_tree {
     // ------------------------------------------------------------------------------------------
     template <int DVR, int K, int KIND>
     int launch_knn_t(const KnnArgs<A>& a, dim3 grid, cudaStream_t st) {
-        size_t smem = TILE_BYTES + (DVR == 0 ? (size_t)TQ * ft.dpad * sizeof(A) : 0);
+        size_t smem = 2 * TILE_BYTES + (DVR == 0 ? (size_t)TQ * ft.dpad * sizeof(A) : 0);
         auto kern = knn_tile_kernel<A, DVR, K, KIND>;
         if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, TQ, smem, st>>>(a);
@@ -684,6 +684,32 @@ static int merge_topk_dev(int device, const uint64_t* idx_lists, const A* dist_l
     return PN_OK;
 }
 
+template <typename A>
+static int pairwise_host(int device, const A* x, size_t n, size_t d, size_t row_stride, A* out) {
+    if (n == 0) return PN_OK;
+    if (!x || !out) return fail(PN_BAD_ARG, "null pointer");
+    if (d == 0 || n >= (1ull << 31) || (n > 1 && row_stride < d)) return fail(PN_BAD_ARG, "bad shape");
+    int dev = device;
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return fail(PN_CUDA, "no CUDA device available (there is no CPU fallback)"); }
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+    DevBuf dx, dout;
+    int rc = dx.ensure(n * d * sizeof(A));
+    if (rc == PN_OK) rc = dout.ensure(n * n * sizeof(A));
+    if (rc == PN_OK) {
+        cudaError_t e = cudaMemcpy2D(dx.p, d * sizeof(A), x, row_stride * sizeof(A), d * sizeof(A), n, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32)), block(32, 32);
+            pairwise_kernel<A><<<grid, block>>>(dx.as<A>(), (uint32_t)n, (uint32_t)d, dout.as<A>());
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, n * n * sizeof(A), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(PN_CUDA, std::string("pairwise: ") + cudaGetErrorString(e));
+    }
+    dx.release(); dout.release();
+    return rc;
+}
+
 }  // namespace petal
 
 // ================================= C ABI ======================================================
@@ -764,6 +790,12 @@ int32_t pn_tree_query_self_dev(pn_tree* t, size_t k, uint64_t* io, void* dd, voi
     if (!t) return fail(PN_BAD_ARG, "tree is null");
     return t->knn_self(k, io, dd, true, (cudaStream_t)stream, sync != 0);
     GUARD_END
+}
+int32_t pn_pairwise_f32(int32_t device, const float* x, size_t n, size_t d, size_t row_stride, float* out) {
+    GUARD_BEGIN return pairwise_host<float>(device, x, n, d, row_stride, out); GUARD_END
+}
+int32_t pn_pairwise_f64(int32_t device, const double* x, size_t n, size_t d, size_t row_stride, double* out) {
+    GUARD_BEGIN return pairwise_host<double>(device, x, n, d, row_stride, out); GUARD_END
 }
 void pn_free(void* p) { free(p); }
 

@@ -19,7 +19,7 @@ namespace petal {
 
 constexpr int TQ = 128;           // queries per CTA of the tile scan, one per thread
 constexpr int RP = 8;             // points per register tile (independent fold chains per thread)
-constexpr int TILE_BYTES = 16384; // shared-memory point tile
+constexpr int TILE_BYTES = 16384; // one shared-memory point tile (two are in flight)
 constexpr int MAX_STACK = 40;     // traversal stack depth (tree depth <= 32)
 constexpr uint32_t NO_ID = 0xFFFFFFFFu;
 
@@ -65,6 +65,30 @@ __device__ __forceinline__ double2 vzero(double) { return make_double2(0., 0.); 
 // cheap squared test only filters, the exact test runs on the sqrt'd value.)
 __device__ __forceinline__ float  thresh2(float kth)  { return xadd(xmul(xmul(kth, kth), 1.00000095367431640625f), FLT_MIN); }
 __device__ __forceinline__ double thresh2(double kth) { return xadd(xmul(xmul(kth, kth), 1.0 + 1.7763568394002505e-15), DBL_MIN); }
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (leaf buckets are contiguous,
+// 16-byte aligned spans, so no tensor map is needed) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_bar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(bar)));
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "BW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra BW_DONE;\n\t"
+        "bra BW_LOOP;\n\t"
+        "BW_DONE:\n\t"
+        "}" ::"r"(smem_addr_u32(bar)), "r"(parity), "r"(100000u) : "memory");
+}
 
 // ---- flattened tree as seen by the device --------------------------------------------------
 template <typename A>
@@ -134,6 +158,51 @@ struct TopK {
     }
 };
 
+// ---- the same container with runtime-indexed arrays, i.e. deliberately in thread-local memory (L1):
+// the tile scan touches its list only on the rare accepted candidate (~k ln(N/k) times per query)
+// while its hot loop is bound by instruction issue, so registers are worth more as occupancy.
+template <typename A, int K>
+struct TopKLocal {
+    A kd[K];
+    uint32_t ki[K];
+    A t2, fd, kth_d;
+    uint32_t fi, kth_i, k;
+    bool has_floor;
+    __device__ __forceinline__ A kth() const { return kth_d; }
+    __device__ __forceinline__ void init(bool active, uint32_t k_) {
+        k = k_;
+#pragma unroll 1
+        for (uint32_t i = 0; i < k; ++i) { kd[i] = pos_inf<A>(); ki[i] = NO_ID; }
+        kth_d = pos_inf<A>(); kth_i = NO_ID;
+        t2 = active ? pos_inf<A>() : A(-1);
+        has_floor = false; fd = A(0); fi = 0;
+    }
+    __device__ __forceinline__ void set_floor(A d, uint32_t i) { has_floor = true; fd = d; fi = i; }
+    __device__ __noinline__ void offer(A d, uint32_t id) {
+        if (has_floor && !(d > fd || (d == fd && id > fi))) return;
+        if (!(d < kth_d || (d == kth_d && id < kth_i))) return;
+        uint32_t p = k - 1;
+#pragma unroll 1
+        while (p > 0) {
+            const A pd = kd[p - 1];
+            const uint32_t pi = ki[p - 1];
+            if (!(d < pd || (d == pd && id < pi))) break;
+            kd[p] = pd; ki[p] = pi;
+            --p;
+        }
+        kd[p] = d; ki[p] = id;
+        kth_d = kd[k - 1]; kth_i = ki[k - 1];
+        t2 = thresh2(kth_d);
+    }
+    __device__ __forceinline__ void offer_sq(A s, uint32_t id) { offer(xsqrt(s), id); }
+    __device__ __forceinline__ void store(A* out_d, uint32_t* out_i, uint32_t) const {
+#pragma unroll 1
+        for (uint32_t i = 0; i < k; ++i) { out_d[i] = kd[i]; out_i[i] = ki[i]; }
+    }
+};
+template <typename A, int K> struct TileTopK { using type = TopKLocal<A, K>; };
+template <typename A> struct TileTopK<A, 1> { using type = TopK<A, 1>; };
+
 // ---- block-wide counts of up to four predicates with ONE barrier ---------------------------
 struct VoteBuf { uint32_t v[2][TQ / 32][4]; };
 __device__ __forceinline__ void block_counts(VoteBuf& vb, int& parity, bool a, bool b, bool c, bool d,
@@ -177,9 +246,10 @@ template <typename A, int DVR, int K, int KIND>
 __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
     using V = typename VT<A>::V;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    V* ps = reinterpret_cast<V*>(smem_raw);
-    V* qs = reinterpret_cast<V*>(smem_raw + TILE_BYTES);  // generic-d only: [dv][TQ]
+    V* ps0 = reinterpret_cast<V*>(smem_raw);                    // tile buffers 0 / 1
+    V* qs = reinterpret_cast<V*>(smem_raw + 2 * TILE_BYTES);    // generic-d only: [dv][TQ]
     __shared__ VoteBuf votes;
+    __shared__ __align__(8) uint64_t tile_bar[2];
     __shared__ unsigned long long s_pairs, s_visits;
 
     const DevTree<A>& t = a.t;
@@ -189,7 +259,11 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
     const uint32_t qid = active ? (a.qorder ? a.qorder[slot] : slot) : 0;
     const int DV = DVR > 0 ? DVR : (int)t.dv;
     const uint32_t k = a.k;
-    if (tid == 0) { s_pairs = 0; s_visits = 0; }
+    if (tid == 0) {
+        s_pairs = 0; s_visits = 0;
+        bulk_bar_init(&tile_bar[0]); bulk_bar_init(&tile_bar[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     V qreg[DVR > 0 ? DVR : 1];
     if (DVR > 0) {
@@ -201,7 +275,7 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
     }
     __syncthreads();
 
-    TopK<A, K> topk;
+    typename TileTopK<A, K>::type topk;
     topk.init(active, k);
     if (a.floor_d && active) topk.set_floor(a.floor_d[qid], a.floor_i[qid]);
 
@@ -222,40 +296,56 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
 
     // leaf loops src/ball_tree.rs:162-173, 217-226: all points of bucket b against all 128 queries
     const int TP = max(RP, (int)(TILE_BYTES / (t.dpad * sizeof(A))) / RP * RP);
+    // Tiles are staged by TMA bulk copies (cp.async.bulk, one elected thread) into two buffers: the copy
+    // of tile i+1 overlaps the distance folds on tile i; one barrier per tile protects buffer reuse.
+    uint32_t tile_use[2] = {0, 0};  // uses of each buffer so far (block-uniform) -> mbarrier phase parity
     auto scan_bucket = [&](uint32_t b, bool need) {
         const uint32_t lo = t.bucket_lo[b], hi = t.bucket_hi[b];
+        if (hi <= lo) return;
         const bool warp_need = __any_sync(0xffffffffu, need);
-        for (uint32_t p0 = lo; p0 < hi; p0 += TP) {
-            const int np = min((int)(hi - p0), TP);
-            __syncthreads();
-            const V* src = t.pts + (size_t)p0 * DV;
-            for (int i = tid; i < np * DV; i += TQ) ps[i] = __ldg(src + i);
-            __syncthreads();
-            if (!warp_need) continue;
-            if (active) my_pairs += np;
-            for (int pp = 0; pp < np; pp += RP) {
-                A acc[RP];
+        const uint32_t row_bytes = t.dpad * (uint32_t)sizeof(A);
+        const uint32_t n_tiles = (hi - lo + TP - 1) / TP;
+        auto issue = [&](uint32_t i) {  // tid == 0 only
+            const uint32_t p0 = lo + i * TP;
+            const uint32_t np = min(hi - p0, (uint32_t)TP);
+            bulk_load(reinterpret_cast<unsigned char*>(ps0) + (i & 1u) * TILE_BYTES, t.pts + (size_t)p0 * DV, np * row_bytes, &tile_bar[i & 1u]);
+        };
+        if (tid == 0) { issue(0); if (n_tiles > 1) issue(1); }
+        for (uint32_t i = 0; i < n_tiles; ++i) {
+            const uint32_t p0 = lo + i * TP;
+            const int np = (int)min(hi - p0, (uint32_t)TP);
+            const uint32_t bsel = i & 1u;
+            const V* ps = reinterpret_cast<const V*>(reinterpret_cast<const unsigned char*>(ps0) + bsel * TILE_BYTES);
+            bulk_wait(&tile_bar[bsel], tile_use[bsel] & 1u);
+            ++tile_use[bsel];
+            if (warp_need) {
+                if (active) my_pairs += np;
+                for (int pp = 0; pp < np; pp += RP) {
+                    A acc[RP];
 #pragma unroll
-                for (int r = 0; r < RP; ++r) acc[r] = A(0);
-                if (DVR > 0) {
+                    for (int r = 0; r < RP; ++r) acc[r] = A(0);
+                    if (DVR > 0) {
 #pragma unroll
-                    for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc) {
+                        for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc) {
 #pragma unroll
-                        for (int r = 0; r < RP; ++r) acc[r] = fold(acc[r], qreg[jc], ps[(pp + r) * DVR + jc]);
+                            for (int r = 0; r < RP; ++r) acc[r] = fold(acc[r], qreg[jc], ps[(pp + r) * DVR + jc]);
+                        }
+                    } else {
+                        for (int jc = 0; jc < DV; ++jc) {
+                            const V qv = qs[jc * TQ + tid];
+#pragma unroll
+                            for (int r = 0; r < RP; ++r) acc[r] = fold(acc[r], qv, ps[(pp + r) * DV + jc]);
+                        }
                     }
-                } else {
-                    for (int jc = 0; jc < DV; ++jc) {
-                        const V qv = qs[jc * TQ + tid];
 #pragma unroll
-                        for (int r = 0; r < RP; ++r) acc[r] = fold(acc[r], qv, ps[(pp + r) * DV + jc]);
+                    for (int r = 0; r < RP; ++r) {
+                        if (pp + r < np && acc[r] <= topk.t2)
+                            topk.offer_sq(acc[r], __ldg(t.ids + p0 + pp + r));
                     }
-                }
-#pragma unroll
-                for (int r = 0; r < RP; ++r) {
-                    if (pp + r < np && acc[r] <= topk.t2)
-                        topk.offer_sq(acc[r], __ldg(t.ids + p0 + pp + r));
                 }
             }
+            __syncthreads();  // everyone is done with this buffer: it may be refilled
+            if (tid == 0 && i + 2 < n_tiles) issue(i + 2);
         }
     };
 
@@ -579,6 +669,32 @@ __global__ void segment_sort_kernel(const uint64_t* __restrict__ offsets, uint64
             __syncwarp();
         }
     }
+}
+
+
+// ---- distance::pairwise (reference src/distance.rs:58-74): dense symmetric n x n matrix of exact
+// fold distances.  A 32 x 32 output tile per block; the two 32-row panels are staged in shared
+// memory in chunks of 32 dimensions, every thread keeps its sequential sum across chunks, so the
+// result is bit-identical to the reference's per-pair fold (and symmetric: (a-b)^2 == (b-a)^2). --
+template <typename A>
+__global__ void pairwise_kernel(const A* __restrict__ x, uint32_t n, uint32_t d, A* __restrict__ out) {
+    __shared__ A pi[32][33], pj[32][33];
+    const uint32_t i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const uint32_t ti = threadIdx.y, tj = threadIdx.x;
+    A acc = A(0);
+    for (uint32_t c0 = 0; c0 < d; c0 += 32) {
+        const uint32_t c = c0 + tj;
+        pi[ti][tj] = (i0 + ti < n && c < d) ? x[(size_t)(i0 + ti) * d + c] : A(0);
+        pj[ti][tj] = (j0 + ti < n && c < d) ? x[(size_t)(j0 + ti) * d + c] : A(0);
+        __syncthreads();
+        const uint32_t lim = min(32u, d - c0);
+        for (uint32_t k = 0; k < lim; ++k) {
+            const A t = xsub(pi[ti][k], pj[tj][k]);
+            acc = xadd(acc, xmul(t, t));
+        }
+        __syncthreads();
+    }
+    if (i0 + ti < n && j0 + tj < n) out[(size_t)(i0 + ti) * n + (j0 + tj)] = xsqrt(acc);
 }
 
 }  // namespace petal

@@ -58,3 +58,25 @@ class Euclidean(Metric):
 
     def distance_to_rdistance(self, d):
         return d * d
+
+
+def pairwise(x, metric: Metric = None, device: int = -1):
+    """distance::pairwise (src/distance.rs:58-74) on the GPU: dense symmetric n x n matrix of exact
+    Euclidean distances (bit-identical to the reference fold).  Only `Euclidean` is offered."""
+    from . import _ffi, _check  # late import: _check lives in the package root
+    if metric is not None and not isinstance(metric, Euclidean):
+        raise TypeError("only Euclidean is offered by the B200 engine")
+    x = np.asarray(x)
+    if x.ndim != 2:
+        raise ValueError("x must be 2-D")
+    if x.dtype not in (np.float32, np.float64):
+        raise TypeError("A must be f32 or f64")
+    if x.shape[0] and x.strides[1] != x.dtype.itemsize and x.shape[1] > 1:
+        x = np.ascontiguousarray(x)
+    n, d = x.shape
+    out = np.zeros((n, n), dtype=x.dtype)
+    if n >= 2:
+        fn = getattr(_ffi.lib(), "pn_pairwise_f32" if x.dtype == np.float32 else "pn_pairwise_f64")
+        rs = x.strides[0] // x.dtype.itemsize
+        _check(fn(device, x.ctypes.data, n, d, rs, out.ctypes.data))
+    return out

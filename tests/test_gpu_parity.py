@@ -289,3 +289,16 @@ def test_self_query(pn, oracle, dtype, n, d, k, algo):
     assert_knn_equal(idx, dist, oi, od)
     assert np.all(dist[:, 0] == 0)
     assert bt.counters()["h2d_bytes"] == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,d", [(2, 2), (1, 3), (33, 1), (100, 7), (257, 40), (64, 130)])
+def test_pairwise(pn, oracle, dtype, n, d):
+    """distance::pairwise (src/distance.rs:58-74): KAT :130-141 and bit-exact parity with the oracle."""
+    assert pn.distance.pairwise(np.array([[3., 4.], [0., 0.]])).tolist() == [[0., 5.], [5., 0.]]
+    assert pn.distance.pairwise(np.array([[0.]])).tolist() == [[0.]]
+    x = np.random.default_rng(n * d).random((n, d)).astype(dtype)
+    got = pn.distance.pairwise(x, pn.distance.Euclidean())
+    want = oracle.pairwise(x)
+    assert np.array_equal(bits(got), bits(want))
+    assert np.array_equal(got, got.T) and np.all(np.diag(got) == 0)
