@@ -19,6 +19,7 @@ rust/petal-neighbors-b200/, see INTEGRATION.md.)
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -229,12 +230,16 @@ class BallTree(_Tree):
         idx_p = C.POINTER(C.c_uint64)()
         fn = getattr(L, f"pn_balltree_query_radius_{self._sfx}")
         _check(fn(self._h, Q.ctypes.data if nq else None, nq, qs, self.dtype.type(radius), C.byref(offs_p), C.byref(idx_p)))
-        try:
-            offsets = np.ctypeslib.as_array(offs_p, shape=(nq + 1,)).copy()
-            total = int(offsets[-1])
-            indices = np.ctypeslib.as_array(idx_p, shape=(total,)).copy() if total else np.empty(0, np.uint64)
-        finally:
-            L.pn_free(offs_p)
+        # zero-copy: the engine-allocated buffers back the arrays and are released with pn_free when
+        # the arrays are garbage-collected (the Rust shim's Vec::from_raw_parts equivalent)
+        offsets = np.ctypeslib.as_array(offs_p, shape=(nq + 1,))
+        weakref.finalize(offsets, L.pn_free, C.cast(offs_p, C.c_void_p))
+        total = int(offsets[-1])
+        if total:
+            indices = np.ctypeslib.as_array(idx_p, shape=(total,))
+            weakref.finalize(indices, L.pn_free, C.cast(idx_p, C.c_void_p))
+        else:
+            indices = np.empty(0, np.uint64)
             L.pn_free(idx_p)
         return offsets, indices
 

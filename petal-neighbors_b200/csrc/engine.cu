@@ -99,6 +99,9 @@ struct Engine final : pn_tree {
     DevBuf w_qraw, w_q, w_home, w_hist, w_cursor, w_order, w_part_d, w_part_i, w_floor_d, w_floor_i,
         w_counters, w_out_i, w_out_d, w_counts, w_offsets, w_hits;
     DevTree<A> dt{};
+    void* pin_stage[2] = {nullptr, nullptr};  // pinned D2H staging for the variable-length radius output
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    static constexpr size_t PIN_BYTES = 16u << 20;
     // tensor path (f32 only): augmented TF32 operands, see tc_filter.cuh
     DevBuf d_baug, d_center, w_aaug, w_qmargin;
     bool tensor_ready = false, last_used_tensor = false;
@@ -116,6 +119,7 @@ struct Engine final : pn_tree {
                               &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
+            for (int i = 0; i < 2; ++i) { if (pin_stage[i]) cudaFreeHost(pin_stage[i]); if (pin_ev[i]) cudaEventDestroy(pin_ev[i]); }
             if (stream) cudaStreamDestroy(stream);
         }
     }
@@ -473,6 +477,43 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 
+    // Device u32 indices -> host u64 indices: D2H in 16 MB pieces through two pinned buffers; while piece
+    // p+1 is in flight, piece p is widened into the (freshly allocated, not yet faulted) destination by a
+    // few host threads -- page-faulting and widening, not the DMA, are the slow part.
+    int copy_out_widen(uint64_t* dst, const uint32_t* src_dev, size_t count, cudaStream_t st) {
+        if (count == 0) return PN_OK;
+        for (int i = 0; i < 2; ++i) {
+            if (!pin_stage[i]) CU(cudaHostAlloc(&pin_stage[i], PIN_BYTES, cudaHostAllocDefault));
+            if (!pin_ev[i]) CU(cudaEventCreateWithFlags(&pin_ev[i], cudaEventDisableTiming));
+        }
+        const size_t per = PIN_BYTES / 4;
+        const size_t pieces = (count + per - 1) / per;
+        auto issue = [&](size_t p) -> int {
+            const size_t off = p * per, cnt = std::min(per, count - off);
+            CU(cudaMemcpyAsync(pin_stage[p & 1], src_dev + off, cnt * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(pin_ev[p & 1], st));
+            return PN_OK;
+        };
+        TRY(issue(0));
+        const unsigned nt = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
+        for (size_t p = 0; p < pieces; ++p) {
+            CU(cudaEventSynchronize(pin_ev[p & 1]));
+            if (p + 1 < pieces) TRY(issue(p + 1));  // the other buffer was consumed in the previous iteration
+            const size_t off = p * per, cnt = std::min(per, count - off);
+            const uint32_t* s32 = (const uint32_t*)pin_stage[p & 1];
+            uint64_t* d64 = dst + off;
+            std::vector<std::thread> th;
+            const size_t chunk = (cnt + nt - 1) / nt;
+            for (unsigned t = 1; t < nt; ++t) {
+                const size_t b = t * chunk, e = std::min(cnt, b + chunk);
+                if (b < e) th.emplace_back([=] { for (size_t i = b; i < e; ++i) d64[i] = s32[i]; });
+            }
+            for (size_t i = 0, e = std::min(cnt, chunk); i < e; ++i) d64[i] = s32[i];
+            for (auto& x : th) x.join();
+        }
+        return PN_OK;
+    }
+
     // every stored point is a query (benches/ball_tree.rs:53-59): no H2D at all
     int knn_self(size_t k, uint64_t* idx, void* distv, bool dev, cudaStream_t st, bool sync) override {
         if (host_only) return fail(PN_CUDA, "tree was built with PN_FLAG_HOST_ONLY: no device, and there is no CPU fallback");
@@ -549,11 +590,11 @@ struct Engine final : pn_tree {
             CUB(cudaMemcpyAsync(offs + q0 + 1, w_offsets.as<uint64_t>() + 1, (size_t)cq * 8, cudaMemcpyDeviceToHost, st));
             CUB(cudaStreamSynchronize(st));
             const uint64_t ctotal = offs[q0 + cq];  // chunk-local total
-            TRYB(w_hits.ensure((ctotal ? ctotal : 1) * 8));
+            TRYB(w_hits.ensure((ctotal ? ctotal : 1) * 4));
             radius_kernel<A><<<blocks, wpb * 32, 0, st>>>(dt, w_q.as<V>(), cq, r, w_counts.as<uint32_t>(), w_offsets.as<uint64_t>(),
-                                                         w_hits.as<uint64_t>(), nullptr);
+                                                         w_hits.as<uint32_t>(), nullptr);
             CUB(cudaGetLastError());
-            segment_sort_kernel<<<blocks, wpb * 32, 0, st>>>(w_offsets.as<uint64_t>(), w_hits.as<uint64_t>(), cq);
+            segment_sort_kernel<<<blocks, wpb * 32, 0, st>>>(w_offsets.as<uint64_t>(), w_hits.as<uint32_t>(), cq);
             CUB(cudaGetLastError());
             if (q0 + chunk >= nq) CUB(cudaEventRecord(ev[3], st));
             counters.kernel_launches += 4;
@@ -563,12 +604,12 @@ struct Engine final : pn_tree {
                 if (!nb) return bail(fail(PN_OOM, "realloc indices"));
                 hit_buf = nb; hit_cap = ncap;
             }
-            if (ctotal) CUB(cudaMemcpyAsync(hit_buf + total, w_hits.p, ctotal * 8, cudaMemcpyDeviceToHost, st));
+            TRYB(copy_out_widen(hit_buf + total, w_hits.as<uint32_t>(), ctotal, st));
             CUB(cudaStreamSynchronize(st));
             for (uint32_t i = 1; i <= cq; ++i) offs[q0 + i] += total;  // chunk-local -> global offsets
             total += ctotal;
             counters.h2d_bytes += (uint64_t)cq * ft.d * sizeof(A);
-            counters.d2h_bytes += (uint64_t)cq * 8 + ctotal * 8;
+            counters.d2h_bytes += (uint64_t)cq * 8 + ctotal * 4;
         }
         if (nq == 0) { CUB(cudaEventRecord(ev[2], st)); CUB(cudaEventRecord(ev[3], st)); }
         CUB(cudaEventRecord(ev[1], st));

@@ -200,8 +200,13 @@ struct TopKLocal {
         for (uint32_t i = 0; i < k; ++i) { out_d[i] = kd[i]; out_i[i] = ki[i]; }
     }
 };
-template <typename A, int K> struct TileTopK { using type = TopKLocal<A, K>; };
-template <typename A> struct TileTopK<A, 1> { using type = TopK<A, 1>; };
+// small d (DVR 1-2: pruned, few thousand pairs per query, insert-heavy) -> registers; otherwise local
+template <typename A, int K, int DVR> struct TileTopK { using type = TopKLocal<A, K>; };
+template <typename A, int K> struct TileTopK<A, K, 1> { using type = TopK<A, K>; };
+template <typename A, int K> struct TileTopK<A, K, 2> { using type = TopK<A, K>; };
+template <typename A, int DVR> struct TileTopK<A, 1, DVR> { using type = TopK<A, 1>; };
+template <typename A> struct TileTopK<A, 1, 1> { using type = TopK<A, 1>; };
+template <typename A> struct TileTopK<A, 1, 2> { using type = TopK<A, 1>; };
 
 // ---- block-wide counts of up to four predicates with ONE barrier ---------------------------
 struct VoteBuf { uint32_t v[2][TQ / 32][4]; };
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
     }
     __syncthreads();
 
-    typename TileTopK<A, K>::type topk;
+    typename TileTopK<A, K, DVR>::type topk;
     topk.init(active, k);
     if (a.floor_d && active) topk.set_floor(a.floor_d[qid], a.floor_i[qid]);
 
@@ -567,7 +572,7 @@ __global__ void scatter_order_kernel(const uint32_t* __restrict__ home, uint32_t
 template <typename A>
 __global__ void radius_kernel(const DevTree<A> t, const typename VT<A>::V* __restrict__ q, uint32_t nq, A r,
                               uint32_t* __restrict__ counts, const uint64_t* __restrict__ offsets,
-                              uint64_t* __restrict__ out, unsigned long long* counters) {
+                              uint32_t* __restrict__ out, unsigned long long* counters) {
     using V = typename VT<A>::V;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -643,21 +648,21 @@ __global__ void offsets_scan_kernel(const uint32_t* __restrict__ counts, uint64_
 // ascending sort of each query's hit list: one warp per segment, bitonic network over the
 // segment padded to a power of two with +inf keys (the reference's order is unspecified DFS
 // order and its tests sort before comparing, src/ball_tree.rs:667, 777)
-__global__ void segment_sort_kernel(const uint64_t* __restrict__ offsets, uint64_t* __restrict__ vals, uint32_t nq) {
+__global__ void segment_sort_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ vals, uint32_t nq) {
     const int lane = threadIdx.x & 31;
     const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= nq) return;
     const uint64_t lo = offsets[qi];
     const uint32_t n = (uint32_t)(offsets[qi + 1] - lo);
     if (n < 2) return;
-    uint64_t* v = vals + lo;
+    uint32_t* v = vals + lo;
     uint32_t np2 = 1;
     while (np2 < n) np2 <<= 1;
     // all-ascending form of the bitonic network (first step of each phase mirrors, i ^ (size-1)):
     // every compare-exchange moves the smaller key down, so the virtual +inf keys at >= n never move
     auto cmpx = [&](uint32_t i, uint32_t j) {
         if (j > i && j < n) {
-            const uint64_t x = v[i], y = v[j];
+            const uint32_t x = v[i], y = v[j];
             if (x > y) { v[i] = y; v[j] = x; }
         }
     };
