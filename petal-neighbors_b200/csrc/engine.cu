@@ -163,7 +163,7 @@ struct Engine final : pn_tree {
     // ------------------------------------------------------------------------------------------
     template <int DVR, int K, int KIND>
     int launch_knn_t(const KnnArgs<A>& a, dim3 grid, cudaStream_t st) {
-        size_t smem = 2 * TILE_BYTES + (DVR == 0 ? (size_t)TQ * ft.dpad * sizeof(A) : 0);
+        size_t smem = DVR < 0 ? 0 : 2 * TILE_BYTES + (DVR == 0 ? (size_t)TQ * ft.dpad * sizeof(A) : 0);
         auto kern = knn_tile_kernel<A, DVR, K, KIND>;
         if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, TQ, smem, st>>>(a);
@@ -177,7 +177,9 @@ struct Engine final : pn_tree {
             case 2: return launch_knn_t<2, K, KIND>(a, grid, st);
             case 4: return launch_knn_t<4, K, KIND>(a, grid, st);
             case 8: return launch_knn_t<8, K, KIND>(a, grid, st);
-            default: return launch_knn_t<0, K, KIND>(a, grid, st);
+            default:
+                if ((size_t)ft.dpad * sizeof(A) > 1024) return launch_knn_t<-1, K, KIND>(a, grid, st);  // wide rows: unstaged
+                return launch_knn_t<0, K, KIND>(a, grid, st);
         }
     }
     int launch_knn(const KnnArgs<A>& a, dim3 grid, cudaStream_t st, bool k1) {
@@ -212,7 +214,8 @@ struct Engine final : pn_tree {
         if (r != CUDA_SUCCESS) return fail(PN_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
         return PN_OK;
     }
-    bool tensor_eligible() const { return sizeof(A) == 4 && algo != PN_ALGO_SIMT && (algo == PN_ALGO_TENSOR || ft.d >= 16); }
+    // the resident A operand (nkc chunks of 8 KB per 128-query subtile) must fit shared memory: Kp <= 384
+    bool tensor_eligible() const { return sizeof(A) == 4 && algo != PN_ALGO_SIMT && (algo == PN_ALGO_TENSOR || ft.d >= 16) && ft.d + tc::NSLOT <= 384; }
     int prepare_tensor() {
         if constexpr (sizeof(A) == 4) {
             if (!tensor_eligible()) return PN_OK;
@@ -654,7 +657,7 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
     if (opts_in) memcpy(&o, opts_in, std::min<size_t>(sizeof(o), opts_in->struct_size ? opts_in->struct_size : sizeof(o)));
     else o.device = -1;
     const size_t dpad = (d + VT<A>::N - 1) / VT<A>::N * VT<A>::N;
-    if (dpad * sizeof(A) > 1024) return fail(PN_BAD_ARG, "dimension too large: a padded row must fit 1024 bytes (f32 d<=256, f64 d<=128)");
+    (void)dpad;
     uint32_t bucket = o.bucket_size ? o.bucket_size : 256;
     if (bucket < 8) bucket = 8;
     uint32_t threads = o.host_threads ? o.host_threads : std::max(1u, std::thread::hardware_concurrency());

@@ -270,12 +270,16 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
+    // DVR > 0: query in registers; DVR == 0: query in a transposed smem copy; DVR < 0 ("wide" rows,
+    // more than 1024 bytes): nothing is staged, query and point rows are read through L1/L2
+    constexpr bool WIDE = DVR < 0;
+    const V* qrow = a.q + (size_t)qid * DV;
     V qreg[DVR > 0 ? DVR : 1];
     if (DVR > 0) {
 #pragma unroll
         for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc)
             qreg[jc] = active ? a.q[(size_t)qid * DV + jc] : vzero(A(0));
-    } else {
+    } else if (!WIDE) {
         for (int jc = 0; jc < DV; ++jc) qs[jc * TQ + tid] = active ? a.q[(size_t)qid * DV + jc] : vzero(A(0));
     }
     __syncthreads();
@@ -293,6 +297,8 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
         if (DVR > 0) {
 #pragma unroll
             for (int jc = 0; jc < (DVR > 0 ? DVR : 1); ++jc) acc = fold(acc, qreg[jc], __ldg(row + jc));
+        } else if (WIDE) {
+            for (int jc = 0; jc < DV; ++jc) acc = fold(acc, __ldg(qrow + jc), __ldg(row + jc));
         } else {
             for (int jc = 0; jc < DV; ++jc) acc = fold(acc, qs[jc * TQ + tid], __ldg(row + jc));
         }
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
     };
 
     // leaf loops src/ball_tree.rs:162-173, 217-226: all points of bucket b against all 128 queries
-    const int TP = max(RP, (int)(TILE_BYTES / (t.dpad * sizeof(A))) / RP * RP);
+    const int TP = max(RP, (int)(TILE_BYTES / (t.dpad * sizeof(A))) / RP * RP);  // unused by the wide variant
     // Tiles are staged by TMA bulk copies (cp.async.bulk, one elected thread) into two buffers: the copy
     // of tile i+1 overlaps the distance folds on tile i; one barrier per tile protects buffer reuse.
     uint32_t tile_use[2] = {0, 0};  // uses of each buffer so far (block-uniform) -> mbarrier phase parity
@@ -308,6 +314,25 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
         const uint32_t lo = t.bucket_lo[b], hi = t.bucket_hi[b];
         if (hi <= lo) return;
         const bool warp_need = __any_sync(0xffffffffu, need);
+        if (WIDE) {  // all lanes read the same point row (one broadcast transaction), each its own query row
+            if (warp_need) {
+                if (active) my_pairs += hi - lo;
+                for (uint32_t p0 = lo; p0 < hi; p0 += RP) {
+                    A acc[RP];
+#pragma unroll
+                    for (int r = 0; r < RP; ++r) acc[r] = A(0);
+                    for (int jc = 0; jc < DV; ++jc) {
+                        const V qv = __ldg(qrow + jc);
+#pragma unroll
+                        for (int r = 0; r < RP; ++r) acc[r] = fold(acc[r], qv, __ldg(t.pts + (size_t)min(p0 + r, hi - 1) * DV + jc));
+                    }
+#pragma unroll
+                    for (int r = 0; r < RP; ++r)
+                        if (p0 + r < hi && acc[r] <= topk.t2) topk.offer_sq(acc[r], __ldg(t.ids + p0 + r));
+                }
+            }
+            return;
+        }
         const uint32_t row_bytes = t.dpad * (uint32_t)sizeof(A);
         const uint32_t n_tiles = (hi - lo + TP - 1) / TP;
         auto issue = [&](uint32_t i) {  // tid == 0 only

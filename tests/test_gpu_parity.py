@@ -94,11 +94,10 @@ def test_errors(pn):
     (5000, 5, 129, 16, 64), (20000, 16, 700, 10, 0), (4000, 17, 130, 10, 128), (3000, 33, 200, 3, 0),
     (3000, 64, 150, 10, 0), (2000, 100, 100, 10, 64), (2500, 128, 131, 10, 0), (6000, 8, 256, 40, 64),
     (3000, 10, 1, 10, 16), (1500, 7, 33, 100, 32),
+    (900, 300, 70, 10, 64), (500, 1000, 40, 5, 0),   # rows wider than 1024 bytes: unstaged "wide" scan
 ])
 def test_ball_knn_random(pn, oracle, dtype, n, d, nq, k, bucket):
     from petal_neighbors_b200 import synth
-    if dtype == np.float64 and d > 128:
-        pytest.skip("f64 rows above 1024 bytes are not supported")
     pts = synth.uniform(n, d, 11 + n + d, dtype)
     Q = synth.uniform(nq, d, 12 + n + d, dtype)
     bt = pn.BallTree.euclidean(pts, bucket_size=bucket)

@@ -25,8 +25,11 @@ def check(pn, oracle, pts, Q, k, **opts):
     assert bad.size == 0, f"index mismatch at {bad[:5]} got {idx[tuple(bad[0])]} want {oi[tuple(bad[0])]}"
     assert np.array_equal(bits(dist), bits(od)), "distances are not bit-identical"
     c = bt.counters()
-    assert c["filter_pairs"] == pts.shape[0] * Q.shape[0] * max(1, -(-k // 16))
-    assert c["rerank_pairs"] >= min(k, pts.shape[0]) * Q.shape[0] // 2
+    if pts.shape[1] + 6 <= 384:
+        assert c["filter_pairs"] == pts.shape[0] * Q.shape[0] * max(1, -(-k // 16))
+        assert c["rerank_pairs"] >= min(k, pts.shape[0]) * Q.shape[0] // 2
+    else:
+        assert c["filter_pairs"] == 0
     return bt, c
 
 
@@ -44,6 +47,8 @@ def check(pn, oracle, pts, Q, k, **opts):
     (50, 16, 10, 10),          # n < one tile
     (7, 16, 3, 10),            # k > n: padded rows
     (20000, 16, 5000, 10),
+    (1500, 300, 300, 10),      # Kp = 320: ten K chunks, MT=1
+    (800, 500, 200, 10),       # too wide for the resident A operand: falls back to the exact wide scan
 ])
 def test_tensor_knn_random(pn, oracle, n, d, nq, k):
     from petal_neighbors_b200 import synth

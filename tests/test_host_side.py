@@ -79,8 +79,6 @@ def fold_dist(a, b):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("n,d,bucket", [(1, 2, 0), (9, 3, 8), (1000, 3, 8), (5000, 16, 64), (4097, 5, 256), (3000, 130, 100)])
 def test_ball_layout_invariants(pn, dtype, n, d, bucket):
-    if dtype == np.float64 and d > 128:
-        pytest.skip("row too large")
     pts = np.random.default_rng(n + d).random((n, d)).astype(dtype)
     t = pn.BallTree.euclidean(pts, host_only=True, bucket_size=bucket)
     lay = t.layout()
