@@ -301,3 +301,31 @@ def test_pairwise(pn, oracle, dtype, n, d):
     want = oracle.pairwise(x)
     assert np.array_equal(bits(got), bits(want))
     assert np.array_equal(got, got.T) and np.all(np.diag(got) == 0)
+
+
+def test_concurrent_queries_on_one_handle(pn, oracle):
+    """Queries on one tree from several host threads are legal (reference: &self queries,
+    Euclidean: Sync, src/distance.rs:19); the engine serialises them and every caller gets its answer."""
+    import threading
+    from petal_neighbors_b200 import synth
+    pts = synth.uniform(20000, 8, 5, np.float32)
+    bt = pn.BallTree.euclidean(pts, bucket_size=64)
+    Qs = [synth.uniform(500 + 37 * i, 8, 100 + i, np.float32) for i in range(6)]
+    out = [None] * len(Qs)
+
+    def work(i):
+        if i % 2:
+            out[i] = bt.query_batch(Qs[i], 10)
+        else:
+            out[i] = bt.query_radius_batch(Qs[i], np.float32(0.25))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(Qs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i, Q in enumerate(Qs):
+        if i % 2:
+            oi, od = oracle.brute_knn(pts, Q, 10)
+            assert_knn_equal(out[i][0], out[i][1], oi, od)
+        else:
+            boffs, bind = oracle.brute_radius(pts, Q, np.float32(0.25))
+            assert np.array_equal(out[i][0], boffs.astype(np.uint64)) and np.array_equal(out[i][1], bind.astype(np.uint64))
