@@ -136,13 +136,31 @@ class BallBuilder {
         std::vector<A> mn(d_), mx(d_);
         const A* r0 = pts_ + (size_t)idx[lo] * stride_;
         for (size_t j = 0; j < d_; ++j) mn[j] = mx[j] = r0[j];
-        for (size_t t = lo + 1; t < hi; ++t) {  // row-wise pass: same result as the per-column pass
-            const A* r = pts_ + (size_t)idx[t] * stride_;
-            for (size_t j = 0; j < d_; ++j) {
-                A v = r[j];
-                if (v < mn[j]) mn[j] = v;
-                if (v > mx[j]) mx[j] = v;
+        auto minmax_range = [&](size_t b, size_t e, A* pmn, A* pmx) {  // row-wise pass: same result as the per-column pass
+            for (size_t t = b; t < e; ++t) {
+                const A* r = pts_ + (size_t)idx[t] * stride_;
+                for (size_t j = 0; j < d_; ++j) {
+                    A v = r[j];
+                    if (v < pmn[j]) pmn[j] = v;
+                    if (v > pmx[j]) pmx[j] = v;
+                }
             }
+        };
+        const uint32_t nt = workers_for(len);
+        if (nt <= 1) {
+            minmax_range(lo + 1, hi, mn.data(), mx.data());
+        } else {  // min / max are order-independent: chunked over threads, identical result
+            std::vector<std::vector<A>> pmn(nt, mn), pmx(nt, mx);
+            std::vector<std::thread> th;
+            const size_t chunk = (len + nt - 1) / nt;
+            for (uint32_t w = 0; w < nt; ++w) {
+                const size_t b = lo + w * chunk, e = std::min(hi, b + chunk);
+                if (b >= e) break;
+                th.emplace_back([&, b, e, w] { minmax_range(b, e, pmn[w].data(), pmx[w].data()); });
+            }
+            for (auto& x : th) x.join();
+            for (uint32_t w = 0; w < nt; ++w)
+                for (size_t j = 0; j < d_; ++j) { if (pmn[w][j] < mn[j]) mn[j] = pmn[w][j]; if (pmx[w][j] > mx[j]) mx[j] = pmx[w][j]; }
         }
         size_t col = 0;
         A best = mx[0] - mn[0];
@@ -159,23 +177,65 @@ class BallBuilder {
                          });
     }
 
-    // Node::init, src/ball_tree.rs:445-461
+    // threads worth using for a pass over `len` rows at the current point of the recursion
+    uint32_t workers_for(size_t len) const {
+        if (len * d_ < (size_t)1 << 22) return 1;
+        return (uint32_t)std::min<size_t>(threads_, len / 65536 + 1);
+    }
+
+    // Node::init, src/ball_tree.rs:445-461.  For large nodes the sum and the max are accumulated per chunk
+    // and combined (the centroid then differs from the strictly sequential sum in the last bits; any centre
+    // with radius = max exact fold distance to it is a valid ball, so results are unaffected).
     void node_init(const std::vector<uint32_t>& idx, size_t lo, size_t hi, A* center, A& radius) {
         const size_t len = hi - lo;
         if (len == 0) { radius = A(-1); return; }
-        for (size_t j = 0; j < d_; ++j) center[j] = A(0);
-        for (size_t t = lo; t < hi; ++t) {
-            const A* r = pts_ + (size_t)idx[t] * stride_;
-            for (size_t j = 0; j < d_; ++j) center[j] += r[j];
+        const uint32_t nt = workers_for(len);
+        const size_t chunk = (len + nt - 1) / nt;
+        auto sum_range = [&](size_t b, size_t e, A* acc) {
+            for (size_t j = 0; j < d_; ++j) acc[j] = A(0);
+            for (size_t t = b; t < e; ++t) {
+                const A* r = pts_ + (size_t)idx[t] * stride_;
+                for (size_t j = 0; j < d_; ++j) acc[j] += r[j];
+            }
+        };
+        auto max_range = [&](size_t b, size_t e) {
+            A m = A(0);
+            for (size_t t = b; t < e; ++t) {
+                A v = fold_distance(center, pts_ + (size_t)idx[t] * stride_, d_);
+                if (v > m) m = v;
+            }
+            return m;
+        };
+        if (nt <= 1) {
+            sum_range(lo, hi, center);
+        } else {
+            std::vector<std::vector<A>> part(nt, std::vector<A>(d_));
+            std::vector<std::thread> th;
+            for (uint32_t w = 0; w < nt; ++w) {
+                const size_t b = lo + w * chunk, e = std::min(hi, b + chunk);
+                if (b >= e) { for (size_t j = 0; j < d_; ++j) part[w][j] = A(0); continue; }
+                th.emplace_back([&, b, e, w] { sum_range(b, e, part[w].data()); });
+            }
+            for (auto& x : th) x.join();
+            for (size_t j = 0; j < d_; ++j) { A sacc = A(0); for (uint32_t w = 0; w < nt; ++w) sacc += part[w][j]; center[j] = sacc; }
         }
         A flen = (A)len;
         for (size_t j = 0; j < d_; ++j) center[j] /= flen;
-        A mxr = A(0);
-        for (size_t t = lo; t < hi; ++t) {
-            A v = fold_distance(center, pts_ + (size_t)idx[t] * stride_, d_);
-            if (v > mxr) mxr = v;
+        if (nt <= 1) {
+            radius = max_range(lo, hi);
+        } else {
+            std::vector<A> pm(nt, A(0));
+            std::vector<std::thread> th;
+            for (uint32_t w = 0; w < nt; ++w) {
+                const size_t b = lo + w * chunk, e = std::min(hi, b + chunk);
+                if (b >= e) continue;
+                th.emplace_back([&, b, e, w] { pm[w] = max_range(b, e); });
+            }
+            for (auto& x : th) x.join();
+            A m = A(0);
+            for (uint32_t w = 0; w < nt; ++w) if (pm[w] > m) m = pm[w];
+            radius = m;
         }
-        radius = mxr;
     }
 
     void recurse(std::vector<uint32_t>& idx, FlatTree<A>& t, uint32_t node, size_t lo, size_t hi, uint32_t level) {
