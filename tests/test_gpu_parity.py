@@ -329,3 +329,40 @@ def test_concurrent_queries_on_one_handle(pn, oracle):
         else:
             boffs, bind = oracle.brute_radius(pts, Q, np.float32(0.25))
             assert np.array_equal(out[i][0], boffs.astype(np.uint64)) and np.array_equal(out[i][1], bind.astype(np.uint64))
+
+
+def test_randomized_shapes_all_entry_points(pn, oracle):
+    """Seeded sweep over random (n, d, nq, k, bucket, dtype, engine): k-NN, 1-NN, radius, VP 1-NN and
+    self-query against the oracle; every case bit-exact."""
+    rng = np.random.default_rng(20261018)
+    for case in range(40):
+        dtype = np.float32 if rng.random() < 0.6 else np.float64
+        n = int(rng.integers(1, 4000))
+        d = int(rng.choice([1, 2, 3, 4, 5, 8, 13, 16, 17, 31, 32, 33, 64, 70]))
+        nq = int(rng.integers(1, 400))
+        k = int(rng.choice([1, 2, 5, 10, 16, 17, 31]))
+        bucket = int(rng.choice([0, 8, 16, 64, 256]))
+        algo = int(rng.choice([0, 1, 2])) if dtype == np.float32 else 1
+        quant = bool(rng.random() < 0.3)                 # lattice data: many exact ties
+        pts = rng.random((n, d))
+        Q = rng.random((nq, d))
+        if quant:
+            pts, Q = np.round(pts * 4), np.round(Q * 4)
+        pts, Q = pts.astype(dtype), Q.astype(dtype)
+        tag = f"case {case}: n={n} d={d} nq={nq} k={k} bucket={bucket} {dtype.__name__} algo={algo} quant={quant}"
+        bt = pn.BallTree.euclidean(pts, bucket_size=bucket, algo=algo)
+        oi, od = oracle.brute_knn(pts, Q, k)
+        idx, dist = bt.query_batch(Q, k)
+        assert np.array_equal(idx, oi.astype(np.uint64)) and np.array_equal(bits(dist), bits(od)), tag
+        ni, nd = bt.query_nearest_batch(Q)
+        assert np.array_equal(ni, oi[:, 0].astype(np.uint64)) and np.array_equal(bits(nd), bits(od[:, 0])), tag
+        r = dtype(np.quantile(od[:, min(k, n) - 1], 0.5))
+        offs, ind = bt.query_radius_batch(Q, r)
+        boffs, bind = oracle.brute_radius(pts, Q, r)
+        assert np.array_equal(offs, boffs.astype(np.uint64)) and np.array_equal(ind, bind.astype(np.uint64)), tag
+        vi, vd = pn.VantagePointTree.euclidean(pts, bucket_size=bucket, algo=algo).query_nearest_batch(Q)
+        assert np.array_equal(vi, oi[:, 0].astype(np.uint64)) and np.array_equal(bits(vd), bits(od[:, 0])), tag
+        if case % 4 == 0:
+            si, sdist = bt.query_self(min(k, 16))
+            soi, sod = oracle.brute_knn(pts, pts, min(k, 16))
+            assert np.array_equal(si, soi.astype(np.uint64)) and np.array_equal(bits(sdist), bits(sod)), tag

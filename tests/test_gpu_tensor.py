@@ -105,3 +105,28 @@ def test_tensor_vp_tree(pn, oracle):
     vi, vd = vp.query_nearest_batch(Q)
     oi, od = oracle.brute_knn(pts, Q, 1)
     assert np.array_equal(vi, oi[:, 0].astype(np.uint64)) and np.array_equal(bits(vd), bits(od[:, 0]))
+
+
+def test_tensor_adversarial_scales(pn, oracle):
+    """Inputs chosen to stress the filter's rounding bound; the answer must stay bit-exact.
+    (a) one extreme outlier: the scale factor is set by it, every other scaled coordinate lands in fp16's
+        subnormal range (the absolute 2^-14 term of E_q has to carry the filter);
+    (b) queries far outside the fp16-safe range (scaled norm > 200): E_q = +inf, everything is reranked;
+    (c) tiny coordinates (1e-20 scale) and huge ones (1e15 scale);
+    (d) near-ties at the k-th boundary: distances that differ in the last few ulps."""
+    from petal_neighbors_b200 import synth
+    rng = np.random.default_rng(23)
+    base = synth.uniform(3000, 16, 7, np.float32)
+    Q = synth.uniform(2100, 16, 8, np.float32)
+    a = base.copy()
+    a[1234] = np.float32(1.0e6)                                    # (a)
+    check(pn, oracle, a, Q, 10)
+    check(pn, oracle, base, Q * np.float32(5000.0), 5)             # (b)
+    check(pn, oracle, base * np.float32(1e-20), Q * np.float32(1e-20), 10)   # (c)
+    check(pn, oracle, base * np.float32(1e15), Q * np.float32(1e15), 10)
+    ring = rng.standard_normal((4000, 16)).astype(np.float32)      # (d) points on a thin shell around the origin
+    ring /= np.linalg.norm(ring, axis=1, keepdims=True)
+    ring *= (1.0 + 1e-6 * rng.standard_normal((4000, 1))).astype(np.float32)
+    Qc = (1e-3 * rng.standard_normal((2100, 16))).astype(np.float32)  # queries near the centre: all distances ~ 1
+    check(pn, oracle, ring, Qc, 10)
+    check(pn, oracle, ring, Qc, 1)
