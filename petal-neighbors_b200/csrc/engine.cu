@@ -257,7 +257,7 @@ struct Engine final : pn_tree {
         auto kern = tc::knn_filter_kernel<DVR, K, MT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (fa.nq + MT * tc::BM - 1) / (MT * tc::BM);
-        kern<<<grid, (5 * MT + 1) * 32, smem, st>>>(map_a, map_b, fa);
+        kern<<<grid, (5 * MT + 2) * 32, smem, st>>>(map_a, map_b, fa);
         CU(cudaGetLastError());
         return PN_OK;
     }
@@ -267,6 +267,8 @@ struct Engine final : pn_tree {
         const size_t budget = 220 * 1024;
         fa.gs = fa.nkc == 1 ? 4 : (fa.nkc == 2 ? 2 : 1);
         fa.stages = (uint32_t)std::min<size_t>(fa.gs > 1 ? 4 : 12, (budget - 7168 - (size_t)4 * mt * K * 32 * 8 - (size_t)mt * fa.nkc * tc::A_CHUNK_BYTES) / (tc::CHUNK_BYTES * fa.gs));
+        fa.stages &= ~1u;  // even: each ring stage always belongs to the same one of the two producer warps
+        if (fa.stages < 2) return fail(PN_CUDA, "tensor path: shared memory budget too small for this dimension");
         if (mt == 2) {
             if (dt.dv == 4) return launch_filter_t<4, K, 2>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 2>(map_a, fa, st);

@@ -22,7 +22,8 @@
 // Queries whose scaled norm leaves the fp16 range get E_q = +inf: every point is reranked exactly.
 //
 // Structure (one CTA = MT x 128 queries, persistent over all point tiles; 1 CTA / SM):
-//   warp 4MT   : TMA producer, cp.async.bulk.tensor 2-D boxes [128 rows x 32 fp16] (64B swizzle)
+//   warps 4MT, 5MT+1 : two TMA producers on alternate ring groups, cp.async.bulk.tensor 2-D boxes
+//                [128 rows x 32 fp16] (64B swizzle)
 //   warps 4MT+1.. : MT tcgen05.mma issuers (one elected lane each, one per 128-query subtile),
 //                kind::f16, M=128 N=128 K=16 per instruction, accumulator stages double-buffered in
 //                TMEM (2 x MT x 128 columns)
@@ -255,7 +256,7 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
 }
 
 template <int DVR, int K, int MT>
-__global__ void __launch_bounds__((5 * MT + 1) * 32, 1)
+__global__ void __launch_bounds__((5 * MT + 2) * 32, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const FilterArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [A: MT*nkc chunks][B ring: stages chunks][barriers]
@@ -297,18 +298,21 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     const uint32_t row_base = blockIdx.x * (MT * BM);
 
-    if (warp == EPI_WARPS) {
-        // ================= TMA producer =================
+    if (warp == EPI_WARPS || warp == EPI_WARPS + MT + 1) {
+        // ================= TMA producers: two warps, alternate ring groups (stages is even) =================
+        const uint32_t pid = warp == EPI_WARPS ? 0u : 1u;
         if (lane == 0) {
-            mbar_expect_tx(a_bar, (uint32_t)(MT * a.nkc * A_CHUNK_BYTES));
-            for (int mt = 0; mt < MT; ++mt)
-                for (uint32_t c = 0; c < a.nkc; ++c)
-                    tma_load_2d(&map_a, a_bar, smem_a + (size_t)(mt * a.nkc + c) * A_CHUNK_BYTES, (int)(c * KC), (int)(row_base + mt * BM));
+            if (pid == 0) {
+                mbar_expect_tx(a_bar, (uint32_t)(MT * a.nkc * A_CHUNK_BYTES));
+                for (int mt = 0; mt < MT; ++mt)
+                    for (uint32_t c = 0; c < a.nkc; ++c)
+                        tma_load_2d(&map_a, a_bar, smem_a + (size_t)(mt * a.nkc + c) * A_CHUNK_BYTES, (int)(c * KC), (int)(row_base + mt * BM));
+            }
             // B ring: groups of `gs` chunks share one full/empty barrier pair, so the consumers pay one
             // barrier wait per group instead of one per 8 KB chunk
             const uint32_t total = a.n_tiles * a.nkc;
             const uint32_t n_groups = (total + a.gs - 1) / a.gs;
-            for (uint32_t g = 0; g < n_groups; ++g) {
+            for (uint32_t g = pid; g < n_groups; g += 2) {
                 const uint32_t s = g % a.stages, ph = (g / a.stages) & 1u;
                 const uint32_t first = g * a.gs, cnt = min(a.gs, total - first);
                 mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -319,7 +323,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
         }
-    } else if (warp > EPI_WARPS) {
+    } else if (warp > EPI_WARPS && warp <= EPI_WARPS + MT) {
         // ================= MMA issuers: one warp (one elected lane) per 128-query subtile ==========
         // The issuing thread's serial chain of mbarrier waits (~90 cycles each even when complete)
         // and tcgen05.mma issues is what bounds small-K tiles, so it is split over MT threads.

@@ -46,7 +46,9 @@ def check(pn, oracle, pts, Q, k, **opts):
     (50, 16, 10, 10),          # n < one tile
     (7, 16, 3, 10),            # k > n: padded rows
     (20000, 16, 5000, 10),
-    (1500, 300, 300, 10),      # Kp = 320: ten K chunks, MT=1
+    (1500, 300, 300, 10),      # Kp = 320: ten K chunks, MT=1, two requests per tile
+    (1200, 200, 260, 10),      # Kp = 224: seven chunks -> second request reads one chunk past the tensor (zero fill)
+    (2500, 170, 300, 10),      # Kp = 192: six chunks, one request per tile, MT=1
     (800, 500, 200, 10),       # too wide for the resident A operand: falls back to the exact wide scan
 ])
 def test_tensor_knn_random(pn, oracle, n, d, nq, k):
