@@ -109,7 +109,6 @@ struct Engine final : pn_tree {
     float pmax = 0.f;      // max |s (p - center)|
     float tscale = 1.f;    // s: power of two bringing the centred coordinates into [-1, 1]
     uint32_t algo = PN_ALGO_AUTO;
-    alignas(64) CUtensorMap map_b;
 
     ~Engine() override {
         if (!host_only) {
@@ -234,7 +233,9 @@ struct Engine final : pn_tree {
             tscale = std::ldexp(1.0f, -ex);
             TRY(d_center.ensure(ft.dpad * 4));
             CU(cudaMemcpy(d_center.p, c.data(), ft.dpad * 4, cudaMemcpyHostToDevice));
-            TRY(d_baug.ensure((size_t)ft.n * kp * 2));
+            const size_t baug_bytes = (ft.n + tc::BN - 1) / tc::BN * tc::BN * (size_t)kp * 2;  // whole tiles
+            TRY(d_baug.ensure(baug_bytes));
+            CU(cudaMemsetAsync(d_baug.p, 0, baug_bytes, stream));
             TRY(w_counters.ensure(256));
             CU(cudaMemset(w_counters.p, 0, 256));
             tc::build_baug_kernel<<<(unsigned)((ft.n + 127) / 128), 128, 0, stream>>>(d_pts.as<float>(), d_center.as<float>(), tscale, (uint32_t)ft.n, ft.d,
@@ -244,7 +245,6 @@ struct Engine final : pn_tree {
             CU(cudaMemcpyAsync(&bits, w_counters.p, 4, cudaMemcpyDeviceToHost, stream));
             CU(cudaStreamSynchronize(stream));
             memcpy(&pmax, &bits, 4);
-            TRY(make_map(&map_b, d_baug.p, ft.n, tc::BN));
             info.device_bytes += d_baug.cap;
             tensor_ready = true;
         }
@@ -257,7 +257,7 @@ struct Engine final : pn_tree {
         auto kern = tc::knn_filter_kernel<DVR, K, MT>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (fa.nq + MT * tc::BM - 1) / (MT * tc::BM);
-        kern<<<grid, (5 * MT + 2) * 32, smem, st>>>(map_a, map_b, fa);
+        kern<<<grid, (5 * MT + 2) * 32, smem, st>>>(map_a, d_baug.as<unsigned char>(), fa);
         CU(cudaGetLastError());
         return PN_OK;
     }
@@ -312,6 +312,9 @@ struct Engine final : pn_tree {
                 fa.part_d = w_part_d.as<float>(); fa.part_i = w_part_i.as<uint32_t>();
                 fa.floor_d = p ? w_floor_d.as<float>() : nullptr; fa.floor_i = p ? w_floor_i.as<uint32_t>() : nullptr;
                 fa.counters = w_counters.as<unsigned long long>();
+#ifdef PN_TC_PROFILE
+                fa.dbg = getenv("PN_TC_DEBUG") ? (uint32_t)atoi(getenv("PN_TC_DEBUG")) : 0u;
+#endif
                 TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
                 merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
                     w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, nq, kk, idx_out, dist_out, k, p * KP,
@@ -409,8 +412,8 @@ struct Engine final : pn_tree {
             unsigned long long pc[20];
             CU(cudaMemcpy(pc, (char*)w_counters.p + 64, sizeof(pc), cudaMemcpyDeviceToHost));
             const double tiles = (double)((ft.n + tc::BN - 1) / tc::BN) * (double)((nq + 255) / 256);
-            fprintf(stderr, "[tc profile] cycles/tile  MMA thread: wait tempty %.0f | wait full %.0f | issue+commit %.0f   epilogue warp: wait tfull %.0f | TMEM read-out %.0f | scan+push %.0f | drain+margin %.0f\n",
-                    pc[0] / tiles, pc[1] / tiles, pc[2] / tiles, pc[6] / tiles, pc[7] / tiles, pc[8] / tiles, pc[9] / tiles);
+            fprintf(stderr, "[tc profile] cycles/tile  MMA thread: wait tempty %.0f | wait full %.0f | issue+commit %.0f   epilogue warp: wait tfull %.0f | TMEM read-out %.0f | scan+push %.0f | drain+margin %.0f   producer 0: wait empty %.0f | issue %.0f\n",
+                    pc[0] / tiles, pc[1] / tiles, pc[2] / tiles, pc[6] / tiles, pc[7] / tiles, pc[8] / tiles, pc[9] / tiles, pc[12] / tiles, pc[13] / tiles);
         }
 #endif
         counters.queries = nq;

@@ -22,8 +22,8 @@
 // Queries whose scaled norm leaves the fp16 range get E_q = +inf: every point is reranked exactly.
 //
 // Structure (one CTA = MT x 128 queries, persistent over all point tiles; 1 CTA / SM):
-//   warps 4MT, 5MT+1 : two TMA producers on alternate ring groups, cp.async.bulk.tensor 2-D boxes
-//                [128 rows x 32 fp16] (64B swizzle)
+//   warps 4MT, 5MT+1 : two TMA producers on alternate ring groups: 1-D bulk copies (cp.async.bulk) of
+//                the pre-tiled, pre-swizzled B image ([128 rows x 32 fp16] chunks, 64B swizzle)
 //   warps 4MT+1.. : MT tcgen05.mma issuers (one elected lane each, one per 128-query subtile),
 //                kind::f16, M=128 N=128 K=16 per instruction, accumulator stages double-buffered in
 //                TMEM (2 x MT x 128 columns)
@@ -92,6 +92,20 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
             smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// true on exactly one lane of a fully converged warp; unlike `lane == 0` it keeps every value computed
+// from warp-uniform inputs in the uniform datapath, so tcgen05.mma gets its descriptors straight from
+// uniform registers (a per-thread branch makes ptxas wrap every UTCHMMA in an ELECT / R2UR.BROADCAST
+// loop, and each issue then waits ~250 cycles for the previous one: scripts/mma_rate.cu)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -197,6 +211,9 @@ struct FilterArgs {
     const float* floor_d;
     const uint32_t* floor_i;
     unsigned long long* counters;  // [2] filter hits (elements passed to the exact rerank)
+#ifdef PN_TC_PROFILE
+    uint32_t dbg;          // diagnostic leg isolation: 1 = epilogue skips the scan, 2 = producer skips the copies
+#endif
 };
 
 // three-piece fp16 split of a non-negative fp32 value (residual < 2^-30 x in the normal range)
@@ -207,24 +224,34 @@ __device__ __forceinline__ void split3_f16(float x, __half& h1, __half& h2, __ha
     h3 = __float2half_rn(r1 - __half2float(h2));
 }
 
-// B operand: one fp16 row per stored point (bucket order).  pmax_bits receives max |p'| (float bits).
+// B operand: one fp16 row per stored point (bucket order), written as the exact shared-memory image
+// the MMA reads: [tile of 128 points][K chunk of 32 fp16][128 rows x 64 B, 64-byte swizzle], so one
+// ring group is ONE contiguous span of global memory and is fetched by a single 1-D bulk copy (a
+// tensor-map request of 128 separate 64-byte rows kept the per-SM feed at ~10 B/cycle).
+// 64-byte swizzle: the 16-byte unit index (address bits 4-5) is XORed with address bits 7-8 = (row >> 1) & 3.
+// pmax_bits receives max |p'| (float bits).  The buffer is zero-filled first (rows past n).
+__device__ __forceinline__ size_t baug_offset(uint32_t row, uint32_t j, uint32_t nkc) {
+    const uint32_t tile = row / BN, r = row % BN, c = j / KC, e = j % KC;
+    return ((size_t)(tile * nkc + c) * BN + r) * KC + (((e >> 3) ^ ((r >> 1) & 3u)) << 3) + (e & 7u);
+}
 __global__ void build_baug_kernel(const float* __restrict__ pts, const float* __restrict__ center, float scale, uint32_t n,
                                   uint32_t d, uint32_t dpad, uint32_t kp, __half* __restrict__ baug, unsigned int* pmax_bits) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = pts + (size_t)i * dpad;
-    __half* o = baug + (size_t)i * kp;
+    const uint32_t nkc = kp / KC;
     float nrm = 0.f;
     for (uint32_t j = 0; j < d; ++j) {
         const float v = (p[j] - center[j]) * scale;
         nrm = nrm + v * v;
-        o[j] = __float2half_rn(-2.0f * v);
+        baug[baug_offset(i, j, nkc)] = __float2half_rn(-2.0f * v);
     }
-    for (uint32_t j = d; j < kp - NSLOT; ++j) o[j] = __float2half_rn(0.f);
+    for (uint32_t j = d; j < kp - NSLOT; ++j) baug[baug_offset(i, j, nkc)] = __float2half_rn(0.f);
     __half h1, h2, h3;
     split3_f16(nrm, h1, h2, h3);
     const __half one = __float2half_rn(1.f);
-    o[kp - 6] = one; o[kp - 5] = one; o[kp - 4] = one; o[kp - 3] = h1; o[kp - 2] = h2; o[kp - 1] = h3;
+    baug[baug_offset(i, kp - 6, nkc)] = one; baug[baug_offset(i, kp - 5, nkc)] = one; baug[baug_offset(i, kp - 4, nkc)] = one;
+    baug[baug_offset(i, kp - 3, nkc)] = h1;  baug[baug_offset(i, kp - 2, nkc)] = h2;  baug[baug_offset(i, kp - 1, nkc)] = h3;
     atomicMax(pmax_bits, __float_as_uint(sqrtf(nrm) * 1.000001f));
 }
 
@@ -257,7 +284,7 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
 
 template <int DVR, int K, int MT>
 __global__ void __launch_bounds__((5 * MT + 2) * 32, 1)
-knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const FilterArgs a) {
+knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char* __restrict__ baug, const FilterArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [A: MT*nkc chunks][B ring: stages chunks][barriers]
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -275,7 +302,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float* tk_d = reinterpret_cast<float*>(qbuf + 4 * MT * QWORDS);   // [EPI_WARPS][K][32]
     uint32_t* tk_i = reinterpret_cast<uint32_t*>(tk_d + 4 * MT * K * 32);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
     constexpr int EPI_WARPS = 4 * MT;
     constexpr int TMEM_COLS = NUM_ACC * MT * BN;  // 256 or 512 (power of two)
 
@@ -285,7 +312,6 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == EPI_WARPS + 1) {  // first MMA warp owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -294,7 +320,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const uint32_t row_base = blockIdx.x * (MT * BM);
 
@@ -312,29 +338,35 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // barrier wait per group instead of one per 8 KB chunk
             const uint32_t total = a.n_tiles * a.nkc;
             const uint32_t n_groups = (total + a.gs - 1) / a.gs;
+            PROF_DECL;
             for (uint32_t g = pid; g < n_groups; g += 2) {
                 const uint32_t s = g % a.stages, ph = (g / a.stages) & 1u;
                 const uint32_t first = g * a.gs, cnt = min(a.gs, total - first);
+                PROF_ADD(1);
                 mbar_wait(&empty_bar[s], ph ^ 1u);
+                PROF_ADD(0);
+#ifdef PN_TC_PROFILE
+                if (a.dbg & 2u) { mbar_arrive(&full_bar[s]); continue; }
+#endif
+                // chunk `it` of the stream sits at byte it * CHUNK_BYTES of the tiled image: one contiguous span per group
                 mbar_expect_tx(&full_bar[s], cnt * CHUNK_BYTES);
-                for (uint32_t i = 0; i < cnt; ++i) {
-                    const uint32_t it = first + i, j = it / a.nkc, c = it % a.nkc;
-                    tma_load_2d(&map_b, &full_bar[s], smem_b + (size_t)(s * a.gs + i) * CHUNK_BYTES, (int)(c * KC), (int)(j * BN));
-                }
+                bulk_copy(smem_b + (size_t)s * a.gs * CHUNK_BYTES, baug + (size_t)first * CHUNK_BYTES, cnt * CHUNK_BYTES, &full_bar[s]);
             }
+            if (pid == 0) PROF_FLUSH(12);
         }
     } else if (warp > EPI_WARPS && warp <= EPI_WARPS + MT) {
         // ================= MMA issuers: one warp (one elected lane) per 128-query subtile ==========
         // The issuing thread's serial chain of mbarrier waits (~90 cycles each even when complete)
         // and tcgen05.mma issues is what bounds small-K tiles, so it is split over MT threads.
-        if (lane == 0) {
+        // The whole warp runs the loop on warp-uniform values; one elected lane issues.
+        {
             const int mt = warp - (EPI_WARPS + 1);
             constexpr uint32_t idesc = make_idesc_f16(BM, BN);
             const uint64_t a_desc0 = make_desc_sw64(smem_u32(smem_a)) + (uint64_t)(mt * a.nkc * (A_CHUNK_BYTES >> 4));
             const uint64_t b_desc0 = make_desc_sw64(smem_u32(smem_b));
             const uint32_t total = a.n_tiles * a.nkc;
             mbar_wait(a_bar, 0);
-            uint32_t it = 0;
+            uint32_t it = 0, g = 0, gi = 0, s = 0, sph = 0;  // stream position: group, chunk in group, ring stage, its phase
             PROF_DECL;
             for (uint32_t j = 0; j < a.n_tiles; ++j) {
                 const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
@@ -343,24 +375,28 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 PROF_ADD(0);
                 const uint32_t d_tmem = tmem_base + (as * MT + mt) * BN;
                 for (uint32_t c = 0; c < a.nkc; ++c, ++it) {
-                    const uint32_t g = it / a.gs, gi = it % a.gs, s = g % a.stages;
                     if (gi == 0) {
-                        mbar_wait(&full_bar[s], (g / a.stages) & 1u);
+                        mbar_wait(&full_bar[s], sph);
                         tc_fence_after();
+                        PROF_ADD(1);
                     }
-                    PROF_ADD(1);
                     // descriptors advance in 16-byte units: +2 per K step of 16 fp16, whole chunks per slot
                     const uint64_t bd = b_desc0 + (uint64_t)((s * a.gs + gi) * (CHUNK_BYTES >> 4));
                     const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
-#pragma unroll
-                    for (int ks = 0; ks < KC / 16; ++ks)
-                        tc_mma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                    if (gi + 1 == a.gs || it + 1 == total) tc_commit(&empty_bar[s]);  // group consumed by this subtile
+                    const bool last = gi + 1 == a.gs || it + 1 == total;
+                    if (elect_one()) {
+                        tc_mma_f16(d_tmem, ad, bd, idesc, c > 0 ? 1u : 0u);
+                        tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                        if (last) tc_commit(&empty_bar[s]);  // group consumed by this subtile
+                    }
+                    __syncwarp();
+                    if (last) { gi = 0; ++g; if (++s == a.stages) { s = 0; sph ^= 1u; } } else ++gi;
                 }
-                tc_commit(&tfull_bar[as * MT + mt]);  // this subtile's accumulator is complete
+                if (elect_one()) tc_commit(&tfull_bar[as * MT + mt]);  // this subtile's accumulator is complete
+                __syncwarp();
                 PROF_ADD(2);
             }
-            if (mt == 0) PROF_FLUSH(0);
+            if (mt == 0 && lane == 0) PROF_FLUSH(0);
         }
     } else {
         // ================= epilogue: one query row per thread =================
@@ -509,6 +545,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
             PROF_ADD(1);
+#ifdef PN_TC_PROFILE
+            if (a.dbg & 1u) continue;
+#endif
 #pragma unroll
             for (int g = 0; g < G; ++g) scan32(r[g], j, g * 32);
             PROF_ADD(2);

@@ -1,0 +1,22 @@
+# Tensor filter probe: scan time and per-role cycle accounting (needs lib/libpetal_b200_prof.so built
+# with -DPN_TC_PROFILE).  PN_TC_DEBUG leg isolation: 1 = no scan, 2 = no copies, 3 = both.
+export PN_B200_LIB=$PWD/petal-neighbors_b200/lib/libpetal_b200_prof.so
+for dbg in ${DBGS:-0 1 2 3}; do
+PN_TC_DEBUG=$dbg timeout 600 python - <<PY 2>&1 | grep -E "profile|scan|Error|error" | sed "s/^/[dbg=$dbg] /"
+import sys, numpy as np
+sys.path.insert(0, ".")
+import petal_neighbors_b200 as pn
+from petal_neighbors_b200 import synth
+for d, n in ((128, 1000000), (16, 1000000)):
+    pts = synth.uniform(n, d, 2, np.float32)
+    bt = pn.BallTree.euclidean(pts, algo=pn.PN_ALGO_TENSOR)
+    for nq in (${NQS:-37888},):
+        Q = synth.uniform(nq, d, 3, np.float32)
+        for k in (1, 10):
+            bt.query_batch(Q, k)
+            sys.stderr.flush()
+            print(f"--- d={d} nq={nq} k={k}", file=sys.stderr, flush=True)
+            bt.query_batch(Q, k)
+            print(f"d={d} n={n} nq={nq} k={k} scan {bt.counters()['scan_ms']:.2f} ms", file=sys.stderr, flush=True)
+PY
+done
