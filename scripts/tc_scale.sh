@@ -17,6 +17,6 @@ for d, n in ((128, 1000000), (16, 1000000)):
             sys.stderr.flush()
             print(f"--- d={d} nq={nq} k={k}", file=sys.stderr, flush=True)
             bt.query_batch(Q, k)
-            print(f"d={d} n={n} nq={nq} k={k} scan {bt.counters()['scan_ms']:.2f} ms", file=sys.stderr, flush=True)
+            c = bt.counters(); print(f"d={d} n={n} nq={nq} k={k} scan {c['scan_ms']:.2f} ms exact evals/query {c['rerank_pairs']/nq:.0f}", file=sys.stderr, flush=True)
 PY
 done
