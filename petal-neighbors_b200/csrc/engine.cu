@@ -103,7 +103,7 @@ struct Engine final : pn_tree {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     static constexpr size_t PIN_BYTES = 16u << 20;
     // tensor path (f32 only): augmented TF32 operands, see tc_filter.cuh
-    DevBuf d_baug, d_center, w_aaug, w_qmargin;
+    DevBuf d_baug, d_center, w_aaug, w_qmargin, w_trace;
     bool tensor_ready = false, last_used_tensor = false;
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
     float pmax = 0.f;      // max |s (p - center)|
@@ -115,7 +115,7 @@ struct Engine final : pn_tree {
             DeviceGuard g(device);
             for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &w_qraw, &w_q, &w_home,
                               &w_hist, &w_cursor, &w_order, &w_part_d, &w_part_i, &w_floor_d, &w_floor_i, &w_counters,
-                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin})
+                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin, &w_trace})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             for (int i = 0; i < 2; ++i) { if (pin_stage[i]) cudaFreeHost(pin_stage[i]); if (pin_ev[i]) cudaEventDestroy(pin_ev[i]); }
@@ -314,6 +314,12 @@ struct Engine final : pn_tree {
                 fa.counters = w_counters.as<unsigned long long>();
 #ifdef PN_TC_PROFILE
                 fa.dbg = getenv("PN_TC_DEBUG") ? (uint32_t)atoi(getenv("PN_TC_DEBUG")) : 0u;
+                if (getenv("PN_TC_TRACE")) {
+                    TRY(w_trace.ensure(12 * 64 * 4 * 8));
+                    CU(cudaMemsetAsync(w_trace.p, 0, 12 * 64 * 4 * 8, st));
+                    fa.trace = w_trace.as<long long>();
+                    fa.trace_t0 = getenv("PN_TC_TRACE_T0") ? (uint32_t)atoi(getenv("PN_TC_TRACE_T0")) : 2000u;
+                }
 #endif
                 TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
                 merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
@@ -412,6 +418,11 @@ struct Engine final : pn_tree {
             unsigned long long pc[20];
             CU(cudaMemcpy(pc, (char*)w_counters.p + 64, sizeof(pc), cudaMemcpyDeviceToHost));
             const double tiles = (double)((ft.n + tc::BN - 1) / tc::BN) * (double)((nq + 255) / 256);
+            if (getenv("PN_TC_TRACE") && w_trace.p) {
+                std::vector<long long> tr(12 * 64 * 4);
+                CU(cudaMemcpy(tr.data(), w_trace.p, tr.size() * 8, cudaMemcpyDeviceToHost));
+                if (FILE* f = fopen(getenv("PN_TC_TRACE"), "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
+            }
             fprintf(stderr, "[tc profile] cycles/tile  MMA thread: wait tempty %.0f | wait full %.0f | issue+commit %.0f   epilogue warp: wait tfull %.0f | TMEM read-out %.0f | scan+push %.0f | drain+margin %.0f   producer 0: wait empty %.0f | issue %.0f\n",
                     pc[0] / tiles, pc[1] / tiles, pc[2] / tiles, pc[6] / tiles, pc[7] / tiles, pc[8] / tiles, pc[9] / tiles, pc[12] / tiles, pc[13] / tiles);
         }

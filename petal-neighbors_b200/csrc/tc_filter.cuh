@@ -46,7 +46,10 @@ namespace tc {
 #define PROF_DECL long long pt_ = clock64(), pc_[6] = {0, 0, 0, 0, 0, 0}
 #define PROF_ADD(i) do { long long n_ = clock64(); pc_[i] += n_ - pt_; pt_ = n_; } while (0)
 #define PROF_FLUSH(base) do { for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&a.counters[8 + (base) + i_], (unsigned long long)pc_[i_]); } while (0)
+// timeline trace of CTA 0: trace[(role * 64 + (tile - trace_t0)) * 4 + event] = clock64()
+#define TRACE(role, tile, ev) do { if (a.trace && blockIdx.x == 0 && (tile) >= a.trace_t0 && (tile) < a.trace_t0 + 64u) a.trace[(((role) * 64) + ((tile) - a.trace_t0)) * 4 + (ev)] = clock64(); } while (0)
 #else
+#define TRACE(role, tile, ev)
 #define PROF_DECL
 #define PROF_ADD(i)
 #define PROF_FLUSH(base)
@@ -213,6 +216,8 @@ struct FilterArgs {
     unsigned long long* counters;  // [2] filter hits (elements passed to the exact rerank)
 #ifdef PN_TC_PROFILE
     uint32_t dbg;          // diagnostic leg isolation: 1 = epilogue skips the scan, 2 = producer skips the copies
+    long long* trace;      // optional timeline of CTA 0, 12 roles x 64 tiles x 4 events
+    uint32_t trace_t0;
 #endif
 };
 
@@ -373,6 +378,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 mbar_wait(&tempty_bar[as * MT + mt], aph ^ 1u);  // this subtile's accumulator stage has been read out
                 tc_fence_after();
                 PROF_ADD(0);
+                if (lane == 0) TRACE(8 + mt, j, 0);
                 const uint32_t d_tmem = tmem_base + (as * MT + mt) * BN;
                 for (uint32_t c = 0; c < a.nkc; ++c, ++it) {
                     if (gi == 0) {
@@ -380,6 +386,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                         tc_fence_after();
                         PROF_ADD(1);
                     }
+                    if (lane == 0 && c == 0) TRACE(8 + mt, j, 1);
                     // descriptors advance in 16-byte units: +2 per K step of 16 fp16, whole chunks per slot
                     const uint64_t bd = b_desc0 + (uint64_t)((s * a.gs + gi) * (CHUNK_BYTES >> 4));
                     const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
@@ -395,6 +402,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 if (elect_one()) tc_commit(&tfull_bar[as * MT + mt]);  // this subtile's accumulator is complete
                 __syncwarp();
                 PROF_ADD(2);
+                if (lane == 0) TRACE(8 + mt, j, 2);
             }
             if (mt == 0 && lane == 0) PROF_FLUSH(0);
         }
@@ -536,6 +544,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             mbar_wait(&tfull_bar[as * MT + mt], aph);
             tc_fence_after();
             PROF_ADD(0);
+            if (lane == 0) TRACE(warp, j, 0);
             const uint32_t taddr = tmem_base + lane_off + (as * MT + mt) * BN;
 #pragma unroll
             for (int g = 0; g < G; ++g) tmem_ld32_issue(taddr + g * 32, r[g]);
@@ -545,14 +554,17 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
             PROF_ADD(1);
+            if (lane == 0) TRACE(warp, j, 1);
 #ifdef PN_TC_PROFILE
             if (a.dbg & 1u) continue;
 #endif
 #pragma unroll
             for (int g = 0; g < G; ++g) scan32(r[g], j, g * 32);
             PROF_ADD(2);
+            if (lane == 0) TRACE(warp, j, 2);
             // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
             if (((j & 31u) == 31u) && qn > 0) { drain(qn); qn = 0; __syncwarp(); }
+            if (lane == 0) TRACE(warp, j, 3);
         }
         if (warp == 0 && lane == 0) PROF_FLUSH(6);
         if (qn > 0) { drain(qn); qn = 0; }
