@@ -251,30 +251,49 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 
-    template <int DVR, int K, int MT>
+    static constexpr size_t filter_fixed_smem(int mt, uint32_t k) {
+        // alignment slack + barriers / TMEM slot + per-warp queues + per-warp top-k lists (k entries per query)
+        return 1024 + 1024 + (size_t)4 * mt * 144 * 4 + (size_t)4 * mt * k * 32 * 8;
+    }
+    template <int DVR, int K, int MT, int NACC>
     int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
-        const size_t smem = 1024 + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES + 1024 + (size_t)4 * MT * 144 * 4 + (size_t)4 * MT * K * 32 * 8;
-        auto kern = tc::knn_filter_kernel<DVR, K, MT>;
+        const size_t smem = filter_fixed_smem(MT, fa.k) + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES;
+        auto kern = tc::knn_filter_kernel<DVR, K, MT, NACC>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (fa.nq + MT * tc::BM - 1) / (MT * tc::BM);
         kern<<<grid, (5 * MT + 2) * 32, smem, st>>>(map_a, d_baug.as<unsigned char>(), fa);
         CU(cudaGetLastError());
         return PN_OK;
     }
+    // subtiles per CTA: 4 (one accumulator stage each) for narrow rows, where the epilogue is the bound; 2 (two
+    // stages each) where the tensor pipe is; 1 when the resident A operand of two subtiles no longer fits
+    int filter_subtiles(uint32_t nkc) const {
+#ifdef PN_TC_PROFILE
+        if (getenv("PN_TC_MT")) return atoi(getenv("PN_TC_MT"));
+#endif
+        return nkc <= 2 ? 4 : (nkc <= 6 ? 2 : 1);
+    }
     template <int K>
     int launch_filter_k(const CUtensorMap& map_a, tc::FilterArgs& fa, cudaStream_t st) {
-        const int mt = fa.nkc <= 6 ? 2 : 1;
-        const size_t budget = 220 * 1024;
-        fa.gs = fa.nkc == 1 ? 4 : (fa.nkc == 2 ? 2 : 1);
-        fa.stages = (uint32_t)std::min<size_t>(fa.gs > 1 ? 4 : 12, (budget - 7168 - (size_t)4 * mt * K * 32 * 8 - (size_t)mt * fa.nkc * tc::A_CHUNK_BYTES) / (tc::CHUNK_BYTES * fa.gs));
+        const int mt = filter_subtiles(fa.nkc);
+        const size_t budget = 224 * 1024;
+        // ring groups of 16 KB (one full/empty barrier pair per group): 2 tiles at Kp = 32, 1 tile at Kp = 64, chunks beyond
+        fa.gs = fa.nkc == 1 ? 2 : (fa.nkc == 2 ? 2 : 1);
+        const size_t fixed = filter_fixed_smem(mt, fa.k) + (size_t)mt * fa.nkc * tc::A_CHUNK_BYTES;
+        fa.stages = fixed < budget ? (uint32_t)std::min<size_t>(fa.gs > 1 ? 8 : 12, (budget - fixed) / (tc::CHUNK_BYTES * fa.gs)) : 0;
         fa.stages &= ~1u;  // even: each ring stage always belongs to the same one of the two producer warps
         if (fa.stages < 2) return fail(PN_CUDA, "tensor path: shared memory budget too small for this dimension");
-        if (mt == 2) {
-            if (dt.dv == 4) return launch_filter_t<4, K, 2>(map_a, fa, st);
-            if (dt.dv == 8) return launch_filter_t<8, K, 2>(map_a, fa, st);
-            return launch_filter_t<0, K, 2>(map_a, fa, st);
+        if (mt == 4) {
+            if (dt.dv == 4) return launch_filter_t<4, K, 4, 1>(map_a, fa, st);
+            if (dt.dv == 8) return launch_filter_t<8, K, 4, 1>(map_a, fa, st);
+            return launch_filter_t<0, K, 4, 1>(map_a, fa, st);
         }
-        return launch_filter_t<0, K, 1>(map_a, fa, st);
+        if (mt == 2) {
+            if (dt.dv == 4) return launch_filter_t<4, K, 2, 2>(map_a, fa, st);
+            if (dt.dv == 8) return launch_filter_t<8, K, 2, 2>(map_a, fa, st);
+            return launch_filter_t<0, K, 2, 2>(map_a, fa, st);
+        }
+        return launch_filter_t<0, K, 1, 2>(map_a, fa, st);
     }
 
     // tensor k-NN: same contract as knn_device
@@ -417,7 +436,7 @@ struct Engine final : pn_tree {
         if (last_used_tensor && w_counters.cap >= 256) {
             unsigned long long pc[20];
             CU(cudaMemcpy(pc, (char*)w_counters.p + 64, sizeof(pc), cudaMemcpyDeviceToHost));
-            const double tiles = (double)((ft.n + tc::BN - 1) / tc::BN) * (double)((nq + 255) / 256);
+            const double tiles = (double)((ft.n + tc::BN - 1) / tc::BN) * (double)((nq + 128 * filter_subtiles(kp / tc::KC) - 1) / (128 * filter_subtiles(kp / tc::KC)));
             if (getenv("PN_TC_TRACE") && w_trace.p) {
                 std::vector<long long> tr(12 * 64 * 4);
                 CU(cudaMemcpy(tr.data(), w_trace.p, tr.size() * 8, cudaMemcpyDeviceToHost));

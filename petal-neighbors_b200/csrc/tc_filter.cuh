@@ -22,6 +22,7 @@
 // Queries whose scaled norm leaves the fp16 range get E_q = +inf: every point is reranked exactly.
 //
 // Structure (one CTA = MT x 128 queries, persistent over all point tiles; 1 CTA / SM):
+//   (MT = 2 or 4 subtiles, see knn_filter_kernel)
 //   warps 4MT, 5MT+1 : two TMA producers on alternate ring groups: 1-D bulk copies (cp.async.bulk) of
 //                the pre-tiled, pre-swizzled B image ([128 rows x 32 fp16] chunks, 64B swizzle)
 //   warps 4MT+1.. : MT tcgen05.mma issuers (one elected lane each, one per 128-query subtile),
@@ -60,7 +61,6 @@ constexpr int BN = 128;            // points per B tile (TMEM columns per accumu
 constexpr int KC = 32;             // fp16 elements per K chunk = one 64-byte swizzle row
 constexpr int CHUNK_BYTES = BN * KC * 2;   // 8 KB: one B ring slot
 constexpr int A_CHUNK_BYTES = BM * KC * 2; // 8 KB: one resident A chunk
-constexpr int NUM_ACC = 2;         // accumulator stages in TMEM
 constexpr int NSLOT = 6;           // K slots used by the folded norms
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -287,7 +287,13 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
     q_margin[i] = in_range ? e : pos_inf<float>();
 }
 
-template <int DVR, int K, int MT>
+// MT subtiles of 128 queries per CTA, NUM_ACC accumulator stages per subtile (MT x NUM_ACC x 128 = the 512 TMEM
+// columns).  Wide rows (tensor-pipe bound) run MT = 2 x NUM_ACC = 2.  Narrow rows (d <= 58), where the epilogue
+// is the bound and each warp's wait -> read-out -> test -> push chain is latency-bound, run MT = 4 x NUM_ACC = 1:
+// sixteen epilogue warps, four independent chains per scheduler, and the tensor pipe round-robins over the four
+// subtiles so that one subtile's read-out hides behind the other three's MMAs.  With 22 warps the register
+// file allows 93 registers per thread, so a stage is read out and tested in two halves of 64 columns.
+template <int DVR, int K, int MT, int NUM_ACC>
 __global__ void __launch_bounds__((5 * MT + 2) * 32, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char* __restrict__ baug, const FilterArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -304,8 +310,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
     uint32_t* qbuf = tmem_slot + 4;  // per epilogue warp: QWORDS x u32 of queue / hand-over scratch
     constexpr int QWORDS = 144;
-    float* tk_d = reinterpret_cast<float*>(qbuf + 4 * MT * QWORDS);   // [EPI_WARPS][K][32]
-    uint32_t* tk_i = reinterpret_cast<uint32_t*>(tk_d + 4 * MT * K * 32);
+    float* tk_d = reinterpret_cast<float*>(qbuf + 4 * MT * QWORDS);   // [EPI_WARPS][k][32], k = a.k <= K
+    uint32_t* tk_i = reinterpret_cast<uint32_t*>(tk_d + 4 * MT * a.k * 32);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
     constexpr int EPI_WARPS = 4 * MT;
@@ -424,7 +430,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         float* x_s = reinterpret_cast<float*>(q_prow + 80);
         uint32_t* x_id = q_prow + 112;
         SmemTopK topk;
-        topk.init(tk_d + warp * (K * 32), tk_i + warp * (K * 32), lane, a.k, active);
+        topk.init(tk_d + warp * (a.k * 32), tk_i + warp * (a.k * 32), lane, a.k, active);
         if (a.floor_d && active) topk.set_floor(a.floor_d[qrow], a.floor_i[qrow]);
         const float margin = active ? a.q_margin[qrow] : 0.f;  // E_q (scaled units)
         const float t2s = a.t2_scale;
@@ -476,8 +482,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             }
         };
 
-        // threshold test of 32 accumulator columns [col0, col0+32) of tile j; hits go to the queue
-        auto scan32 = [&](const uint32_t (&r)[32], uint32_t j, int col0) {
+        // threshold test of 32 accumulator columns [col0, col0+32) of tile j: per-lane hit mask (0 in every lane
+        // when no lane of the warp has a hit)
+        auto test32 = [&](const uint32_t (&r)[32], uint32_t j, int col0) -> uint32_t {
             // block minima over 4 blocks of 8 consecutive columns; only blocks that pass are searched
             float mb[4];
 #pragma unroll
@@ -487,7 +494,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 mb[b] = fminf(fminf(x0, x1), fminf(__uint_as_float(r[8 * b + 6]), __uint_as_float(r[8 * b + 7])));
             }
             const float m = fminf(fminf(mb[0], mb[1]), fminf(mb[2], mb[3]));
-            if (!__any_sync(full, m <= theta)) return;
+            if (!__any_sync(full, m <= theta)) return 0u;
             uint32_t bits = 0;
             if (m <= theta) {
 #pragma unroll
@@ -500,6 +507,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 const int valid = (int)t.n - (int)(j * BN + col0);  // rows past the last point are zero-filled
                 if (valid < 32) bits &= valid > 0 ? ((1u << valid) - 1u) : 0u;
             }
+            return bits;
+        };
+        // hits of one 32-column group go to the warp's queue (ballot compaction); a full queue is drained at once
+        auto push32 = [&](uint32_t bits, uint32_t j, int col0) {
             for (;;) {
                 const bool has = bits != 0;
                 const unsigned mask = __ballot_sync(full, has);
@@ -534,7 +545,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         // The whole 128-column accumulator stage is pulled into registers at once and released
         // BEFORE it is tested: with only two stages in TMEM the MMA -> read-out -> release loop of a
         // stage is the critical path, so nothing but the TMEM loads may sit inside it.
-        constexpr int G = BN / 32;
+        constexpr int H = MT > 2 ? 2 : 1;   // read-out halves per stage
+        constexpr int G = BN / 32 / H;      // 32-column groups per half
         uint32_t r[G][32];
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         PROF_DECL;
@@ -546,20 +558,34 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             PROF_ADD(0);
             if (lane == 0) TRACE(warp, j, 0);
             const uint32_t taddr = tmem_base + lane_off + (as * MT + mt) * BN;
+            uint32_t bits[H * G];
+            bool any = false;
 #pragma unroll
-            for (int g = 0; g < G; ++g) tmem_ld32_issue(taddr + g * 32, r[g]);
+            for (int h = 0; h < H; ++h) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) tmem_ld_wait(r[g]);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
-            PROF_ADD(1);
-            if (lane == 0) TRACE(warp, j, 1);
+                for (int g = 0; g < G; ++g) tmem_ld32_issue(taddr + (h * G + g) * 32, r[g]);
+#pragma unroll
+                for (int g = 0; g < G; ++g) tmem_ld_wait(r[g]);
+                if (h == H - 1) {
+                    // the stage is released as soon as its last column is in registers, BEFORE that half is
+                    // tested: the MMA -> read-out -> release loop of a stage is the critical path
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
+                    PROF_ADD(1);
+                    if (lane == 0) TRACE(warp, j, 1);
+                }
 #ifdef PN_TC_PROFILE
-            if (a.dbg & 1u) continue;
+                if (a.dbg & 1u) continue;
 #endif
 #pragma unroll
-            for (int g = 0; g < G; ++g) scan32(r[g], j, g * 32);
+                for (int g = 0; g < G; ++g) { bits[h * G + g] = test32(r[g], j, (h * G + g) * 32); any |= bits[h * G + g] != 0; }
+            }
+            // the variable-length part (queue pushes, exact reranks) comes after the stage has been released
+            if (__any_sync(full, any)) {
+#pragma unroll
+                for (int g = 0; g < H * G; ++g) push32(bits[g], j, g * 32);
+            }
             PROF_ADD(2);
             if (lane == 0) TRACE(warp, j, 2);
             // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
