@@ -44,16 +44,20 @@ namespace tc {
 
 // -DPN_TC_PROFILE: per-role cycle accounting into counters[8..] (diagnostic builds only)
 #ifdef PN_TC_PROFILE
-#define PROF_DECL long long pt_ = clock64(), pc_[6] = {0, 0, 0, 0, 0, 0}
-#define PROF_ADD(i) do { long long n_ = clock64(); pc_[i] += n_ - pt_; pt_ = n_; } while (0)
+// 32-bit clocks and accumulators: the roles run with as few as 80 registers per thread
+#define PROF_DECL unsigned pt_ = (unsigned)clock(), pc_[6] = {0, 0, 0, 0, 0, 0}
+#define PROF_ADD(i) do { unsigned n_ = (unsigned)clock(); pc_[i] += n_ - pt_; pt_ = n_; } while (0)
 #define PROF_FLUSH(base) do { for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&a.counters[8 + (base) + i_], (unsigned long long)pc_[i_]); } while (0)
-// timeline trace of CTA 0: trace[(role * 64 + (tile - trace_t0)) * 4 + event] = clock64()
-#define TRACE(role, tile, ev) do { if (a.trace && blockIdx.x == 0 && (tile) >= a.trace_t0 && (tile) < a.trace_t0 + 64u) a.trace[(((role) * 64) + ((tile) - a.trace_t0)) * 4 + (ev)] = clock64(); } while (0)
 #else
-#define TRACE(role, tile, ev)
 #define PROF_DECL
 #define PROF_ADD(i)
 #define PROF_FLUSH(base)
+#endif
+// -DPN_TC_TRACE (with PN_TC_PROFILE): timeline trace of CTA 0: trace[(role * 64 + (tile - trace_t0)) * 4 + event] = clock64()
+#if defined(PN_TC_PROFILE) && defined(PN_TC_TRACE)
+#define TRACE(role, tile, ev) do { if (a.trace && blockIdx.x == 0 && (tile) >= a.trace_t0 && (tile) < a.trace_t0 + 64u) a.trace[(((role) * 64) + ((tile) - a.trace_t0)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(role, tile, ev)
 #endif
 
 constexpr int BM = 128;            // queries per accumulator tile (TMEM lanes)
@@ -482,9 +486,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             }
         };
 
-        // threshold test of 32 accumulator columns [col0, col0+32) of tile j: per-lane hit mask (0 in every lane
-        // when no lane of the warp has a hit)
-        auto test32 = [&](const uint32_t (&r)[32], uint32_t j, int col0) -> uint32_t {
+        // threshold test of 32 accumulator columns [col0, col0+32) of tile j: per-lane hit mask in `bits`; returns
+        // (warp-uniform) whether any lane of the warp has a hit
+        auto test32 = [&](const uint32_t (&r)[32], uint32_t j, int col0, uint32_t& bits) -> bool {
             // block minima over 4 blocks of 8 consecutive columns; only blocks that pass are searched
             float mb[4];
 #pragma unroll
@@ -494,8 +498,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 mb[b] = fminf(fminf(x0, x1), fminf(__uint_as_float(r[8 * b + 6]), __uint_as_float(r[8 * b + 7])));
             }
             const float m = fminf(fminf(mb[0], mb[1]), fminf(mb[2], mb[3]));
-            if (!__any_sync(full, m <= theta)) return 0u;
-            uint32_t bits = 0;
+            bits = 0;
+            if (!__any_sync(full, m <= theta)) return false;
             if (m <= theta) {
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
@@ -507,7 +511,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 const int valid = (int)t.n - (int)(j * BN + col0);  // rows past the last point are zero-filled
                 if (valid < 32) bits &= valid > 0 ? ((1u << valid) - 1u) : 0u;
             }
-            return bits;
+            return true;
         };
         // hits of one 32-column group go to the warp's queue (ballot compaction); a full queue is drained at once
         auto push32 = [&](uint32_t bits, uint32_t j, int col0) {
@@ -542,55 +546,144 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             }
         };
 
+        // fused threshold test + push of one group (two-stage configurations): a threshold tightened by a drain
+        // already applies to the next group of the same tile
+        auto scan32 = [&](const uint32_t (&r)[32], uint32_t j, int col0) {
+            // block minima over 4 blocks of 8 consecutive columns; only blocks that pass are searched
+            float mb[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float x0 = fminf(__uint_as_float(r[8 * b]), fminf(__uint_as_float(r[8 * b + 1]), __uint_as_float(r[8 * b + 2])));
+                const float x1 = fminf(__uint_as_float(r[8 * b + 3]), fminf(__uint_as_float(r[8 * b + 4]), __uint_as_float(r[8 * b + 5])));
+                mb[b] = fminf(fminf(x0, x1), fminf(__uint_as_float(r[8 * b + 6]), __uint_as_float(r[8 * b + 7])));
+            }
+            const float m = fminf(fminf(mb[0], mb[1]), fminf(mb[2], mb[3]));
+            if (!__any_sync(full, m <= theta)) return;
+            uint32_t bits = 0;
+            if (m <= theta) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (mb[b] <= theta) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) bits |= (__uint_as_float(r[8 * b + i]) <= theta ? 1u : 0u) << (8 * b + i);
+                    }
+                }
+                const int valid = (int)t.n - (int)(j * BN + col0);  // rows past the last point are zero-filled
+                if (valid < 32) bits &= valid > 0 ? ((1u << valid) - 1u) : 0u;
+            }
+            for (;;) {
+                const bool has = bits != 0;
+                const unsigned mask = __ballot_sync(full, has);
+                if (!mask) break;
+                if (has) {
+                    const int i = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int slot = qn + __popc(mask & lt_mask);
+                    const uint32_t prow = j * BN + col0 + i;
+                    q_prow[slot] = prow;
+                    q_owner[slot] = (unsigned char)lane;
+                    // the exact rerank happens tiles later: start pulling the candidate's row and id now
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.pts + (size_t)prow * DV));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.ids + prow));
+                }
+                qn += __popc(mask);
+                hits += __popc(mask);
+                __syncwarp();
+                if (qn >= 32) {
+                    drain(32);
+                    const int rest = qn - 32;  // < 32
+                    uint32_t tp = 0; unsigned char to = 0;
+                    if (lane < rest) { tp = q_prow[32 + lane]; to = q_owner[32 + lane]; }
+                    __syncwarp();
+                    if (lane < rest) { q_prow[lane] = tp; q_owner[lane] = to; }
+                    __syncwarp();
+                    qn = rest;
+                }
+            }
+        };
+
         // The whole 128-column accumulator stage is pulled into registers at once and released
         // BEFORE it is tested: with only two stages in TMEM the MMA -> read-out -> release loop of a
         // stage is the critical path, so nothing but the TMEM loads may sit inside it.
-        constexpr int H = MT > 2 ? 2 : 1;   // read-out halves per stage
-        constexpr int G = BN / 32 / H;      // 32-column groups per half
-        uint32_t r[G][32];
-        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        PROF_DECL;
-        for (uint32_t j = 0; j < a.n_tiles; ++j) {
-            const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
-            PROF_ADD(3);
-            mbar_wait(&tfull_bar[as * MT + mt], aph);
-            tc_fence_after();
-            PROF_ADD(0);
-            if (lane == 0) TRACE(warp, j, 0);
-            const uint32_t taddr = tmem_base + lane_off + (as * MT + mt) * BN;
-            uint32_t bits[H * G];
-            bool any = false;
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-#pragma unroll
-                for (int g = 0; g < G; ++g) tmem_ld32_issue(taddr + (h * G + g) * 32, r[g]);
-#pragma unroll
+        if constexpr (MT <= 2) {
+            constexpr int G = BN / 32;
+            uint32_t r[G][32];
+            const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+            PROF_DECL;
+            for (uint32_t j = 0; j < a.n_tiles; ++j) {
+                const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
+                PROF_ADD(3);
+                mbar_wait(&tfull_bar[as * MT + mt], aph);
+                tc_fence_after();
+                PROF_ADD(0);
+                const uint32_t taddr = tmem_base + lane_off + (as * MT + mt) * BN;
+    #pragma unroll
+                for (int g = 0; g < G; ++g) tmem_ld32_issue(taddr + g * 32, r[g]);
+    #pragma unroll
                 for (int g = 0; g < G; ++g) tmem_ld_wait(r[g]);
-                if (h == H - 1) {
-                    // the stage is released as soon as its last column is in registers, BEFORE that half is
-                    // tested: the MMA -> read-out -> release loop of a stage is the critical path
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
-                    PROF_ADD(1);
-                    if (lane == 0) TRACE(warp, j, 1);
-                }
-#ifdef PN_TC_PROFILE
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
+                PROF_ADD(1);
+    #ifdef PN_TC_PROFILE
                 if (a.dbg & 1u) continue;
-#endif
-#pragma unroll
-                for (int g = 0; g < G; ++g) { bits[h * G + g] = test32(r[g], j, (h * G + g) * 32); any |= bits[h * G + g] != 0; }
+    #endif
+    #pragma unroll
+                for (int g = 0; g < G; ++g) scan32(r[g], j, g * 32);
+                PROF_ADD(2);
+                // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
+                if (((j & 31u) == 31u) && qn > 0) { drain(qn); qn = 0; __syncwarp(); }
             }
-            // the variable-length part (queue pushes, exact reranks) comes after the stage has been released
-            if (__any_sync(full, any)) {
-#pragma unroll
-                for (int g = 0; g < H * G; ++g) push32(bits[g], j, g * 32);
+        } else {
+            constexpr int H = MT > 2 ? 2 : 1;   // read-out halves per stage
+            constexpr int G = BN / 32 / H;      // 32-column groups per half
+            uint32_t r[G][32];
+            const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+            PROF_DECL;
+            for (uint32_t j = 0; j < a.n_tiles; ++j) {
+                const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
+                PROF_ADD(3);
+                mbar_wait(&tfull_bar[as * MT + mt], aph);
+                tc_fence_after();
+                PROF_ADD(0);
+                if (lane == 0) TRACE(warp, j, 0);
+                const uint32_t taddr = tmem_base + lane_off + (as * MT + mt) * BN;
+                uint32_t bits[H * G];  // hit masks (H = 2)
+                uint32_t any = 0;  // groups with a hit in some lane (warp-uniform)
+    #pragma unroll
+                for (int h = 0; h < H; ++h) {
+    #pragma unroll
+                    for (int g = 0; g < G; ++g) tmem_ld32_issue(taddr + (h * G + g) * 32, r[g]);
+    #pragma unroll
+                    for (int g = 0; g < G; ++g) tmem_ld_wait(r[g]);
+                    if (h == H - 1) {
+                        // the stage is released as soon as its last column is in registers, BEFORE that half is
+                        // tested: the MMA -> read-out -> release loop of a stage is the critical path
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
+                        PROF_ADD(1);
+                        if (lane == 0) TRACE(warp, j, 1);
+                    }
+    #ifdef PN_TC_PROFILE
+                    if (a.dbg & 1u) continue;
+    #endif
+                    // every test comes before any push, so that the variable-length part (queue pushes, exact reranks)
+                    // never delays the next read-out
+    #pragma unroll
+                    for (int g = 0; g < G; ++g) any |= test32(r[g], j, (h * G + g) * 32, bits[h * G + g]) ? 1u << (h * G + g) : 0u;
+                }
+                if (any) {
+    #pragma unroll
+                    for (int g = 0; g < H * G; ++g)
+                        if (any & (1u << g)) push32(bits[g], j, g * 32);
+                }
+                PROF_ADD(2);
+                if (lane == 0) TRACE(warp, j, 2);
+                // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
+                if (((j & 31u) == 31u) && qn > 0) { drain(qn); qn = 0; __syncwarp(); }
+                if (lane == 0) TRACE(warp, j, 3);
             }
-            PROF_ADD(2);
-            if (lane == 0) TRACE(warp, j, 2);
-            // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
-            if (((j & 31u) == 31u) && qn > 0) { drain(qn); qn = 0; __syncwarp(); }
-            if (lane == 0) TRACE(warp, j, 3);
         }
         if (warp == 0 && lane == 0) PROF_FLUSH(6);
         if (qn > 0) { drain(qn); qn = 0; }

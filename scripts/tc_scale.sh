@@ -10,7 +10,7 @@ from petal_neighbors_b200 import synth
 for d, n in ((128, 1000000), (16, 1000000)):
     pts = synth.uniform(n, d, 2, np.float32)
     bt = pn.BallTree.euclidean(pts, algo=pn.PN_ALGO_TENSOR)
-    for nq in (${NQS:-37888},):
+    for nq in (${NQS:-75776},):
         Q = synth.uniform(nq, d, 3, np.float32)
         for k in (1, 10):
             bt.query_batch(Q, k)
