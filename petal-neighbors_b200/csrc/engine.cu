@@ -260,8 +260,9 @@ struct Engine final : pn_tree {
         const size_t smem = filter_fixed_smem(MT, fa.k) + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES;
         auto kern = tc::knn_filter_kernel<DVR, K, MT, NACC>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (fa.nq + MT * tc::BM - 1) / (MT * tc::BM);
-        kern<<<grid, (5 * MT + 2) * 32, smem, st>>>(map_a, d_baug.as<unsigned char>(), fa);
+        const unsigned gx = (fa.nq - fa.row0 + MT * tc::BM - 1) / (MT * tc::BM);
+        const unsigned gy = (fa.n_tiles + fa.tiles_per_split - 1) / fa.tiles_per_split;
+        kern<<<dim3(gx, gy), (5 * MT + 2) * 32, smem, st>>>(map_a, d_baug.as<unsigned char>(), fa);
         CU(cudaGetLastError());
         return PN_OK;
     }
@@ -307,8 +308,31 @@ struct Engine final : pn_tree {
             const bool k1 = (k == 1);
             const uint32_t KP = k1 ? 1 : 16;
             const uint32_t n_pass = (k + KP - 1) / KP;
-            TRY(w_part_d.ensure((size_t)nq * KP * 4));
-            TRY(w_part_i.ensure((size_t)nq * KP * 4));
+            // Launch plan.  A CTA serves QT = 128 x subtiles queries against the whole point stream, so whole waves of
+            // n_sms CTAs keep every SM busy; what is left (fewer query tiles than SMs: the tail of a large batch, or
+            // all of a small one) runs as a second launch whose grid.y splits the point stream S ways -- each CTA scans
+            // 1/S of the points for its queries and writes its own top-k list, merged by merge_lists_kernel.
+            const uint32_t n_tiles = (uint32_t)((ft.n + tc::BN - 1) / tc::BN);
+            const uint32_t QT = 128u * (uint32_t)filter_subtiles(kp / tc::KC);
+            const uint32_t n_qt = (nq + QT - 1) / QT;
+            uint32_t main_qt = n_qt / (uint32_t)n_sms * (uint32_t)n_sms, tail_qt = n_qt - main_qt, S = 1, tps = n_tiles;
+            if (tail_qt) {
+                // S minimises the tail's duration in units of one full scan, ceil(tail_qt S / n_sms) / S, with a charge
+                // of 12 % per extra split (measured: every split starts its own top-k lists, so the exact reranks of a
+                // query grow ~ linearly with S, and there is one more list to merge)
+                const uint32_t s_max = std::max<uint32_t>(1u, std::min<uint32_t>({std::max<uint32_t>(16u, (uint32_t)n_sms / tail_qt), n_tiles / 64u, (uint32_t)MAX_LISTS}));
+                double best = 1e30;
+                for (uint32_t c = 1; c <= s_max; ++c) {
+                    const double cost = (double)((tail_qt * c + n_sms - 1) / n_sms) / c * (1.0 + 0.12 * (c - 1));
+                    if (cost < best) { best = cost; S = c; }
+                }
+                tps = (n_tiles + S - 1) / S;
+                S = (n_tiles + tps - 1) / tps;  // every split non-empty
+            }
+            if (S == 1) { main_qt = n_qt; tail_qt = 0; }
+            const uint32_t q_main = (uint32_t)std::min<uint64_t>((uint64_t)main_qt * QT, nq), q_tail = nq - q_main;
+            TRY(w_part_d.ensure(((size_t)q_main + (size_t)S * q_tail) * KP * 4));
+            TRY(w_part_i.ensure(((size_t)q_main + (size_t)S * q_tail) * KP * 4));
             TRY(w_counters.ensure(256));
             if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * 4)); TRY(w_floor_i.ensure((size_t)nq * 4)); }
             CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
@@ -324,8 +348,8 @@ struct Engine final : pn_tree {
                 tc::FilterArgs fa{};
                 fa.t = *reinterpret_cast<DevTree<float>*>(&dt);
                 fa.q = reinterpret_cast<const float4*>(qpad); fa.q_margin = w_qmargin.as<float>();
-                fa.nq = nq; fa.k = kk;
-                fa.n_tiles = (uint32_t)((ft.n + tc::BN - 1) / tc::BN);
+                fa.k = kk;
+                fa.n_tiles = n_tiles;
                 fa.nkc = kp / tc::KC;
                 fa.t2_scale = tscale * tscale * (1.0f + (float)(ft.d + 4) * 1.1920928955078125e-07f);
                 fa.part_d = w_part_d.as<float>(); fa.part_i = w_part_i.as<uint32_t>();
@@ -340,13 +364,29 @@ struct Engine final : pn_tree {
                     fa.trace_t0 = getenv("PN_TC_TRACE_T0") ? (uint32_t)atoi(getenv("PN_TC_TRACE_T0")) : 2000u;
                 }
 #endif
-                TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
-                merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
-                    w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, nq, kk, idx_out, dist_out, k, p * KP,
-                    n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr,
-                    self_query ? d_ids.as<uint32_t>() : nullptr);
-                CU(cudaGetLastError());
-                counters.kernel_launches += 2;
+                A* fl_d = n_pass > 1 ? w_floor_d.as<A>() : nullptr;
+                uint32_t* fl_i = n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr;
+                const uint32_t* rmap = self_query ? d_ids.as<uint32_t>() : nullptr;
+                if (q_main) {
+                    fa.row0 = 0; fa.nq = q_main; fa.tiles_per_split = n_tiles;
+                    TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
+                    merge_lists_kernel<A, uint32_t><<<(q_main + 127) / 128, 128, 0, st>>>(
+                        w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, q_main, kk, idx_out, dist_out, k, p * KP, fl_d, fl_i, rmap);
+                    CU(cudaGetLastError());
+                    counters.kernel_launches += 2;
+                }
+                if (q_tail) {
+                    fa.row0 = q_main; fa.nq = nq; fa.tiles_per_split = tps;
+                    fa.part_d = w_part_d.as<float>() + (size_t)q_main * kk; fa.part_i = w_part_i.as<uint32_t>() + (size_t)q_main * kk;
+                    TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
+                    // with a row map (self query) the merge addresses output rows absolutely; otherwise the outputs are offset
+                    merge_lists_kernel<A, uint32_t><<<(q_tail + 127) / 128, 128, 0, st>>>(
+                        reinterpret_cast<const A*>(fa.part_d), fa.part_i, S, q_tail, kk, rmap ? idx_out : idx_out + (size_t)q_main * k,
+                        rmap ? dist_out : dist_out + (size_t)q_main * k, k, p * KP, fl_d ? fl_d + q_main : nullptr,
+                        fl_i ? fl_i + q_main : nullptr, rmap ? rmap + q_main : nullptr);
+                    CU(cudaGetLastError());
+                    counters.kernel_launches += 2;
+                }
                 counters.filter_pairs += (uint64_t)ft.n * nq;
             }
             CU(cudaEventRecord(ev[3], st));

@@ -207,13 +207,16 @@ struct FilterArgs {
     DevTree<float> t;
     const float4* q;       // nq x dpad exact zero-padded queries (rerank)
     const float* q_margin; // nq: E_q in scaled units (+inf when the query leaves the fp16 range)
-    uint32_t nq, k;
+    uint32_t nq, k;        // nq: one past the last query row of this launch
+    uint32_t row0;         // first query row of this launch (CTA x serves rows row0 + x MT 128 ...)
     uint32_t n_tiles;      // ceil(n / BN)
+    uint32_t tiles_per_split;  // grid.y splits the point stream: CTA (x, y) scans tiles [y tps, min(n_tiles, (y+1) tps))
+                               // and writes list y; the lists are merged by merge_lists_kernel
     uint32_t nkc;          // K chunks (Kp / 32)
     uint32_t stages;       // B ring depth in groups
     uint32_t gs;           // chunks per ring group (one full/empty barrier pair per group)
     float t2_scale;        // s^2 (1 + (d+4) 2^-23): exact squared threshold -> scaled filter units
-    float* part_d;         // [nq][k]
+    float* part_d;         // [grid.y][nq - row0][k]
     uint32_t* part_i;
     const float* floor_d;
     const uint32_t* floor_i;
@@ -337,7 +340,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    const uint32_t row_base = blockIdx.x * (MT * BM);
+    const uint32_t row_base = a.row0 + blockIdx.x * (MT * BM);
+    // this CTA's share of the point stream (every split is non-empty: the host guarantees grid.y tps < n_tiles + tps)
+    const uint32_t j_begin = blockIdx.y * a.tiles_per_split;
+    const uint32_t n_my = min(a.n_tiles - j_begin, a.tiles_per_split);
 
     if (warp == EPI_WARPS || warp == EPI_WARPS + MT + 1) {
         // ================= TMA producers: two warps, alternate ring groups (stages is even) =================
@@ -351,8 +357,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             }
             // B ring: groups of `gs` chunks share one full/empty barrier pair, so the consumers pay one
             // barrier wait per group instead of one per 8 KB chunk
-            const uint32_t total = a.n_tiles * a.nkc;
+            const uint32_t total = n_my * a.nkc;
             const uint32_t n_groups = (total + a.gs - 1) / a.gs;
+            const unsigned char* bsrc = baug + (size_t)j_begin * a.nkc * CHUNK_BYTES;
             PROF_DECL;
             for (uint32_t g = pid; g < n_groups; g += 2) {
                 const uint32_t s = g % a.stages, ph = (g / a.stages) & 1u;
@@ -365,7 +372,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
 #endif
                 // chunk `it` of the stream sits at byte it * CHUNK_BYTES of the tiled image: one contiguous span per group
                 mbar_expect_tx(&full_bar[s], cnt * CHUNK_BYTES);
-                bulk_copy(smem_b + (size_t)s * a.gs * CHUNK_BYTES, baug + (size_t)first * CHUNK_BYTES, cnt * CHUNK_BYTES, &full_bar[s]);
+                bulk_copy(smem_b + (size_t)s * a.gs * CHUNK_BYTES, bsrc + (size_t)first * CHUNK_BYTES, cnt * CHUNK_BYTES, &full_bar[s]);
             }
             if (pid == 0) PROF_FLUSH(12);
         }
@@ -379,11 +386,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             constexpr uint32_t idesc = make_idesc_f16(BM, BN);
             const uint64_t a_desc0 = make_desc_sw64(smem_u32(smem_a)) + (uint64_t)(mt * a.nkc * (A_CHUNK_BYTES >> 4));
             const uint64_t b_desc0 = make_desc_sw64(smem_u32(smem_b));
-            const uint32_t total = a.n_tiles * a.nkc;
+            const uint32_t total = n_my * a.nkc;
             mbar_wait(a_bar, 0);
             uint32_t it = 0, g = 0, gi = 0, s = 0, sph = 0;  // stream position: group, chunk in group, ring stage, its phase
             PROF_DECL;
-            for (uint32_t j = 0; j < a.n_tiles; ++j) {
+            for (uint32_t j = 0; j < n_my; ++j) {
                 const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
                 mbar_wait(&tempty_bar[as * MT + mt], aph ^ 1u);  // this subtile's accumulator stage has been read out
                 tc_fence_after();
@@ -610,8 +617,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             uint32_t r[G][32];
             const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
             PROF_DECL;
-            for (uint32_t j = 0; j < a.n_tiles; ++j) {
-                const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
+            for (uint32_t jr = 0; jr < n_my; ++jr) {
+                const uint32_t j = j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
+                const uint32_t as = jr % NUM_ACC, aph = (jr / NUM_ACC) & 1u;
                 PROF_ADD(3);
                 mbar_wait(&tfull_bar[as * MT + mt], aph);
                 tc_fence_after();
@@ -640,8 +648,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             uint32_t r[G][32];
             const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
             PROF_DECL;
-            for (uint32_t j = 0; j < a.n_tiles; ++j) {
-                const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
+            for (uint32_t jr = 0; jr < n_my; ++jr) {
+                const uint32_t j = j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
+                const uint32_t as = jr % NUM_ACC, aph = (jr / NUM_ACC) & 1u;
                 PROF_ADD(3);
                 mbar_wait(&tfull_bar[as * MT + mt], aph);
                 tc_fence_after();
@@ -688,7 +697,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         if (warp == 0 && lane == 0) PROF_FLUSH(6);
         if (qn > 0) { drain(qn); qn = 0; }
         if (active) {
-            const size_t base = (size_t)qrow * a.k;
+            const size_t base = ((size_t)blockIdx.y * (a.nq - a.row0) + (qrow - a.row0)) * a.k;
             topk.store(a.part_d + base, a.part_i + base);
         }
         if (a.counters && lane == 0) atomicAdd(&a.counters[2], hits);
