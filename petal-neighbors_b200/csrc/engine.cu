@@ -103,7 +103,7 @@ struct Engine final : pn_tree {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     static constexpr size_t PIN_BYTES = 16u << 20;
     // tensor path (f32 only): augmented TF32 operands, see tc_filter.cuh
-    DevBuf d_baug, d_center, w_aaug, w_qmargin, w_trace;
+    DevBuf d_baug, d_center, w_aaug, w_qmargin, w_trace, w_gbound;
     bool tensor_ready = false, last_used_tensor = false;
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
     float pmax = 0.f;      // max |s (p - center)|
@@ -115,7 +115,7 @@ struct Engine final : pn_tree {
             DeviceGuard g(device);
             for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &w_qraw, &w_q, &w_home,
                               &w_hist, &w_cursor, &w_order, &w_part_d, &w_part_i, &w_floor_d, &w_floor_i, &w_counters,
-                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin, &w_trace})
+                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin, &w_trace, &w_gbound})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             for (int i = 0; i < 2; ++i) { if (pin_stage[i]) cudaFreeHost(pin_stage[i]); if (pin_ev[i]) cudaEventDestroy(pin_ev[i]); }
@@ -257,8 +257,12 @@ struct Engine final : pn_tree {
     }
     template <int DVR, int K, int MT, int NACC>
     int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
+        return fa.g_bound ? launch_filter_s<DVR, K, MT, NACC, true>(map_a, fa, st) : launch_filter_s<DVR, K, MT, NACC, false>(map_a, fa, st);
+    }
+    template <int DVR, int K, int MT, int NACC, bool SHARED>
+    int launch_filter_s(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
         const size_t smem = filter_fixed_smem(MT, fa.k) + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES;
-        auto kern = tc::knn_filter_kernel<DVR, K, MT, NACC>;
+        auto kern = tc::knn_filter_kernel<DVR, K, MT, NACC, SHARED>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned gx = (fa.nq - fa.row0 + MT * tc::BM - 1) / (MT * tc::BM);
         const unsigned gy = (fa.n_tiles + fa.tiles_per_split - 1) / fa.tiles_per_split;
@@ -272,7 +276,9 @@ struct Engine final : pn_tree {
 #ifdef PN_TC_PROFILE
         if (getenv("PN_TC_MT")) return atoi(getenv("PN_TC_MT"));
 #endif
-        return nkc <= 2 ? 4 : (nkc <= 6 ? 2 : 1);
+        // measured (scripts/mt_sweep.sh, 1M points, k = 10): d = 16: 208 -> 165 ms; d = 64: 58.0 -> 51.0 ms; d = 96 (Kp = 128,
+        // the resident A operand of four subtiles would take 128 KB): 68.1 -> 65.5 ms, not worth the shallow ring
+        return nkc <= 3 ? 4 : (nkc <= 6 ? 2 : 1);
     }
     template <int K>
     int launch_filter_k(const CUtensorMap& map_a, tc::FilterArgs& fa, cudaStream_t st) {
@@ -368,7 +374,7 @@ struct Engine final : pn_tree {
                 uint32_t* fl_i = n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr;
                 const uint32_t* rmap = self_query ? d_ids.as<uint32_t>() : nullptr;
                 if (q_main) {
-                    fa.row0 = 0; fa.nq = q_main; fa.tiles_per_split = n_tiles;
+                    fa.row0 = 0; fa.nq = q_main; fa.tiles_per_split = n_tiles; fa.g_bound = nullptr;
                     TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
                     merge_lists_kernel<A, uint32_t><<<(q_main + 127) / 128, 128, 0, st>>>(
                         w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, q_main, kk, idx_out, dist_out, k, p * KP, fl_d, fl_i, rmap);
@@ -377,6 +383,11 @@ struct Engine final : pn_tree {
                 }
                 if (q_tail) {
                     fa.row0 = q_main; fa.nq = nq; fa.tiles_per_split = tps;
+                    if (S > 1) {  // the splits of a query share their k-th bounds (initialised to a huge finite float)
+                        TRY(w_gbound.ensure((size_t)q_tail * 4));
+                        CU(cudaMemsetAsync(w_gbound.p, 0x7f, (size_t)q_tail * 4, st));
+                        fa.g_bound = w_gbound.as<float>();
+                    }
                     fa.part_d = w_part_d.as<float>() + (size_t)q_main * kk; fa.part_i = w_part_i.as<uint32_t>() + (size_t)q_main * kk;
                     TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
                     // with a row map (self query) the merge addresses output rows absolutely; otherwise the outputs are offset

@@ -216,6 +216,7 @@ struct FilterArgs {
     uint32_t stages;       // B ring depth in groups
     uint32_t gs;           // chunks per ring group (one full/empty barrier pair per group)
     float t2_scale;        // s^2 (1 + (d+4) 2^-23): exact squared threshold -> scaled filter units
+    float* g_bound;        // [nq - row0] or null: k-th bounds (exact squared units) shared by the splits of a query
     float* part_d;         // [grid.y][nq - row0][k]
     uint32_t* part_i;
     const float* floor_d;
@@ -300,7 +301,9 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
 // sixteen epilogue warps, four independent chains per scheduler, and the tensor pipe round-robins over the four
 // subtiles so that one subtile's read-out hides behind the other three's MMAs.  With 22 warps the register
 // file allows 93 registers per thread, so a stage is read out and tested in two halves of 64 columns.
-template <int DVR, int K, int MT, int NUM_ACC>
+// SHARED: the launch splits the point stream (grid.y > 1) and the splits of a query share their k-th bounds; compiled
+// out of the whole-stream launch, where the extra state costs registers the 80-register configuration does not have.
+template <int DVR, int K, int MT, int NUM_ACC, bool SHARED>
 __global__ void __launch_bounds__((5 * MT + 2) * 32, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char* __restrict__ baug, const FilterArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -446,6 +449,18 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         const float margin = active ? a.q_margin[qrow] : 0.f;  // E_q (scaled units)
         const float t2s = a.t2_scale;
         float theta = active ? pos_inf<float>() : -pos_inf<float>();
+        // Theta_q from the best known k-th bound.  When the point stream is split over several CTAs, the k-th distance
+        // of ANY split's list is an upper bound of the final k-th distance, so the splits of a query publish theirs
+        // (atomicMin on the float bits: the bounds are non-negative) and each filters with the smallest one.
+        float* gb = SHARED && active ? a.g_bound + (qrow - a.row0) : nullptr;
+        auto refresh_theta = [&](bool publish) {
+            float b = topk.t2;
+            if (SHARED && gb) {
+                if (publish) atomicMin(reinterpret_cast<int*>(gb), __float_as_int(b));
+                b = fminf(b, __ldcg(gb));
+            }
+            theta = xadd(xmul(b, t2s), margin);
+        };
         const unsigned full = 0xffffffffu;
         const unsigned lt_mask = (1u << lane) - 1u;
         unsigned long long hits = 0;
@@ -486,7 +501,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                     const float se = x_s[lane];
                     if (se <= topk.t2) {
                         topk.offer_sq(se, x_id[lane]);
-                        theta = xadd(xmul(topk.t2, t2s), margin);
+                        refresh_theta(true);
                     }
                 }
                 __syncwarp();
@@ -640,8 +655,12 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 for (int g = 0; g < G; ++g) scan32(r[g], j, g * 32);
                 PROF_ADD(2);
                 // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
-                if (((j & 31u) == 31u) && qn > 0) { drain(qn); qn = 0; __syncwarp(); }
+                if ((j & 31u) == 31u) {
+                    if (qn > 0) { drain(qn); qn = 0; __syncwarp(); }
+                    if (SHARED && gb) refresh_theta(false);  // pick up the other splits' progress
+                }
             }
+            if (warp == 0 && lane == 0) PROF_FLUSH(6);
         } else {
             constexpr int H = MT > 2 ? 2 : 1;   // read-out halves per stage
             constexpr int G = BN / 32 / H;      // 32-column groups per half
@@ -690,11 +709,14 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 PROF_ADD(2);
                 if (lane == 0) TRACE(warp, j, 2);
                 // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
-                if (((j & 31u) == 31u) && qn > 0) { drain(qn); qn = 0; __syncwarp(); }
+                if ((j & 31u) == 31u) {
+                    if (qn > 0) { drain(qn); qn = 0; __syncwarp(); }
+                    if (SHARED && gb) refresh_theta(false);  // pick up the other splits' progress
+                }
                 if (lane == 0) TRACE(warp, j, 3);
             }
+            if (warp == 0 && lane == 0) PROF_FLUSH(6);
         }
-        if (warp == 0 && lane == 0) PROF_FLUSH(6);
         if (qn > 0) { drain(qn); qn = 0; }
         if (active) {
             const size_t base = ((size_t)blockIdx.y * (a.nq - a.row0) + (qrow - a.row0)) * a.k;
