@@ -7,8 +7,8 @@
 // by ONE augmented FP16 contraction (fp32 accumulate): A row = [q'_0 .. q'_{d-1}, 0.., n1, n2, n3,
 // 1, 1, 1] with |q'|^2 = n1+n2+n3 split into fp16 pieces, B row = [-2p'_0 .., 0.., 1, 1, 1, m1, m2,
 // m3], so the TMEM accumulator holds D~^2 itself and the epilogue is a bare threshold test.  FP16
-// has the significand of TF32 at half the bytes: the scan is bound by L2->SM operand traffic
-// (every CTA streams all points) and by shared-memory operand reads, both of which halve.
+// has the significand of TF32 at half the bytes (L2->SM operand traffic and shared-memory operand
+// reads both halve).
 // The filter is only a filter: every element with D~^2 <= Theta_q is re-evaluated with the exact
 // sequential non-FMA fold of kernels.cuh (Euclidean::distance, reference src/distance.rs:26-35)
 // and selected on the (sqrt'd distance, index) key, so results are bit-identical to the SIMT path
@@ -21,16 +21,18 @@
 // three-piece norms: < 2^-30; fp32 accumulation, norm evaluation and centring: the quadratic term).
 // Queries whose scaled norm leaves the fp16 range get E_q = +inf: every point is reranked exactly.
 //
-// Structure (one CTA = MT x 128 queries, persistent over all point tiles; 1 CTA / SM):
-//   (MT = 2 or 4 subtiles, see knn_filter_kernel)
-//   warps 4MT, 5MT+1 : two TMA producers on alternate ring groups: 1-D bulk copies (cp.async.bulk) of
-//                the pre-tiled, pre-swizzled B image ([128 rows x 32 fp16] chunks, 64B swizzle)
-//   warps 4MT+1.. : MT tcgen05.mma issuers (one elected lane each, one per 128-query subtile),
-//                kind::f16, M=128 N=128 K=16 per instruction, accumulator stages double-buffered in
-//                TMEM (2 x MT x 128 columns)
-//   warps 0..4MT-1 : epilogue, one query row per thread: tcgen05.ld 32x32b.x32 (software-pipelined
-//                    across tiles) -> min tree -> threshold -> ballot-compacted hit queue -> batched
-//                    exact rerank + sorted insertion into the owning thread's top-k
+// Structure (one CTA = MT x 128 queries, persistent over its share of the point tiles; 1 CTA / SM;
+// MT x NUM_ACC x 128 = the 512 TMEM columns: 2 subtiles x 2 stages for wide rows, 4 x 1 for narrow ones):
+//   warps 4MT, 5MT+1 : two producers on alternate ring groups: 1-D bulk copies (cp.async.bulk) of the
+//                pre-tiled, pre-swizzled B image ([128 rows x 32 fp16] chunks, 64B swizzle)
+//   warps 4MT+1.. : MT tcgen05.mma issuers, one per 128-query subtile: the whole warp runs the loop on
+//                warp-uniform values, elect.sync picks the issuing lane (descriptors stay in uniform
+//                registers); kind::f16, M=128 N=128 K=16 per instruction
+//   warps 0..4MT-1 : epilogue, one query row per thread: tcgen05.ld 32x32b.x32 -> stage released ->
+//                    FMNMX3 min tree -> threshold -> ballot-compacted hit queue -> batched exact rerank
+//                    + sorted insertion into the owning thread's top-k (shared memory)
+// grid.y splits the point stream (small batches, the last partial wave of large ones); the splits of a
+// query share their k-th bounds through global memory and merge_lists_kernel merges their lists.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
