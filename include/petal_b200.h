@@ -55,7 +55,7 @@ typedef enum pn_dtype { PN_F32 = 0, PN_F64 = 1 } pn_dtype;
 typedef enum pn_algo {
     PN_ALGO_AUTO = 0,
     PN_ALGO_SIMT = 1,  /* exact difference-form FP32/FP64 tiles on the CUDA cores */
-    PN_ALGO_TENSOR = 2 /* tcgen05 FP16 filter + exact rerank (f32 input; AUTO: d >= 16, batches >= 16) */
+    PN_ALGO_TENSOR = 2 /* tcgen05 FP16 filter + exact rerank (f32 input; AUTO: every batch size when d >= 16) */
 } pn_algo;
 
 #define PN_FLAG_HOST_ONLY 1u /* build + flatten on the host only (no device; queries fail with

@@ -442,11 +442,12 @@ struct Engine final : pn_tree {
     // order (perfect tile coherence); results are written to the ORIGINAL row of each point
     int knn_device(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st,
                    bool self_query = false) {
-        // AUTO: with the point stream split over the SMs the tensor path wins from a handful of queries on (uniform 1M x 16:
+        // AUTO: with the point stream split over the SMs the tensor path wins at every batch size measured (uniform 1M x 16:
         // 1 query 0.43 vs 0.80 ms, 1024 queries 1.2 vs 8.3 ms; 1M x 128: 0.43 vs 3.8 ms and 1.3 vs 31.8 ms,
-        // scripts/small_batch.py); single queries and tiny batches keep the pruned scan, which on well-clustered data
-        // touches a few buckets only
-        last_used_tensor = tensor_ready && (algo == PN_ALGO_TENSOR || nq >= 16);
+        // scripts/small_batch.py), so AUTO uses it for every batch size whenever the tree is tensor-eligible (f32, d >= 16).
+        // The pruned scan can still win for single queries on tightly clustered data (it touches a few buckets only):
+        // PN_ALGO_SIMT selects it.
+        last_used_tensor = tensor_ready;
         if (last_used_tensor) return knn_device_tensor(qraw, nq, stride, k, idx_out, dist_out, st, self_query);
         const bool sort = !self_query && ft.n_buckets > 1 && nq > (uint32_t)TQ;
         if (!self_query) TRY(stage_queries(qraw, nq, stride, st, sort));

@@ -86,7 +86,7 @@ def test_tensor_auto_selection(pn, oracle):
     from petal_neighbors_b200 import synth
     pts = synth.uniform(30000, 16, 2, np.float32)
     Q = synth.uniform(4096, 16, 3, np.float32)
-    bt = pn.BallTree.euclidean(pts)             # AUTO: f32, d >= 16, nq >= 16 -> tensor
+    bt = pn.BallTree.euclidean(pts)             # AUTO: f32, d >= 16 -> tensor at every batch size
     idx, dist = bt.query_batch(Q, 10)
     assert bt.counters()["filter_pairs"] == 30000 * 4096
     oi, od = oracle.brute_knn(pts, Q, 10)
@@ -94,9 +94,11 @@ def test_tensor_auto_selection(pn, oracle):
     idx, dist = bt.query_batch(Q[:100], 10)     # the point stream is split over the SMs for small batches
     assert bt.counters()["filter_pairs"] == 30000 * 100
     assert np.array_equal(idx, oi[:100].astype(np.uint64)) and np.array_equal(bits(dist), bits(od[:100]))
-    idx, dist = bt.query_batch(Q[:8], 10)       # tiny batch -> pruned SIMT scan
-    assert bt.counters()["filter_pairs"] == 0
-    assert np.array_equal(idx, oi[:8].astype(np.uint64))
+    idx, dist = bt.query_batch(Q[:1], 10)       # a single query too
+    assert bt.counters()["filter_pairs"] == 30000
+    assert np.array_equal(idx, oi[:1].astype(np.uint64)) and np.array_equal(bits(dist), bits(od[:1]))
+    i1, d1 = bt.query(Q[0], 10)                 # the reference's own call shape
+    assert np.array_equal(i1, oi[0].astype(i1.dtype)) and np.array_equal(bits(d1), bits(od[0]))
     bs = pn.BallTree.euclidean(pts, algo=pn.PN_ALGO_SIMT)
     idx2, dist2 = bs.query_batch(Q, 10)
     assert bs.counters()["filter_pairs"] == 0 and np.array_equal(idx2, oi.astype(np.uint64))
