@@ -168,40 +168,47 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 
 // Per-thread running top-k kept in SHARED memory ([slot][lane], conflict-free): it is only touched
 // when the hit queue is drained, and keeping it out of the register file lets the epilogue hold a
-// whole 128-column accumulator stage in registers instead.  Same (distance, index) order and floor
-// semantics as TopK in kernels.cuh; only kth / thresh2 live in registers.
+// whole accumulator stage in registers instead.  Only the k-th key / thresh2 live in registers.
+// Same (distance, index) order and floor semantics as TopK in kernels.cuh.  An entry is ONE 64-bit key,
+// (float bits of the sqrt'd distance) << 32 | index: distances are non-negative, so unsigned integer order of the
+// key is exactly the lexicographic (distance, index) order, an empty slot (+inf, NO_ID) is the largest key, and a
+// shift of the sorted insertion is one 64-bit load, one compare and one 64-bit store.  (The hit path is bound by
+// instruction issue in divergent code -- an insertion with independent loads but more instructions was 1.6x slower.)
 struct SmemTopK {
-    float* sd;       // [k][32] distances of this warp, this lane's column = lane
-    uint32_t* si;    // [k][32]
-    float kth, t2, fd;
-    uint32_t kth_i, fi, k;
-    bool has_floor;
-    __device__ __forceinline__ void init(float* d, uint32_t* i, int lane, uint32_t k_, bool active) {
-        sd = d + lane; si = i + lane; k = k_;
-        for (uint32_t s = 0; s < k; ++s) { sd[s * 32] = pos_inf<float>(); si[s * 32] = NO_ID; }
-        kth = pos_inf<float>(); kth_i = NO_ID;
-        t2 = active ? pos_inf<float>() : -1.f;
-        has_floor = false; fd = 0.f; fi = 0;
+    unsigned long long* sk;  // [k][32] keys of this warp, this lane's column = lane
+    unsigned long long kth_key, floor_key;
+    float t2;
+    uint32_t k;
+    static __device__ __forceinline__ unsigned long long make_key(float d, uint32_t i) {
+        return ((unsigned long long)__float_as_uint(d) << 32) | i;
     }
-    __device__ __forceinline__ void set_floor(float d, uint32_t i) { has_floor = true; fd = d; fi = i; }
+    __device__ __forceinline__ void init(unsigned long long* base, int lane, uint32_t k_, bool active) {
+        sk = base + lane; k = k_;
+        kth_key = make_key(pos_inf<float>(), NO_ID);
+        for (uint32_t s = 0; s < k; ++s) sk[s * 32] = kth_key;
+        t2 = active ? pos_inf<float>() : -1.f;
+        floor_key = 0ull;  // nothing is below it: set_floor() raises it
+    }
+    __device__ __forceinline__ void set_floor(float d, uint32_t i) { floor_key = make_key(d, i) + 1ull; }  // keys must exceed (d, i)
     __device__ __forceinline__ void offer_sq(float s, uint32_t id) {
-        const float d = xsqrt(s);
-        if (has_floor && !(d > fd || (d == fd && id > fi))) return;
-        if (!(d < kth || (d == kth && id < kth_i))) return;
+        const unsigned long long key = make_key(xsqrt(s), id);
+        if (key < floor_key || key >= kth_key) return;
         uint32_t p = k - 1;  // sorted insertion from the tail
         while (p > 0) {
-            const float pd = sd[(p - 1) * 32];
-            const uint32_t pi = si[(p - 1) * 32];
-            if (!(d < pd || (d == pd && id < pi))) break;
-            sd[p * 32] = pd; si[p * 32] = pi;
+            const unsigned long long pk = sk[(p - 1) * 32];
+            if (key >= pk) break;
+            sk[p * 32] = pk;
             --p;
         }
-        sd[p * 32] = d; si[p * 32] = id;
-        kth = sd[(k - 1) * 32]; kth_i = si[(k - 1) * 32];
-        t2 = thresh2(kth);
+        sk[p * 32] = key;
+        kth_key = sk[(k - 1) * 32];
+        t2 = thresh2(__uint_as_float((uint32_t)(kth_key >> 32)));
     }
     __device__ __forceinline__ void store(float* out_d, uint32_t* out_i) const {
-        for (uint32_t s = 0; s < k; ++s) { out_d[s] = sd[s * 32]; out_i[s] = si[s * 32]; }
+        for (uint32_t s = 0; s < k; ++s) {
+            const unsigned long long e = sk[s * 32];
+            out_d[s] = __uint_as_float((uint32_t)(e >> 32)); out_i[s] = (uint32_t)e;
+        }
     }
 };
 
@@ -322,8 +329,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
     uint32_t* qbuf = tmem_slot + 4;  // per epilogue warp: QWORDS x u32 of queue / hand-over scratch
     constexpr int QWORDS = 144;
-    float* tk_d = reinterpret_cast<float*>(qbuf + 4 * MT * QWORDS);   // [EPI_WARPS][k][32], k = a.k <= K
-    uint32_t* tk_i = reinterpret_cast<uint32_t*>(tk_d + 4 * MT * a.k * 32);
+    unsigned long long* tk = reinterpret_cast<unsigned long long*>(qbuf + 4 * MT * QWORDS);   // [EPI_WARPS][k][32] keys, k = a.k <= K
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
     constexpr int EPI_WARPS = 4 * MT;
@@ -446,7 +452,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         float* x_s = reinterpret_cast<float*>(q_prow + 80);
         uint32_t* x_id = q_prow + 112;
         SmemTopK topk;
-        topk.init(tk_d + warp * (a.k * 32), tk_i + warp * (a.k * 32), lane, a.k, active);
+        topk.init(tk + warp * (a.k * 32), lane, a.k, active);
         if (a.floor_d && active) topk.set_floor(a.floor_d[qrow], a.floor_i[qrow]);
         const float margin = active ? a.q_margin[qrow] : 0.f;  // E_q (scaled units)
         const float t2s = a.t2_scale;

@@ -1,5 +1,6 @@
-# A/B of engine builds in one GPU session: petal-neighbors_b200/lib/variants/*.so, interleaved, two rounds.
-for round in 1 2; do
+# A/B of engine builds in one GPU session: petal-neighbors_b200/lib/variants/*.so (built with different -D knobs or
+# from different commits), interleaved over ROUNDS rounds; the same box, so differences of 0.5 % are meaningful.
+for round in $(seq 1 ${ROUNDS:-1}); do
 for so in petal-neighbors_b200/lib/variants/*.so; do
 export PN_B200_LIB=$PWD/$so
 echo "== $so (round $round)"
@@ -9,7 +10,7 @@ import sys, numpy as np
 sys.path.insert(0, ".")
 import petal_neighbors_b200 as pn
 from petal_neighbors_b200 import synth
-for d, n, nq, k in ((128, 2000000, 151552, 10), (64, 1000000, 303104, 1), (32, 1000000, 303104, 10)):
+for d, n, nq, k in ${SHAPES:-((128, 2000000, 151552, 10), (64, 1000000, 303104, 1), (32, 1000000, 303104, 10), (16, 1000000, 2048, 10))}:
     pts = synth.uniform(n, d, 2, np.float32); Q = synth.uniform(nq, d, 3, np.float32)
     bt = pn.BallTree.euclidean(pts, algo=pn.PN_ALGO_TENSOR)
     bt.query_batch(Q, k); bt.query_batch(Q, k); a = bt.counters()['scan_ms']; bt.query_batch(Q, k); b = bt.counters()['scan_ms']
