@@ -253,7 +253,7 @@ struct Engine final : pn_tree {
 
     static constexpr size_t filter_fixed_smem(int mt, uint32_t k) {
         // alignment slack + barriers / TMEM slot + per-warp queues + per-warp top-k lists (k entries per query)
-        return 1024 + 1024 + (size_t)4 * mt * 144 * 4 + (size_t)4 * mt * k * 32 * 8;
+        return 1024 + 1024 + (size_t)4 * mt * 192 * 4 + (size_t)4 * mt * k * 32 * 8;
     }
     template <int DVR, int K, int MT, int NACC>
     int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {

@@ -190,9 +190,8 @@ struct SmemTopK {
         floor_key = 0ull;  // nothing is below it: set_floor() raises it
     }
     __device__ __forceinline__ void set_floor(float d, uint32_t i) { floor_key = make_key(d, i) + 1ull; }  // keys must exceed (d, i)
-    __device__ __forceinline__ void offer_sq(float s, uint32_t id) {
-        const unsigned long long key = make_key(xsqrt(s), id);
-        if (key < floor_key || key >= kth_key) return;
+    __device__ __forceinline__ bool offer_key(unsigned long long key) {
+        if (key < floor_key || key >= kth_key) return false;
         uint32_t p = k - 1;  // sorted insertion from the tail
         while (p > 0) {
             const unsigned long long pk = sk[(p - 1) * 32];
@@ -203,6 +202,7 @@ struct SmemTopK {
         sk[p * 32] = key;
         kth_key = sk[(k - 1) * 32];
         t2 = thresh2(__uint_as_float((uint32_t)(kth_key >> 32)));
+        return true;
     }
     __device__ __forceinline__ void store(float* out_d, uint32_t* out_i) const {
         for (uint32_t s = 0; s < k; ++s) {
@@ -328,7 +328,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
     uint64_t* a_bar = tempty_bar + NUM_ACC * MT;     // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
     uint32_t* qbuf = tmem_slot + 4;  // per epilogue warp: QWORDS x u32 of queue / hand-over scratch
-    constexpr int QWORDS = 144;
+    constexpr int QWORDS = 192;  // 64 queue entries + 32 hand-over slots, 8 bytes each
     unsigned long long* tk = reinterpret_cast<unsigned long long*>(qbuf + 4 * MT * QWORDS);   // [EPI_WARPS][k][32] keys, k = a.k <= K
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
@@ -447,10 +447,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         const DevTree<float>& t = a.t;
         const int DV = DVR > 0 ? DVR : (int)t.dv;
         // per-warp scratch: 64 queued point rows, 64 owner lanes, 32 + 32 hand-over slots
-        uint32_t* q_prow = qbuf + warp * QWORDS;
-        unsigned char* q_owner = reinterpret_cast<unsigned char*>(q_prow + 64);
-        float* x_s = reinterpret_cast<float*>(q_prow + 80);
-        uint32_t* x_id = q_prow + 112;
+        // per-warp scratch: 64 queue entries (point row | owner lane << 32) and 32 hand-over slots (top-k keys)
+        unsigned long long* q_ent = reinterpret_cast<unsigned long long*>(qbuf + warp * QWORDS);
+        unsigned long long* x_key = q_ent + 64;
         SmemTopK topk;
         topk.init(tk + warp * (a.k * 32), lane, a.k, active);
         if (a.floor_d && active) topk.set_floor(a.floor_d[qrow], a.floor_i[qrow]);
@@ -478,13 +477,13 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         // e; results are handed to the owning lanes in rounds (one entry per owner per round) so all
         // owners insert concurrently
         auto drain = [&](int cnt) {
-            float s = pos_inf<float>();
-            uint32_t id = NO_ID;
+            unsigned long long key = ~0ull;
             int o = 32 + lane;  // unique dummy owner for idle lanes
             const bool valid = lane < cnt;
             if (valid) {
-                o = q_owner[lane];
-                const uint32_t prow = q_prow[lane];
+                const unsigned long long e = q_ent[lane];
+                o = (int)(e >> 32);
+                const uint32_t prow = (uint32_t)e;
                 const float4* qr = a.q + (size_t)(wrow0 + o) * DV;
                 const float4* pr = t.pts + (size_t)prow * DV;
                 float acc = 0.f;
@@ -494,23 +493,19 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 } else {
                     for (int jc = 0; jc < DV; ++jc) acc = fold(acc, __ldg(qr + jc), __ldg(pr + jc));
                 }
-                s = acc;
-                id = __ldg(t.ids + prow);
+                // the evaluating lanes take the square roots in parallel; the owners only compare and insert keys
+                key = SmemTopK::make_key(xsqrt(acc), __ldg(t.ids + prow));
             }
             const unsigned grp = __match_any_sync(full, o);
             const int rank = __popc(grp & lt_mask);
             const int rounds = __reduce_max_sync(full, valid ? rank + 1 : 0);
             for (int r = 0; r < rounds; ++r) {
                 const bool send = valid && rank == r;
-                if (send) { x_s[o] = s; x_id[o] = id; }
+                if (send) x_key[o] = key;
                 const unsigned owners = __reduce_or_sync(full, send ? (1u << o) : 0u);
                 __syncwarp();
                 if ((owners >> lane) & 1u) {
-                    const float se = x_s[lane];
-                    if (se <= topk.t2) {
-                        topk.offer_sq(se, x_id[lane]);
-                        refresh_theta(true);
-                    }
+                    if (topk.offer_key(x_key[lane])) refresh_theta(true);
                 }
                 __syncwarp();
             }
@@ -554,11 +549,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                     bits &= bits - 1;
                     const int slot = qn + __popc(mask & lt_mask);
                     const uint32_t prow = j * BN + col0 + i;
-                    q_prow[slot] = prow;
-                    q_owner[slot] = (unsigned char)lane;
+                    q_ent[slot] = (unsigned long long)prow | ((unsigned long long)lane << 32);
                     // the exact rerank happens tiles later: start pulling the candidate's row and id now
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(t.pts + (size_t)prow * DV));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.ids + prow));
                 }
                 qn += __popc(mask);
                 hits += __popc(mask);
@@ -566,10 +559,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 if (qn >= 32) {
                     drain(32);
                     const int rest = qn - 32;  // < 32
-                    uint32_t tp = 0; unsigned char to = 0;
-                    if (lane < rest) { tp = q_prow[32 + lane]; to = q_owner[32 + lane]; }
+                    unsigned long long te = 0;
+                    if (lane < rest) te = q_ent[32 + lane];
                     __syncwarp();
-                    if (lane < rest) { q_prow[lane] = tp; q_owner[lane] = to; }
+                    if (lane < rest) q_ent[lane] = te;
                     __syncwarp();
                     qn = rest;
                 }
@@ -610,11 +603,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                     bits &= bits - 1;
                     const int slot = qn + __popc(mask & lt_mask);
                     const uint32_t prow = j * BN + col0 + i;
-                    q_prow[slot] = prow;
-                    q_owner[slot] = (unsigned char)lane;
+                    q_ent[slot] = (unsigned long long)prow | ((unsigned long long)lane << 32);
                     // the exact rerank happens tiles later: start pulling the candidate's row and id now
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(t.pts + (size_t)prow * DV));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.ids + prow));
                 }
                 qn += __popc(mask);
                 hits += __popc(mask);
@@ -622,10 +613,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 if (qn >= 32) {
                     drain(32);
                     const int rest = qn - 32;  // < 32
-                    uint32_t tp = 0; unsigned char to = 0;
-                    if (lane < rest) { tp = q_prow[32 + lane]; to = q_owner[32 + lane]; }
+                    unsigned long long te = 0;
+                    if (lane < rest) te = q_ent[32 + lane];
                     __syncwarp();
-                    if (lane < rest) { q_prow[lane] = tp; q_owner[lane] = to; }
+                    if (lane < rest) q_ent[lane] = te;
                     __syncwarp();
                     qn = rest;
                 }
