@@ -137,3 +137,34 @@ def test_tensor_adversarial_scales(pn, oracle):
     Qc = (1e-3 * rng.standard_normal((2100, 16))).astype(np.float32)  # queries near the centre: all distances ~ 1
     check(pn, oracle, ring, Qc, 10)
     check(pn, oracle, ring, Qc, 1)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (40000, 16, 700, 10),      # 313 tiles, 2 query tiles of 512: the point stream is split 4 ways, shared k-th bounds
+    (40000, 16, 700, 40),      # the same with three passes (floors) over the split stream
+    (40000, 16, 3, 1),         # a tiny batch, K = 1
+    (36000, 64, 600, 10),      # generic row width, four subtiles, split stream
+    (33000, 128, 300, 10),     # two subtiles x two stages, split stream
+    (70000, 16, 76000, 10),    # one whole wave (148 x 512 queries) + a one-tile tail launch split over the stream
+])
+def test_tensor_split_point_stream(pn, oracle, n, d, nq, k):
+    """Batches smaller than a wave (and the last partial wave of larger ones) split the point stream over grid.y;
+    the per-split lists are merged and the splits share their k-th bounds -- results must not change."""
+    from petal_neighbors_b200 import synth
+    pts = synth.uniform(n, d, 61 + n + d, np.float32)
+    pts[n // 2] = pts[n // 3]                      # an exact duplicate across two different splits
+    Q = synth.uniform(nq, d, 62 + n + d, np.float32)
+    Q[0] = pts[n // 3]                             # ... queried at distance 0: tie broken by index
+    check(pn, oracle, pts, Q, k)
+
+
+def test_tensor_self_query_split(pn, oracle):
+    """Self query on a tensor-eligible tree: the row map of the merge kernel and the tail launch together."""
+    from petal_neighbors_b200 import synth
+    n, d, k = 30000, 16, 10
+    pts = synth.uniform(n, d, 77, np.float32)
+    bt = pn.BallTree.euclidean(pts, algo=pn.PN_ALGO_TENSOR)
+    idx, dist = bt.query_self(k)
+    oi, od = oracle.brute_knn(pts, pts, k)
+    assert np.array_equal(idx, oi.astype(np.uint64)) and np.array_equal(bits(dist), bits(od))
+    assert bt.counters()["h2d_bytes"] == 0
