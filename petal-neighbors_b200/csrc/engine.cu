@@ -219,15 +219,37 @@ struct Engine final : pn_tree {
         if constexpr (sizeof(A) == 4) {
             if (!tensor_eligible()) return PN_OK;
             kp = (ft.d + tc::NSLOT + tc::KC - 1) / tc::KC * tc::KC;
-            // centre = mean of the stored points (double accumulation on the host)
+            // centre = mean of the stored points (double accumulation on the host), then the largest centred
+            // coordinate.  Both passes run over fixed chunks of 64 Ki rows on the host threads and combine the
+            // chunk partials in chunk order, so the result does not depend on the number of threads.
+            const size_t CH = 65536, n_ch = (ft.n + CH - 1) / CH;
+            const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>({n_ch, 32, std::max(1u, std::thread::hardware_concurrency())}));
+            auto chunks = [&](auto&& body) {  // body(chunk index), chunks dealt round-robin to nt threads
+                std::vector<std::thread> th;
+                for (unsigned w = 1; w < nt; ++w) th.emplace_back([&, w] { for (size_t c = w; c < n_ch; c += nt) body(c); });
+                for (size_t c = 0; c < n_ch; c += nt) body(c);
+                for (auto& t : th) t.join();
+            };
+            std::vector<double> part(n_ch * ft.dpad, 0.0);
+            chunks([&](size_t c) {
+                double* m = &part[c * ft.dpad];
+                for (size_t i = c * CH, e = std::min<size_t>(ft.n, (c + 1) * CH); i < e; ++i)
+                    for (uint32_t j = 0; j < ft.d; ++j) m[j] += (double)ft.pts[i * ft.dpad + j];
+            });
             std::vector<double> mean(ft.dpad, 0.0);
-            for (size_t i = 0; i < ft.n; ++i)
-                for (uint32_t j = 0; j < ft.d; ++j) mean[j] += (double)ft.pts[i * ft.dpad + j];
+            for (size_t c = 0; c < n_ch; ++c)
+                for (uint32_t j = 0; j < ft.d; ++j) mean[j] += part[c * ft.dpad + j];
             std::vector<float> c(ft.dpad, 0.f);
             for (uint32_t j = 0; j < ft.d; ++j) c[j] = (float)(mean[j] / (double)ft.n);
+            std::vector<float> pmaxabs(n_ch, 0.f);
+            chunks([&](size_t ch) {
+                float m = 0.f;
+                for (size_t i = ch * CH, e = std::min<size_t>(ft.n, (ch + 1) * CH); i < e; ++i)
+                    for (uint32_t j = 0; j < ft.d; ++j) m = std::max(m, std::fabs(ft.pts[i * ft.dpad + j] - c[j]));
+                pmaxabs[ch] = m;
+            });
             float maxabs = 0.f;
-            for (size_t i = 0; i < ft.n; ++i)
-                for (uint32_t j = 0; j < ft.d; ++j) maxabs = std::max(maxabs, std::fabs(ft.pts[i * ft.dpad + j] - c[j]));
+            for (size_t ch = 0; ch < n_ch; ++ch) maxabs = std::max(maxabs, pmaxabs[ch]);
             int ex = 0;
             if (maxabs > 0.f && std::isfinite(maxabs)) { std::frexp(maxabs, &ex); }  // maxabs = m 2^ex, m in [0.5, 1)
             tscale = std::ldexp(1.0f, -ex);

@@ -97,8 +97,9 @@ class BallBuilder {
         t.centers.assign((size_t)t.n_nodes * t.dpad, A(0));
         t.radii.assign(t.n_nodes, A(-1));
         base_ = lo;
+        // 1. partition, top-down: one min/max pass + one selection per level (nothing else touches the rows here)
         recurse(idx, t, 0, lo, hi, 0);
-        // flatten: points in bucket (idx) order, zero-padded to dpad
+        // 2. flatten: points in bucket (idx) order, zero-padded to dpad
         t.pts.assign(n * (size_t)t.dpad, A(0));
         t.ids.resize(n);
         parallel_for(n, [&](size_t b, size_t e) {
@@ -108,14 +109,16 @@ class BallBuilder {
                 std::memcpy(&t.pts[i * t.dpad], pts_ + (size_t)src * stride_, d_ * sizeof(A));
             }
         });
+        // 3. + 4. centroids bottom-up from bucket sums, radii in one pass over the flattened rows
+        node_balls(t);
         t.bucket_max = 0;
         for (uint32_t b = 0; b < t.n_buckets; ++b)
             t.bucket_max = std::max(t.bucket_max, t.bucket_hi[b] - t.bucket_lo[b]);
     }
 
   private:
-    template <typename F> void parallel_for(size_t n, F f) {
-        uint32_t nt = (uint32_t)std::min<size_t>(threads_, (n + 65535) / 65536);
+    template <typename F> void parallel_for(size_t n, F f, size_t grain = 65536) {
+        uint32_t nt = (uint32_t)std::min<size_t>(threads_, (n + grain - 1) / grain);
         if (nt <= 1) { f(0, n); return; }
         std::vector<std::thread> th;
         size_t chunk = (n + nt - 1) / nt;
@@ -183,63 +186,93 @@ class BallBuilder {
         return (uint32_t)std::min<size_t>(threads_, len / 65536 + 1);
     }
 
-    // Node::init, src/ball_tree.rs:445-461.  For large nodes the sum and the max are accumulated per chunk
-    // and combined (the centroid then differs from the strictly sequential sum in the last bits; any centre
-    // with radius = max exact fold distance to it is a valid ball, so results are unaffected).
-    void node_init(const std::vector<uint32_t>& idx, size_t lo, size_t hi, A* center, A& radius) {
-        const size_t len = hi - lo;
-        if (len == 0) { radius = A(-1); return; }
-        const uint32_t nt = workers_for(len);
-        const size_t chunk = (len + nt - 1) / nt;
-        auto sum_range = [&](size_t b, size_t e, A* acc) {
-            for (size_t j = 0; j < d_; ++j) acc[j] = A(0);
-            for (size_t t = b; t < e; ++t) {
-                const A* r = pts_ + (size_t)idx[t] * stride_;
-                for (size_t j = 0; j < d_; ++j) acc[j] += r[j];
+    // Node::init, src/ball_tree.rs:445-461, for every node of the flattened tree at once.
+    //   centroid: a bucket's sum is the sequential sum of its rows in idx order (exactly the reference's Node::init
+    //     for a single-bucket tree); an internal node's sum is left child + right child, so all centroids cost ONE pass
+    //     over the points instead of one per level.  (The centroid of a large node then differs from the strictly
+    //     sequential sum in the last bits -- it is in fact more accurate; any centre with radius = max exact fold
+    //     distance to it is a valid ball, so results are unaffected.)
+    //   radius: max over the node's points of Euclidean::distance(centroid, point), src/distance.rs:26-35.  One pass
+    //     over the rows: each row is folded against the centroids of its L+1 ancestors at once -- the fold over the
+    //     dimensions stays sequential per ancestor (bit-exact), the loop over the ancestors vectorises.
+    void node_balls(FlatTree<A>& t) {
+        const size_t dp = t.dpad, nb = t.n_buckets, L = t.L;
+        std::vector<A> sum((size_t)t.n_nodes * dp, A(0));
+        std::vector<uint64_t> cnt(t.n_nodes, 0);
+        parallel_for(nb, [&](size_t b0, size_t b1) {
+            for (size_t b = b0; b < b1; ++b) {
+                A* acc = &sum[(t.n_internal + b) * dp];
+                for (size_t i = t.bucket_lo[b]; i < t.bucket_hi[b]; ++i) {
+                    const A* r = &t.pts[i * dp];
+                    for (size_t j = 0; j < d_; ++j) acc[j] += r[j];
+                }
+                cnt[t.n_internal + b] = t.bucket_hi[b] - t.bucket_lo[b];
             }
-        };
-        auto max_range = [&](size_t b, size_t e) {
-            A m = A(0);
-            for (size_t t = b; t < e; ++t) {
-                A v = fold_distance(center, pts_ + (size_t)idx[t] * stride_, d_);
-                if (v > m) m = v;
-            }
-            return m;
-        };
-        if (nt <= 1) {
-            sum_range(lo, hi, center);
-        } else {
-            std::vector<std::vector<A>> part(nt, std::vector<A>(d_));
-            std::vector<std::thread> th;
-            for (uint32_t w = 0; w < nt; ++w) {
-                const size_t b = lo + w * chunk, e = std::min(hi, b + chunk);
-                if (b >= e) { for (size_t j = 0; j < d_; ++j) part[w][j] = A(0); continue; }
-                th.emplace_back([&, b, e, w] { sum_range(b, e, part[w].data()); });
-            }
-            for (auto& x : th) x.join();
-            for (size_t j = 0; j < d_; ++j) { A sacc = A(0); for (uint32_t w = 0; w < nt; ++w) sacc += part[w][j]; center[j] = sacc; }
+        }, 1);
+        for (size_t node = t.n_internal; node-- > 0;) {  // children before parents
+            const A* l = &sum[(2 * node + 1) * dp];
+            const A* r = &sum[(2 * node + 2) * dp];
+            A* o = &sum[node * dp];
+            for (size_t j = 0; j < d_; ++j) o[j] = l[j] + r[j];
+            cnt[node] = cnt[2 * node + 1] + cnt[2 * node + 2];
         }
-        A flen = (A)len;
-        for (size_t j = 0; j < d_; ++j) center[j] /= flen;
-        if (nt <= 1) {
-            radius = max_range(lo, hi);
-        } else {
-            std::vector<A> pm(nt, A(0));
-            std::vector<std::thread> th;
-            for (uint32_t w = 0; w < nt; ++w) {
-                const size_t b = lo + w * chunk, e = std::min(hi, b + chunk);
-                if (b >= e) continue;
-                th.emplace_back([&, b, e, w] { pm[w] = max_range(b, e); });
+        for (size_t node = 0; node < t.n_nodes; ++node) {
+            A* c = &t.centers[node * dp];
+            if (cnt[node] == 0) { t.radii[node] = A(-1); continue; }
+            const A flen = (A)cnt[node];
+            for (size_t j = 0; j < d_; ++j) c[j] = sum[node * dp + j] / flen;
+            t.radii[node] = A(0);
+        }
+        // radii: per worker a private max per node, merged afterwards (max is order independent)
+        const size_t LV = L + 1;
+        const uint32_t nw = std::max<uint32_t>(1, (uint32_t)std::min<size_t>(threads_, (t.n * d_ >> 20) + 1));
+        std::vector<std::vector<A>> wmax(nw, std::vector<A>(t.n_nodes, A(0)));
+        auto work = [&](uint32_t w) {
+            std::vector<A> ct(d_ * LV), acc(LV);  // the ancestors' centroids, transposed: ct[j][level]
+            std::vector<uint32_t> anc(LV);
+            A* mx = wmax[w].data();
+            const size_t b0 = nb * w / nw, b1 = nb * (w + 1) / nw;
+            for (size_t b = b0; b < b1; ++b) {
+                if (t.bucket_hi[b] == t.bucket_lo[b]) continue;
+                size_t h = t.n_internal + b;  // heap index of the bucket node; its ancestor `up` levels above is ((h+1) >> up) - 1
+                for (size_t up = 0; up < LV; ++up) {
+                    anc[up] = (uint32_t)(((h + 1) >> up) - 1);
+                    const A* c = &t.centers[(size_t)anc[up] * dp];
+                    for (size_t j = 0; j < d_; ++j) ct[j * LV + up] = c[j];
+                }
+                for (size_t i = t.bucket_lo[b]; i < t.bucket_hi[b]; ++i) {
+                    const A* r = &t.pts[i * dp];
+                    for (size_t up = 0; up < LV; ++up) acc[up] = A(0);
+                    for (size_t j = 0; j < d_; ++j) {
+                        const A v = r[j];
+                        const A* cj = &ct[j * LV];
+                        for (size_t up = 0; up < LV; ++up) {
+                            const A diff = cj[up] - v;   // x1 = centroid, x2 = point, as in Node::init
+                            acc[up] += diff * diff;
+                        }
+                    }
+                    for (size_t up = 0; up < LV; ++up) {
+                        const A dist = std::sqrt(acc[up]);
+                        if (dist > mx[anc[up]]) mx[anc[up]] = dist;
+                    }
+                }
             }
+        };
+        if (nw == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (uint32_t w = 0; w < nw; ++w) th.emplace_back(work, w);
             for (auto& x : th) x.join();
+        }
+        for (size_t node = 0; node < t.n_nodes; ++node) {
+            if (cnt[node] == 0) continue;
             A m = A(0);
-            for (uint32_t w = 0; w < nt; ++w) if (pm[w] > m) m = pm[w];
-            radius = m;
+            for (uint32_t w = 0; w < nw; ++w) if (wmax[w][node] > m) m = wmax[w][node];
+            t.radii[node] = m;
         }
     }
 
     void recurse(std::vector<uint32_t>& idx, FlatTree<A>& t, uint32_t node, size_t lo, size_t hi, uint32_t level) {
-        node_init(idx, lo, hi, &t.centers[(size_t)node * t.dpad], t.radii[node]);
         if (level == t.L) {
             uint32_t b = node - t.n_internal;
             t.bucket_lo[b] = (uint32_t)(lo - base_);
