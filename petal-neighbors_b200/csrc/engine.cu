@@ -320,6 +320,12 @@ struct Engine final : pn_tree {
         if (mt == 2) {
             if (dt.dv == 4) return launch_filter_t<4, K, 2, 2>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 2, 2>(map_a, fa, st);
+#ifdef PN_TC_PROFILE
+            // experiment (PN_TC_TS=1, diagnostic builds): two subtiles x ONE stage with the A operand in tensor memory.
+            // Bit-exact, and the MMA drops from 85 to 70 cycles, but the single accumulator stage serialises MMA and
+            // read-out of a subtile: 10M-shaped d = 128 scan 70.4 -> 74.0 ms (scripts/ts_test.sh).  Not used.
+            if (getenv("PN_TC_TS") && atoi(getenv("PN_TC_TS")) != 0) return launch_filter_t<0, K, 2, 1>(map_a, fa, st);
+#endif
             return launch_filter_t<0, K, 2, 2>(map_a, fa, st);
         }
         return launch_filter_t<0, K, 1, 2>(map_a, fa, st);

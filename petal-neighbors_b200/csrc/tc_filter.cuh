@@ -132,6 +132,21 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, A operand from tensor memory (TS form): [lane = query row][K packed two fp16 per 32-bit column]
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory -> tensor memory copy of one K step of the A operand: 128 rows x 256 bits (16 fp16) = 8 columns
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // K-major, 64-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = (8 rows x 64 B)/16 [32,46) | version 1 [46,48) | SWIZZLE_64B = 4 [61,64)
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
@@ -333,7 +348,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
     constexpr int EPI_WARPS = 4 * MT;
-    constexpr int TMEM_COLS = NUM_ACC * MT * BN;  // 256 or 512 (power of two)
+    // Wide rows with one accumulator stage per subtile keep the A operand in tensor memory (TS-form MMA): the pipe then
+    // reads only B from shared memory (measured 70 instead of 85 cycles per 128x128x16 MMA, scripts/mma_rate.cu).
+    // Columns: MT accumulators of 128, then MT A operands of Kp/2 (two fp16 per column), 512 allocated.
+    constexpr bool TS = MT == 2 && NUM_ACC == 1;
+    constexpr int TMEM_COLS = TS ? 512 : NUM_ACC * MT * BN;  // power of two
 
     if (warp == EPI_WARPS && lane == 0) {
         for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MT); }
@@ -399,6 +418,20 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             const uint64_t b_desc0 = make_desc_sw64(smem_u32(smem_b));
             const uint32_t total = n_my * a.nkc;
             mbar_wait(a_bar, 0);
+            // TS: this subtile's A operand goes to tensor memory once, K step by K step (copies and MMAs issued by one
+            // thread execute in order)
+            const uint32_t a_tmem = tmem_base + MT * BN + mt * (a.nkc * 16);
+            if (TS) {
+                tc_fence_after();
+                if (elect_one()) {
+                    for (uint32_t c = 0; c < a.nkc; ++c) {
+                        const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
+                        tc_cp_128x256b(a_tmem + c * 16, ad);
+                        tc_cp_128x256b(a_tmem + c * 16 + 8, ad + 2);
+                    }
+                }
+                __syncwarp();
+            }
             uint32_t it = 0, g = 0, gi = 0, s = 0, sph = 0;  // stream position: group, chunk in group, ring stage, its phase
             PROF_DECL;
             for (uint32_t j = 0; j < n_my; ++j) {
@@ -420,8 +453,13 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                     const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
                     const bool last = gi + 1 == a.gs || it + 1 == total;
                     if (elect_one()) {
-                        tc_mma_f16(d_tmem, ad, bd, idesc, c > 0 ? 1u : 0u);
-                        tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                        if (TS) {
+                            tc_mma_f16_ts(d_tmem, a_tmem + c * 16, bd, idesc, c > 0 ? 1u : 0u);
+                            tc_mma_f16_ts(d_tmem, a_tmem + c * 16 + 8, bd + 2, idesc, 1u);
+                        } else {
+                            tc_mma_f16(d_tmem, ad, bd, idesc, c > 0 ? 1u : 0u);
+                            tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                        }
                         if (last) tc_commit(&empty_bar[s]);  // group consumed by this subtile
                     }
                     __syncwarp();
