@@ -66,6 +66,14 @@ inline void check_create(int32_t st) {
 inline void check(int32_t st) {
     if (st != PN_OK) throw std::runtime_error(std::string("petal_b200: ") + pn_last_error_message());
 }
+// The reference's distance fold zips the two rows and silently truncates to the shorter one
+// (src/distance.rs:26-35); the C ABI reads exactly `d` elements per query row, so a wrong-sized query would be
+// an out-of-bounds read.  Every wrapper method checks the dimension first.
+inline void check_dim(size_t got, size_t want, const char* what) {
+    if (got != want)
+        throw std::invalid_argument(std::string("petal_neighbors: ") + what + " has dimension " + std::to_string(got) +
+                                    ", the tree has " + std::to_string(want));
+}
 template <typename A> struct Abi;
 template <> struct Abi<float> {
     static constexpr auto ball_create = pn_balltree_create_f32;
@@ -105,11 +113,13 @@ template <typename A> class BallTree {
     ~BallTree() { if (h_) pn_tree_destroy(h_); }
 
     std::pair<size_t, A> query_nearest(const std::vector<A>& point) const {
+        detail::check_dim(point.size(), d_, "point");
         uint64_t i = 0; A dist = 0;
         detail::check(detail::Abi<A>::nearest(h_, point.data(), 1, d_, &i, &dist));
         return {size_t(i), dist};
     }
     std::pair<std::vector<size_t>, std::vector<A>> query(const std::vector<A>& point, size_t k) const {
+        detail::check_dim(point.size(), d_, "point");
         if (k == 0) return {};
         std::vector<uint64_t> idx(k); std::vector<A> dist(k);
         detail::check(detail::Abi<A>::query(h_, point.data(), 1, d_, k, idx.data(), dist.data()));
@@ -117,14 +127,17 @@ template <typename A> class BallTree {
         return {std::vector<size_t>(idx.begin(), idx.begin() + m), std::vector<A>(dist.begin(), dist.begin() + m)};
     }
     std::vector<size_t> query_radius(const std::vector<A>& point, A distance) const {
+        detail::check_dim(point.size(), d_, "point");
         auto r = query_radius_batch(View2<A>(point.data(), 1, d_), distance);
         return r.second;
     }
     // batched additions
     void query_batch(const View2<A>& q, size_t k, uint64_t* idx_out, A* dist_out) const {
+        check_view(q);
         detail::check(detail::Abi<A>::query(h_, q.data, q.rows, q.row_stride, k, idx_out, dist_out));
     }
     std::pair<std::vector<size_t>, std::vector<size_t>> query_radius_batch(const View2<A>& q, A distance) const {
+        check_view(q);
         uint64_t *po = nullptr, *pi = nullptr;
         detail::check(detail::Abi<A>::radius(h_, q.data, q.rows, q.row_stride, distance, &po, &pi));
         std::vector<size_t> offs(po, po + q.rows + 1), ind(pi, pi + po[q.rows]);
@@ -137,6 +150,11 @@ template <typename A> class BallTree {
     pn_tree* handle() const { return h_; }
 
   private:
+    void check_view(const View2<A>& q) const {
+        detail::check_dim(q.cols, d_, "query batch");
+        if (q.cols > 1 && q.col_stride != 1) throw std::invalid_argument("petal_neighbors: query rows must be contiguous");
+        if (q.rows > 1 && q.row_stride < q.cols) throw std::invalid_argument("petal_neighbors: query row stride < dimension");
+    }
     BallTree(const View2<A>& p, const pn_build_opts* opts) : n_(p.rows), d_(p.cols) {
         detail::check_create(detail::Abi<A>::ball_create(p.data, p.rows, p.cols, p.row_stride, p.col_stride, opts, &h_));
     }
@@ -151,11 +169,15 @@ template <typename A> class VantagePointTree {
     VantagePointTree(const VantagePointTree&) = delete;
     ~VantagePointTree() { if (h_) pn_tree_destroy(h_); }
     std::pair<size_t, A> query_nearest(const std::vector<A>& needle) const {
+        detail::check_dim(needle.size(), d_, "needle");
         uint64_t i = 0; A dist = 0;
         detail::check(detail::Abi<A>::vp_nearest(h_, needle.data(), 1, d_, &i, &dist));
         return {size_t(i), dist};
     }
     void query_nearest_batch(const View2<A>& q, uint64_t* idx_out, A* dist_out) const {
+        detail::check_dim(q.cols, d_, "query batch");
+        if ((q.cols > 1 && q.col_stride != 1) || (q.rows > 1 && q.row_stride < q.cols))
+            throw std::invalid_argument("petal_neighbors: query rows must be contiguous with row stride >= dimension");
         detail::check(detail::Abi<A>::vp_nearest(h_, q.data, q.rows, q.row_stride, idx_out, dist_out));
     }
 

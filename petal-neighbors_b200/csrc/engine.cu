@@ -277,14 +277,14 @@ struct Engine final : pn_tree {
         // alignment slack + barriers / TMEM slot + per-warp queues + per-warp top-k lists (k entries per query)
         return 1024 + 1024 + (size_t)4 * mt * 192 * 4 + (size_t)4 * mt * k * 32 * 8;
     }
-    template <int DVR, int K, int MT, int NACC>
+    template <int DVR, int K, int MT, int NACC, int SW = tc::BN>
     int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
-        return fa.g_bound ? launch_filter_s<DVR, K, MT, NACC, true>(map_a, fa, st) : launch_filter_s<DVR, K, MT, NACC, false>(map_a, fa, st);
+        return fa.g_bound ? launch_filter_s<DVR, K, MT, NACC, true, SW>(map_a, fa, st) : launch_filter_s<DVR, K, MT, NACC, false, SW>(map_a, fa, st);
     }
-    template <int DVR, int K, int MT, int NACC, bool SHARED>
+    template <int DVR, int K, int MT, int NACC, bool SHARED, int SW>
     int launch_filter_s(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
         const size_t smem = filter_fixed_smem(MT, fa.k) + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES;
-        auto kern = tc::knn_filter_kernel<DVR, K, MT, NACC, SHARED>;
+        auto kern = tc::knn_filter_kernel<DVR, K, MT, NACC, SHARED, SW>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned gx = (fa.nq - fa.row0 + MT * tc::BM - 1) / (MT * tc::BM);
         const unsigned gy = (fa.n_tiles + fa.tiles_per_split - 1) / fa.tiles_per_split;
@@ -313,6 +313,13 @@ struct Engine final : pn_tree {
         fa.stages &= ~1u;  // even: each ring stage always belongs to the same one of the two producer warps
         if (fa.stages < 2) return fail(PN_CUDA, "tensor path: shared memory budget too small for this dimension");
         if (mt == 4) {
+            // EXPERIMENT: PN_TC_HALF=0 selects the previous one-stage-per-subtile configuration
+            static const bool half = !(getenv("PN_TC_HALF") && atoi(getenv("PN_TC_HALF")) == 0);
+            if (half) {
+                if (dt.dv == 4) return launch_filter_t<4, K, 4, 2, 64>(map_a, fa, st);
+                if (dt.dv == 8) return launch_filter_t<8, K, 4, 2, 64>(map_a, fa, st);
+                return launch_filter_t<0, K, 4, 2, 64>(map_a, fa, st);
+            }
             if (dt.dv == 4) return launch_filter_t<4, K, 4, 1>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 4, 1>(map_a, fa, st);
             return launch_filter_t<0, K, 4, 1>(map_a, fa, st);

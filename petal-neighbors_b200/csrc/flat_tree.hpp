@@ -74,8 +74,9 @@ class BallBuilder {
     void shard_range(std::vector<uint32_t>& idx, uint32_t depth, uint32_t index, size_t& lo, size_t& hi) {
         lo = 0; hi = n_;
         for (uint32_t lev = 0; lev < depth; ++lev) {
-            if (hi - lo < 2) break;
-            split(idx, lo, hi);
+            // ranges of 0 or 1 points keep descending by the same mid rule, so that exactly one shard owns each point
+            // (the others come out empty, hi == lo) even when n < 2^depth
+            if (hi - lo >= 2) split(idx, lo, hi);
             size_t mid = (lo + hi) / 2;
             bool right = (index >> (depth - 1 - lev)) & 1u;
             if (right) lo = mid; else hi = mid;

@@ -327,7 +327,7 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
 // file allows 93 registers per thread, so a stage is read out and tested in two halves of 64 columns.
 // SHARED: the launch splits the point stream (grid.y > 1) and the splits of a query share their k-th bounds; compiled
 // out of the whole-stream launch, where the extra state costs registers the 80-register configuration does not have.
-template <int DVR, int K, int MT, int NUM_ACC, bool SHARED>
+template <int DVR, int K, int MT, int NUM_ACC, bool SHARED, int SW = BN>
 __global__ void __launch_bounds__((5 * MT + 2) * 32, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char* __restrict__ baug, const FilterArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -352,7 +352,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
     // reads only B from shared memory (measured 70 instead of 85 cycles per 128x128x16 MMA, scripts/mma_rate.cu).
     // Columns: MT accumulators of 128, then MT A operands of Kp/2 (two fp16 per column), 512 allocated.
     constexpr bool TS = MT == 2 && NUM_ACC == 1;
-    constexpr int TMEM_COLS = TS ? 512 : NUM_ACC * MT * BN;  // power of two
+    constexpr int TMEM_COLS = TS ? 512 : NUM_ACC * MT * SW;  // power of two
+    // accumulator units per B tile: a stage holds SW columns, i.e. the distances of 128 queries to SW of the tile's 128
+    // points; with SW = 64 the four-subtile configuration gets TWO stages per subtile out of the same 512 columns
+    constexpr int U = BN / SW;
+    static_assert(SW == BN || (SW == 64 && !TS), "stage width is a whole tile or half a tile");
 
     if (warp == EPI_WARPS && lane == 0) {
         for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MT); }
@@ -413,7 +417,6 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         // The whole warp runs the loop on warp-uniform values; one elected lane issues.
         {
             const int mt = warp - (EPI_WARPS + 1);
-            constexpr uint32_t idesc = make_idesc_f16(BM, BN);
             const uint64_t a_desc0 = make_desc_sw64(smem_u32(smem_a)) + (uint64_t)(mt * a.nkc * (A_CHUNK_BYTES >> 4));
             const uint64_t b_desc0 = make_desc_sw64(smem_u32(smem_b));
             const uint32_t total = n_my * a.nkc;
@@ -433,42 +436,51 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 __syncwarp();
             }
             uint32_t it = 0, g = 0, gi = 0, s = 0, sph = 0;  // stream position: group, chunk in group, ring stage, its phase
+            uint32_t u = 0;  // accumulator units issued so far: stage u % NUM_ACC, phase (u / NUM_ACC) & 1
+            constexpr uint32_t idesc_u = make_idesc_f16(BM, SW);
             PROF_DECL;
             for (uint32_t j = 0; j < n_my; ++j) {
-                const uint32_t as = j % NUM_ACC, aph = (j / NUM_ACC) & 1u;
-                mbar_wait(&tempty_bar[as * MT + mt], aph ^ 1u);  // this subtile's accumulator stage has been read out
-                tc_fence_after();
-                PROF_ADD(0);
-                if (lane == 0) TRACE(8 + mt, j, 0);
-                const uint32_t d_tmem = tmem_base + (as * MT + mt) * BN;
-                for (uint32_t c = 0; c < a.nkc; ++c, ++it) {
-                    if (gi == 0) {
-                        mbar_wait(&full_bar[s], sph);
-                        tc_fence_after();
-                        PROF_ADD(1);
-                    }
-                    if (lane == 0 && c == 0) TRACE(8 + mt, j, 1);
-                    // descriptors advance in 16-byte units: +2 per K step of 16 fp16, whole chunks per slot
-                    const uint64_t bd = b_desc0 + (uint64_t)((s * a.gs + gi) * (CHUNK_BYTES >> 4));
-                    const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
-                    const bool last = gi + 1 == a.gs || it + 1 == total;
-                    if (elect_one()) {
-                        if (TS) {
-                            tc_mma_f16_ts(d_tmem, a_tmem + c * 16, bd, idesc, c > 0 ? 1u : 0u);
-                            tc_mma_f16_ts(d_tmem, a_tmem + c * 16 + 8, bd + 2, idesc, 1u);
-                        } else {
-                            tc_mma_f16(d_tmem, ad, bd, idesc, c > 0 ? 1u : 0u);
-                            tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                const uint32_t it0 = it, g0 = g, gi0 = gi, s0 = s, sph0 = sph;  // ring position of this tile's first chunk
+#pragma unroll
+                for (int h = 0; h < U; ++h, ++u) {
+                    // every unit of a tile walks the tile's chunks again (rows [h SW, (h+1) SW) of each); the ring
+                    // groups are waited for by the first unit and handed back by the last
+                    if (h) { it = it0; g = g0; gi = gi0; s = s0; sph = sph0; }
+                    const uint32_t as = u % NUM_ACC, aph = (u / NUM_ACC) & 1u;
+                    mbar_wait(&tempty_bar[as * MT + mt], aph ^ 1u);  // this subtile's accumulator stage has been read out
+                    tc_fence_after();
+                    PROF_ADD(0);
+                    if (lane == 0) TRACE(8 + mt, j, 0);
+                    const uint32_t d_tmem = tmem_base + (as * MT + mt) * SW;
+                    for (uint32_t c = 0; c < a.nkc; ++c, ++it) {
+                        if (gi == 0 && h == 0) {
+                            mbar_wait(&full_bar[s], sph);
+                            tc_fence_after();
+                            PROF_ADD(1);
                         }
-                        if (last) tc_commit(&empty_bar[s]);  // group consumed by this subtile
+                        if (lane == 0 && c == 0) TRACE(8 + mt, j, 1);
+                        // descriptors advance in 16-byte units: +2 per K step of 16 fp16, whole chunks per slot, 64 B per row
+                        const uint64_t bd = b_desc0 + (uint64_t)((s * a.gs + gi) * (CHUNK_BYTES >> 4) + h * (SW * KC * 2 >> 4));
+                        const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
+                        const bool last = gi + 1 == a.gs || it + 1 == total;
+                        if (elect_one()) {
+                            if (TS) {
+                                tc_mma_f16_ts(d_tmem, a_tmem + c * 16, bd, idesc_u, c > 0 ? 1u : 0u);
+                                tc_mma_f16_ts(d_tmem, a_tmem + c * 16 + 8, bd + 2, idesc_u, 1u);
+                            } else {
+                                tc_mma_f16(d_tmem, ad, bd, idesc_u, c > 0 ? 1u : 0u);
+                                tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc_u, 1u);
+                            }
+                            if (last && h == U - 1) tc_commit(&empty_bar[s]);  // group consumed by this subtile
+                        }
+                        __syncwarp();
+                        if (last) { gi = 0; ++g; if (++s == a.stages) { s = 0; sph ^= 1u; } } else ++gi;
                     }
+                    if (elect_one()) tc_commit(&tfull_bar[as * MT + mt]);  // this unit's accumulator is complete
                     __syncwarp();
-                    if (last) { gi = 0; ++g; if (++s == a.stages) { s = 0; sph ^= 1u; } } else ++gi;
+                    PROF_ADD(2);
+                    if (lane == 0) TRACE(8 + mt, j, 2);
                 }
-                if (elect_one()) tc_commit(&tfull_bar[as * MT + mt]);  // this subtile's accumulator is complete
-                __syncwarp();
-                PROF_ADD(2);
-                if (lane == 0) TRACE(8 + mt, j, 2);
             }
             if (mt == 0 && lane == 0) PROF_FLUSH(0);
         }
@@ -696,6 +708,59 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                     if (qn > 0) { drain(qn); qn = 0; __syncwarp(); }
                     if (SHARED && gb) refresh_theta(false);  // pick up the other splits' progress
                 }
+            }
+            if (warp == 0 && lane == 0) PROF_FLUSH(6);
+        } else if constexpr (SW < BN) {
+            // Half-tile stages (narrow rows): each subtile owns TWO 64-column stages, so the MMA of the next half tile runs
+            // while this one is read out and tested, and the four warps sharing a stage get half a tile of slack against
+            // each other (with one whole-tile stage the slowest sibling's hit path gated every tile of its subtile).
+            // A stage is released as soon as its columns are in registers, before they are tested.
+            constexpr int G = SW / 32;          // 32-column groups per unit
+            uint32_t r[G][32];
+            const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+            uint32_t u = 0;
+            PROF_DECL;
+            for (uint32_t jr = 0; jr < n_my; ++jr) {
+                const uint32_t j = j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
+#pragma unroll
+                for (int h = 0; h < U; ++h, ++u) {
+                    const uint32_t as = u % NUM_ACC, aph = (u / NUM_ACC) & 1u;
+                    PROF_ADD(3);
+                    mbar_wait(&tfull_bar[as * MT + mt], aph);
+                    tc_fence_after();
+                    PROF_ADD(0);
+                    if (lane == 0 && h == 0) TRACE(warp, j, 0);
+                    const uint32_t taddr = tmem_base + lane_off + (as * MT + mt) * SW;
+    #pragma unroll
+                    for (int g = 0; g < G; ++g) tmem_ld32_issue(taddr + g * 32, r[g]);
+    #pragma unroll
+                    for (int g = 0; g < G; ++g) tmem_ld_wait(r[g]);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[as * MT + mt]);
+                    PROF_ADD(1);
+                    if (lane == 0 && h == 0) TRACE(warp, j, 1);
+    #ifdef PN_TC_PROFILE
+                    if (a.dbg & 1u) continue;
+    #endif
+                    uint32_t bits[G];
+                    uint32_t any = 0;  // groups with a hit in some lane (warp-uniform)
+    #pragma unroll
+                    for (int g = 0; g < G; ++g) any |= test32(r[g], j, (h * G + g) * 32, bits[g]) ? 1u << g : 0u;
+                    if (any) {
+    #pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            if (any & (1u << g)) push32(bits[g], j, (h * G + g) * 32);
+                    }
+                    PROF_ADD(2);
+                }
+                if (lane == 0) TRACE(warp, j, 2);
+                // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
+                if ((j & 31u) == 31u) {
+                    if (qn > 0) { drain(qn); qn = 0; __syncwarp(); }
+                    if (SHARED && gb) refresh_theta(false);  // pick up the other splits' progress
+                }
+                if (lane == 0) TRACE(warp, j, 3);
             }
             if (warp == 0 && lane == 0) PROF_FLUSH(6);
         } else {

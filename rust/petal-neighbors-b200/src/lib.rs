@@ -53,11 +53,41 @@ impl Drop for Handle {
     }
 }
 
-fn strides<A>(points: &CowArray<'_, A, Ix2>) -> (usize, usize) {
+/// Element strides of a 2-D array as the C ABI wants them, or `None` when a stride is negative
+/// (a reversed view): the caller then copies to standard layout first.  Casting a negative `isize`
+/// stride with `as usize` would hand the engine a huge positive one.
+fn strides<A>(points: &CowArray<'_, A, Ix2>) -> Option<(usize, usize)> {
     let s = points.strides();
+    if (points.nrows() > 1 && s[0] < 0) || (points.ncols() > 1 && s[1] < 0) {
+        return None;
+    }
     let rs = if points.nrows() > 1 { s[0] as usize } else { points.ncols().max(1) };
     let cs = if points.ncols() > 1 { s[1] as usize } else { 1 };
-    (rs, cs)
+    Some((rs, cs))
+}
+
+/// The reference's distance fold zips the two rows and silently truncates to the shorter one
+/// (src/distance.rs:26-35).  The C ABI reads exactly `d` elements per query row, so a wrong-sized
+/// query would be an out-of-bounds read from safe code: every query method checks first.
+fn check_dim(got: usize, want: usize, what: &str) {
+    assert!(got == want, "petal_neighbors: {what} has dimension {got}, the tree has {want}");
+}
+
+/// Points for `create`: borrowed as they are when the strides are non-negative, otherwise copied
+/// to standard layout (the copy only lives for the duration of the call -- the engine keeps its
+/// own flattened copy on the device).
+fn with_points<A: Element, R>(
+    points: &CowArray<'_, A, Ix2>,
+    f: impl FnOnce(*const A, usize, usize, usize, usize) -> R,
+) -> R {
+    let (n, d) = (points.nrows(), points.ncols());
+    match strides(points) {
+        Some((rs, cs)) => f(points.as_ptr(), n, d, rs, cs),
+        None => {
+            let dense = points.as_standard_layout();
+            f(dense.as_ptr(), n, d, d.max(1), 1)
+        }
+    }
 }
 
 /// Ball tree; the partition is built on the host with the reference's split rule and lives,
@@ -80,14 +110,14 @@ impl<'a, A: Element> BallTree<'a, A, Euclidean> {
     pub fn new<T: Into<CowArray<'a, A, Ix2>>>(points: T, metric: Euclidean) -> Result<Self, ArrayError> {
         let points: CowArray<'a, A, Ix2> = points.into();
         let (n, d) = (points.nrows(), points.ncols());
-        let (rs, cs) = strides(&points);
         let mut h = std::ptr::null_mut();
-        check_create(unsafe { A::ball_create(points.as_ptr(), n, d, rs, cs, std::ptr::null(), &mut h) })?;
+        check_create(with_points(&points, |p, n, d, rs, cs| unsafe { A::ball_create(p, n, d, rs, cs, std::ptr::null(), &mut h) }))?;
         Ok(Self { handle: Handle(h), n, d, metric, _p: PhantomData })
     }
 
     /// reference src/ball_tree.rs:80-86
     pub fn query_nearest<S: Data<Elem = A>>(&self, point: &ArrayBase<S, Ix1>) -> (usize, A) {
+        check_dim(point.len(), self.d, "point");
         let q = point.to_owned();
         let (mut i, mut dist) = (0u64, A::zero());
         check(unsafe { A::ball_nearest(self.handle.0, q.as_ptr(), 1, self.d, &mut i, &mut dist) });
@@ -96,6 +126,7 @@ impl<'a, A: Element> BallTree<'a, A, Euclidean> {
 
     /// reference src/ball_tree.rs:102-121
     pub fn query<S: Data<Elem = A>>(&self, point: &ArrayBase<S, Ix1>, k: usize) -> (Vec<usize>, Vec<A>) {
+        check_dim(point.len(), self.d, "point");
         if k == 0 {
             return (Vec::new(), Vec::new());
         }
@@ -109,6 +140,7 @@ impl<'a, A: Element> BallTree<'a, A, Euclidean> {
 
     /// reference src/ball_tree.rs:137-142 (indices ascending)
     pub fn query_radius<S: Data<Elem = A>>(&self, point: &ArrayBase<S, Ix1>, distance: A) -> Vec<usize> {
+        check_dim(point.len(), self.d, "point");
         let q = point.to_owned();
         let (offsets, indices) = self.radius_raw(q.as_ptr(), 1, self.d, distance);
         debug_assert_eq!(offsets.len(), 2);
@@ -117,6 +149,7 @@ impl<'a, A: Element> BallTree<'a, A, Euclidean> {
 
     /// Batched `query`: row-major `nq x k`; rows padded with (usize::MAX, +inf) when k > n.
     pub fn query_batch(&self, queries: &ArrayView2<A>, k: usize) -> (Array2<usize>, Array2<A>) {
+        check_dim(queries.ncols(), self.d, "query batch");
         let q = queries.as_standard_layout();
         let nq = q.nrows();
         let mut idx = vec![0u64; nq * k];
@@ -129,6 +162,7 @@ impl<'a, A: Element> BallTree<'a, A, Euclidean> {
     }
 
     pub fn query_nearest_batch(&self, queries: &ArrayView2<A>) -> (Array1<usize>, Array1<A>) {
+        check_dim(queries.ncols(), self.d, "query batch");
         let q = queries.as_standard_layout();
         let nq = q.nrows();
         let mut idx = vec![0u64; nq];
@@ -139,6 +173,7 @@ impl<'a, A: Element> BallTree<'a, A, Euclidean> {
 
     /// Batched `query_radius`: CSR `(offsets[nq + 1], indices)`.
     pub fn query_radius_batch(&self, queries: &ArrayView2<A>, distance: A) -> (Vec<usize>, Vec<usize>) {
+        check_dim(queries.ncols(), self.d, "query batch");
         let q = queries.as_standard_layout();
         self.radius_raw(q.as_ptr(), q.nrows(), self.d, distance)
     }
@@ -191,15 +226,15 @@ impl<'a, A: Element> VantagePointTree<'a, A, Euclidean> {
     /// reference src/vantage_point_tree.rs:51-72
     pub fn new<T: Into<CowArray<'a, A, Ix2>>>(points: T, metric: Euclidean) -> Result<Self, ArrayError> {
         let points: CowArray<'a, A, Ix2> = points.into();
-        let (n, d) = (points.nrows(), points.ncols());
-        let (rs, cs) = strides(&points);
+        let d = points.ncols();
         let mut h = std::ptr::null_mut();
-        check_create(unsafe { A::vp_create(points.as_ptr(), n, d, rs, cs, std::ptr::null(), &mut h) })?;
+        check_create(with_points(&points, |p, n, d, rs, cs| unsafe { A::vp_create(p, n, d, rs, cs, std::ptr::null(), &mut h) }))?;
         Ok(Self { handle: Handle(h), d, metric, _p: PhantomData })
     }
 
     /// reference src/vantage_point_tree.rs:88-98
     pub fn query_nearest<S: Data<Elem = A>>(&self, needle: &ArrayBase<S, Ix1>) -> (usize, A) {
+        check_dim(needle.len(), self.d, "needle");
         let q = needle.to_owned();
         let (mut i, mut dist) = (0u64, A::zero());
         check(unsafe { A::vp_nearest(self.handle.0, q.as_ptr(), 1, self.d, &mut i, &mut dist) });
@@ -207,6 +242,7 @@ impl<'a, A: Element> VantagePointTree<'a, A, Euclidean> {
     }
 
     pub fn query_nearest_batch(&self, queries: &ArrayView2<A>) -> (Array1<usize>, Array1<A>) {
+        check_dim(queries.ncols(), self.d, "query batch");
         let q = queries.as_standard_layout();
         let nq = q.nrows();
         let mut idx = vec![0u64; nq];
