@@ -1,6 +1,8 @@
 // engine.cu -- host side of libpetal_b200.so: tree handles, workspaces, kernel launches and the
 // C ABI declared in include/petal_b200.h.  No CPU fallback: every query entry point launches the
 // sm_100a kernels of kernels.cuh or fails with PN_CUDA.
+#include <sys/mman.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -99,10 +101,17 @@ struct Engine final : pn_tree {
     DevBuf w_qraw, w_q, w_home, w_hist, w_cursor, w_order, w_part_d, w_part_i, w_floor_d, w_floor_i,
         w_counters, w_out_i, w_out_d, w_counts, w_offsets, w_hits;
     DevTree<A> dt{};
+    // host-buffer calls are software-pipelined over chunks of queries: H2D of chunk i+1 and D2H of chunk i-1 run on their own
+    // streams under the kernels of chunk i (two sets of raw-query / result buffers)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[2] = {nullptr, nullptr}, e_cmp[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
+    DevBuf w_qraw2[2], w_oi2[2], w_od2[2];
+    DevBuf r_qraw[2], r_q[2], r_counts[2], r_offsets[2], r_hits[2];  // radius pipeline workspaces
+    unsigned long long* pin_tot = nullptr;                            // pinned: chunk totals of the radius count pass
     void* pin_stage[2] = {nullptr, nullptr};  // pinned D2H staging for the variable-length radius output
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     static constexpr size_t PIN_BYTES = 16u << 20;
-    // tensor path (f32 only): augmented TF32 operands, see tc_filter.cuh
+    // tensor path (f32 input only): augmented FP16 operands, see tc_filter.cuh
     DevBuf d_baug, d_center, w_aaug, w_qmargin, w_trace, w_gbound;
     bool tensor_ready = false, last_used_tensor = false;
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
@@ -118,7 +127,16 @@ struct Engine final : pn_tree {
                               &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin, &w_trace, &w_gbound})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
-            for (int i = 0; i < 2; ++i) { if (pin_stage[i]) cudaFreeHost(pin_stage[i]); if (pin_ev[i]) cudaEventDestroy(pin_ev[i]); }
+            for (int i = 0; i < 2; ++i) {
+                if (pin_stage[i]) cudaFreeHost(pin_stage[i]);
+                if (pin_ev[i]) cudaEventDestroy(pin_ev[i]);
+                w_qraw2[i].release(); w_oi2[i].release(); w_od2[i].release();
+                r_qraw[i].release(); r_q[i].release(); r_counts[i].release(); r_offsets[i].release(); r_hits[i].release();
+                for (cudaEvent_t e : {e_in[i], e_cmp[i], e_out[i]}) if (e) cudaEventDestroy(e);
+            }
+            if (pin_tot) cudaFreeHost(pin_tot);
+            if (s_in) cudaStreamDestroy(s_in);
+            if (s_out) cudaStreamDestroy(s_out);
             if (stream) cudaStreamDestroy(stream);
         }
     }
@@ -253,6 +271,9 @@ struct Engine final : pn_tree {
             int ex = 0;
             if (maxabs > 0.f && std::isfinite(maxabs)) { std::frexp(maxabs, &ex); }  // maxabs = m 2^ex, m in [0.5, 1)
             tscale = std::ldexp(1.0f, -ex);
+            // data spans so small (or so large) that s or s^2 leaves the normal float range: the scaled operands would
+            // hold inf/NaN and the filter would silently drop candidates -- such trees stay on the exact scan
+            if (!std::isnormal(tscale) || !std::isnormal(tscale * tscale) || !std::isfinite(maxabs)) { tensor_ready = false; return PN_OK; }
             TRY(d_center.ensure(ft.dpad * 4));
             CU(cudaMemcpy(d_center.p, c.data(), ft.dpad * 4, cudaMemcpyHostToDevice));
             const size_t baug_bytes = (ft.n + tc::BN - 1) / tc::BN * tc::BN * (size_t)kp * 2;  // whole tiles
@@ -313,8 +334,13 @@ struct Engine final : pn_tree {
         fa.stages &= ~1u;  // even: each ring stage always belongs to the same one of the two producer warps
         if (fa.stages < 2) return fail(PN_CUDA, "tensor path: shared memory budget too small for this dimension");
         if (mt == 4) {
-            // EXPERIMENT: PN_TC_HALF=0 selects the previous one-stage-per-subtile configuration
-            static const bool half = !(getenv("PN_TC_HALF") && atoi(getenv("PN_TC_HALF")) == 0);
+            // One K chunk (d <= 26): two half-tile stages per subtile (149.2 vs 151.8 ms on config 2, 21 % fewer exact
+            // reranks: thresholds tightened by the first half already apply to the second).  With two or three chunks the
+            // N = 64 MMAs (75 cycles against 86 for N = 128) cost more than the second stage buys: d = 64: 92.4 vs 88.4 ms.
+            bool half = fa.nkc == 1;
+#ifdef PN_TC_PROFILE
+            if (getenv("PN_TC_HALF")) half = atoi(getenv("PN_TC_HALF")) != 0;
+#endif
             if (half) {
                 if (dt.dv == 4) return launch_filter_t<4, K, 4, 2, 64>(map_a, fa, st);
                 if (dt.dv == 8) return launch_filter_t<8, K, 4, 2, 64>(map_a, fa, st);
@@ -339,8 +365,8 @@ struct Engine final : pn_tree {
     }
 
     // tensor k-NN: same contract as knn_device
-    int knn_device_tensor(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st,
-                          bool self_query = false) {
+    int knn_device_tensor(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint32_t kstride, uint64_t* idx_out, A* dist_out,
+                          cudaStream_t st, bool self_query = false) {
         if constexpr (sizeof(A) == 4) {
             if (!self_query) TRY(stage_queries(qraw, nq, stride, st, false));
             const float* qpad = self_query ? d_pts.as<float>() : w_q.as<float>();
@@ -374,9 +400,7 @@ struct Engine final : pn_tree {
             const uint32_t q_main = (uint32_t)std::min<uint64_t>((uint64_t)main_qt * QT, nq), q_tail = nq - q_main;
             TRY(w_part_d.ensure(((size_t)q_main + (size_t)S * q_tail) * KP * 4));
             TRY(w_part_i.ensure(((size_t)q_main + (size_t)S * q_tail) * KP * 4));
-            TRY(w_counters.ensure(256));
             if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * 4)); TRY(w_floor_i.ensure((size_t)nq * 4)); }
-            CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
             tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(qpad, d_center.as<float>(), tscale, nq, ft.d, ft.dpad, kp, pmax,
                                                                     w_aaug.as<__half>(), w_qmargin.as<float>());
             CU(cudaGetLastError());
@@ -412,7 +436,7 @@ struct Engine final : pn_tree {
                     fa.row0 = 0; fa.nq = q_main; fa.tiles_per_split = n_tiles; fa.g_bound = nullptr;
                     TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
                     merge_lists_kernel<A, uint32_t><<<(q_main + 127) / 128, 128, 0, st>>>(
-                        w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, q_main, kk, idx_out, dist_out, k, p * KP, fl_d, fl_i, rmap);
+                        w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, q_main, kk, idx_out, dist_out, kstride, p * KP, fl_d, fl_i, rmap);
                     CU(cudaGetLastError());
                     counters.kernel_launches += 2;
                 }
@@ -427,8 +451,8 @@ struct Engine final : pn_tree {
                     TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
                     // with a row map (self query) the merge addresses output rows absolutely; otherwise the outputs are offset
                     merge_lists_kernel<A, uint32_t><<<(q_tail + 127) / 128, 128, 0, st>>>(
-                        reinterpret_cast<const A*>(fa.part_d), fa.part_i, S, q_tail, kk, rmap ? idx_out : idx_out + (size_t)q_main * k,
-                        rmap ? dist_out : dist_out + (size_t)q_main * k, k, p * KP, fl_d ? fl_d + q_main : nullptr,
+                        reinterpret_cast<const A*>(fa.part_d), fa.part_i, S, q_tail, kk, rmap ? idx_out : idx_out + (size_t)q_main * kstride,
+                        rmap ? dist_out : dist_out + (size_t)q_main * kstride, kstride, p * KP, fl_d ? fl_d + q_main : nullptr,
                         fl_i ? fl_i + q_main : nullptr, rmap ? rmap + q_main : nullptr);
                     CU(cudaGetLastError());
                     counters.kernel_launches += 2;
@@ -475,15 +499,23 @@ struct Engine final : pn_tree {
     // k-NN for nq queries whose raw rows are already on the device; results to device buffers
     // self_query: the queries are the stored points themselves, already padded, resident and in bucket
     // order (perfect tile coherence); results are written to the ORIGINAL row of each point
-    int knn_device(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint64_t* idx_out, A* dist_out, cudaStream_t st,
+    int knn_device(const A* qraw, uint32_t nq, size_t stride, uint32_t k_req, uint64_t* idx_out, A* dist_out, cudaStream_t st,
                    bool self_query = false) {
+        // k > n: only n neighbours exist; scan for those and pad the remaining columns directly
+        const uint32_t kstride = k_req, k = (uint32_t)std::min<uint64_t>(k_req, ft.n);
+        if (k < kstride) {
+            const size_t tot = (size_t)nq * (kstride - k);
+            pad_rows_kernel<A><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(idx_out, dist_out, nq, kstride, k);
+            CU(cudaGetLastError());
+            ++counters.kernel_launches;
+        }
         // AUTO: with the point stream split over the SMs the tensor path wins at every batch size measured (uniform 1M x 16:
         // 1 query 0.43 vs 0.80 ms, 1024 queries 1.2 vs 8.3 ms; 1M x 128: 0.43 vs 3.8 ms and 1.3 vs 31.8 ms,
         // scripts/small_batch.py), so AUTO uses it for every batch size whenever the tree is tensor-eligible (f32, d >= 16).
         // The pruned scan can still win for single queries on tightly clustered data (it touches a few buckets only):
         // PN_ALGO_SIMT selects it.
         last_used_tensor = tensor_ready;
-        if (last_used_tensor) return knn_device_tensor(qraw, nq, stride, k, idx_out, dist_out, st, self_query);
+        if (last_used_tensor) return knn_device_tensor(qraw, nq, stride, k, kstride, idx_out, dist_out, st, self_query);
         const bool sort = !self_query && ft.n_buckets > 1 && nq > (uint32_t)TQ;
         if (!self_query) TRY(stage_queries(qraw, nq, stride, st, sort));
         const uint32_t tiles = (nq + TQ - 1) / TQ;
@@ -495,9 +527,7 @@ struct Engine final : pn_tree {
         const uint32_t n_pass = (k + KP - 1) / KP;
         TRY(w_part_d.ensure((size_t)n_splits * nq * KP * sizeof(A)));
         TRY(w_part_i.ensure((size_t)n_splits * nq * KP * 4));
-        TRY(w_counters.ensure(32));
         if (n_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * sizeof(A))); TRY(w_floor_i.ensure((size_t)nq * 4)); }
-        CU(cudaMemsetAsync(w_counters.p, 0, 32, st));
         CU(cudaEventRecord(ev[2], st));
         for (uint32_t p = 0; p < n_pass; ++p) {
             const uint32_t kk = std::min(KP, k - p * KP);
@@ -509,7 +539,7 @@ struct Engine final : pn_tree {
             a.counters = w_counters.as<unsigned long long>();
             TRY(launch_knn(a, dim3(tiles, n_splits), st, k1));
             merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
-                w_part_d.as<A>(), w_part_i.as<uint32_t>(), n_splits, nq, kk, idx_out, dist_out, k, p * KP,
+                w_part_d.as<A>(), w_part_i.as<uint32_t>(), n_splits, nq, kk, idx_out, dist_out, kstride, p * KP,
                 n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr,
                 self_query ? d_ids.as<uint32_t>() : nullptr);
             CU(cudaGetLastError());
@@ -554,9 +584,31 @@ struct Engine final : pn_tree {
         if (nq > 1 && stride < ft.d) return fail(PN_BAD_ARG, "q_row_stride < dimension");
         return PN_OK;
     }
+    // k is a u32 inside the engine; the result buffers of a chunk (w_out_*) are k * 12..16 bytes per query
+    static int check_k(size_t k) {
+        if (k > (1u << 20)) return fail(PN_BAD_ARG, "k must be <= 2^20");
+        return PN_OK;
+    }
+
+    int ensure_io() {
+        if (s_in) return PN_OK;
+        CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i)
+            for (cudaEvent_t* e : {&e_in[i], &e_cmp[i], &e_out[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        return PN_OK;
+    }
+    // queries per chunk of a host-buffer call: whole waves of the tensor scan (n_sms CTAs x 512 queries), at most four
+    // of them, so that a large batch becomes >= 4 chunks whose copies hide under the neighbouring chunks' kernels
+    size_t host_chunk(size_t nq) const {
+        const size_t wave = (size_t)n_sms * 512;
+        if (nq < 2 * wave) return nq;
+        return std::min<size_t>(4, std::max<size_t>(1, nq / (4 * wave))) * wave;
+    }
 
     int knn_host(const void* qv, size_t nq, size_t stride, size_t k, uint64_t* idx, void* distv) override {
         TRY(check_query_args(qv, nq, stride));
+        TRY(check_k(k));
         if (k == 0 || nq == 0) return PN_OK;  // src/ball_tree.rs:106-108
         if (!idx || !distv) return fail(PN_BAD_ARG, "output buffer is null");
         std::lock_guard<std::mutex> lk(mu);
@@ -567,29 +619,59 @@ struct Engine final : pn_tree {
         A* dist = (A*)distv;
         cudaStream_t st = stream;
         TRY(use_stream(st));
-        // bounded device workspace: chunks of at most 2^20 queries
-        const size_t chunk = 1u << 20;
-        CU(cudaEventRecord(ev[0], st));
-        for (size_t q0 = 0; q0 < nq; q0 += chunk) {
-            const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
-            TRY(w_qraw.ensure((size_t)cq * ft.d * sizeof(A)));
-            TRY(w_out_i.ensure((size_t)cq * k * 8));
-            TRY(w_out_d.ensure((size_t)cq * k * sizeof(A)));
-            CU(cudaMemcpy2DAsync(w_qraw.p, ft.d * sizeof(A), q + q0 * stride, stride * sizeof(A), ft.d * sizeof(A), cq,
-                                 cudaMemcpyHostToDevice, st));
-            TRY(knn_device(w_qraw.as<A>(), cq, ft.d, (uint32_t)k, w_out_i.as<uint64_t>(), w_out_d.as<A>(), st));
-            CU(cudaMemcpyAsync(idx + q0 * k, w_out_i.p, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(dist + q0 * k, w_out_d.p, (size_t)cq * k * sizeof(A), cudaMemcpyDeviceToHost, st));
-            counters.h2d_bytes += (uint64_t)cq * ft.d * sizeof(A);
-            counters.d2h_bytes += (uint64_t)cq * k * (8 + sizeof(A));
-            if (q0 + chunk < nq) CU(cudaStreamSynchronize(st));  // workspace reuse
+        TRY(ensure_io());
+        const size_t chunk = host_chunk(nq), n_chunks = (nq + chunk - 1) / chunk;
+        const size_t spitch = std::max<size_t>(stride, ft.d) * sizeof(A);  // a single row may come with any stride
+        // every allocation happens before the first copy is enqueued (cudaMalloc synchronises the device)
+        for (int b = 0; b < (n_chunks > 1 ? 2 : 1); ++b) {
+            TRY(w_qraw2[b].ensure(chunk * ft.d * sizeof(A)));
+            TRY(w_oi2[b].ensure(chunk * k * 8));
+            TRY(w_od2[b].ensure(chunk * k * sizeof(A)));
         }
+        TRY(w_counters.ensure(256));
+        CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
+        CU(cudaEventRecord(ev[0], st));
+        CU(cudaStreamWaitEvent(s_in, ev[0], 0));
+        // Enqueue order: H2D(c), kernels(c), then D2H(c-1).  With pageable host memory a D2H copy blocks the host until it
+        // is done, so it is issued only after the next chunk's kernels are already queued behind it on the device.
+        auto d2h = [&](size_t c) -> int {
+            const int b = (int)(c & 1);
+            const size_t q0 = c * chunk;
+            const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
+            CU(cudaStreamWaitEvent(s_out, e_cmp[b], 0));
+            CU(cudaMemcpyAsync(idx + q0 * k, w_oi2[b].p, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, s_out));
+            CU(cudaMemcpyAsync(dist + q0 * k, w_od2[b].p, (size_t)cq * k * sizeof(A), cudaMemcpyDeviceToHost, s_out));
+            CU(cudaEventRecord(e_out[b], s_out));
+            counters.d2h_bytes += (uint64_t)cq * k * (8 + sizeof(A));
+            return PN_OK;
+        };
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const int b = (int)(c & 1);
+            const size_t q0 = c * chunk;
+            const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
+            // H2D: the raw-query buffer is free once the kernels of chunk c-2 are done
+            if (c >= 2) CU(cudaStreamWaitEvent(s_in, e_cmp[b], 0));
+            CU(cudaMemcpy2DAsync(w_qraw2[b].p, ft.d * sizeof(A), q + q0 * stride, spitch, ft.d * sizeof(A), cq, cudaMemcpyHostToDevice, s_in));
+            CU(cudaEventRecord(e_in[b], s_in));
+            // kernels: need the queries, and the result buffers back from the D2H of chunk c-2
+            CU(cudaStreamWaitEvent(st, e_in[b], 0));
+            if (c >= 2) CU(cudaStreamWaitEvent(st, e_out[b], 0));
+            TRY(knn_device(w_qraw2[b].as<A>(), cq, ft.d, (uint32_t)k, w_oi2[b].as<uint64_t>(), w_od2[b].as<A>(), st));
+            CU(cudaEventRecord(e_cmp[b], st));
+            counters.h2d_bytes += (uint64_t)cq * ft.d * sizeof(A);
+            if (c >= 1) TRY(d2h(c - 1));
+        }
+        TRY(d2h(n_chunks - 1));
+        // the call ends when the last results are on the host: the tree's stream joins the D2H stream
+        CU(cudaStreamWaitEvent(st, e_out[(n_chunks - 1) & 1], 0));
+        if (n_chunks > 1) CU(cudaStreamWaitEvent(st, e_out[(n_chunks - 2) & 1], 0));
         CU(cudaEventRecord(ev[1], st));
         return fetch_counters(st, nq);
     }
 
     int knn_dev(const void* qv, size_t nq, size_t stride, size_t k, uint64_t* idx, void* distv, cudaStream_t st, bool sync) override {
         TRY(check_query_args(qv, nq, stride));
+        TRY(check_k(k));
         if (k == 0 || nq == 0) return PN_OK;
         if (!idx || !distv) return fail(PN_BAD_ARG, "output buffer is null");
         std::lock_guard<std::mutex> lk(mu);
@@ -598,6 +680,8 @@ struct Engine final : pn_tree {
         if (!st) st = stream;
         TRY(use_stream(st));
         counters = pn_counters{};
+        TRY(w_counters.ensure(256));
+        CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
         CU(cudaEventRecord(ev[0], st));
         TRY(knn_device((const A*)qv, (uint32_t)nq, stride, (uint32_t)k, idx, (A*)distv, st));
         CU(cudaEventRecord(ev[1], st));
@@ -624,7 +708,7 @@ struct Engine final : pn_tree {
             return PN_OK;
         };
         TRY(issue(0));
-        const unsigned nt = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
+        const unsigned nt = std::max(1u, std::min(12u, std::thread::hardware_concurrency() / 2));
         for (size_t p = 0; p < pieces; ++p) {
             CU(cudaEventSynchronize(pin_ev[p & 1]));
             if (p + 1 < pieces) TRY(issue(p + 1));  // the other buffer was consumed in the previous iteration
@@ -647,6 +731,7 @@ struct Engine final : pn_tree {
     int knn_self(size_t k, uint64_t* idx, void* distv, bool dev, cudaStream_t st, bool sync) override {
         if (host_only) return fail(PN_CUDA, "tree was built with PN_FLAG_HOST_ONLY: no device, and there is no CPU fallback");
         if (ft.n != ft.n_total) return fail(PN_BAD_ARG, "self-query needs the whole point set in this handle (not a shard)");
+        TRY(check_k(k));
         if (k == 0) return PN_OK;
         if (!idx || !distv) return fail(PN_BAD_ARG, "output buffer is null");
         std::lock_guard<std::mutex> lk(mu);
@@ -662,6 +747,8 @@ struct Engine final : pn_tree {
             TRY(w_out_d.ensure((size_t)nq * k * sizeof(A)));
             oi = w_out_i.as<uint64_t>(); od = w_out_d.as<A>();
         }
+        TRY(w_counters.ensure(256));
+        CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
         CU(cudaEventRecord(ev[0], st));
         TRY(knn_device(d_pts.as<A>(), nq, ft.dpad, (uint32_t)k, oi, od, st, true));
         if (!dev) {
@@ -675,6 +762,24 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 
+    // Result buffers of the radius call are handed to the caller (released with pn_free = free()).  Large ones are
+    // 2 MiB-aligned and advised as huge pages: writing hundreds of MB of freshly mapped memory is otherwise dominated by
+    // 4 KiB page faults.
+    static void* result_alloc(size_t bytes) {
+        if (bytes < (8u << 20)) return malloc(bytes ? bytes : 8);
+        const size_t al = 2u << 20;
+        void* p = aligned_alloc(al, (bytes + al - 1) / al * al);
+#ifdef MADV_HUGEPAGE
+        if (p) madvise(p, (bytes + al - 1) / al * al, MADV_HUGEPAGE);
+#endif
+        return p;
+    }
+
+    // Two-stage software pipeline over chunks of queries, two workspace sets on two streams:
+    //   A(c): H2D queries, pad, count traversal, offsets scan, chunk total -> pinned word
+    //   B(c): fill traversal at the offsets, per-query sort, D2H of offsets and hits (widened u32 -> u64 on the host)
+    // A(c+1) is enqueued before the host blocks on B(c)'s copies, so the next chunk's traversal runs under the D2H and the
+    // host-side widening of this one.
     int radius_host(const void* qv, size_t nq, size_t stride, double rr, uint64_t** offs_out, uint64_t** idx_out) override {
         TRY(check_query_args(qv, nq, stride));
         if (ft.kind != 0) return fail(PN_BAD_ARG, "query_radius is a BallTree method (the reference VP tree has none)");
@@ -687,60 +792,88 @@ struct Engine final : pn_tree {
         const A* q = (const A*)qv;
         cudaStream_t st = stream;
         TRY(use_stream(st));
+        TRY(ensure_io());
+        cudaStream_t sx[2] = {s_in, s_out};  // the two pipeline streams (alternate chunks)
         uint64_t* offs = (uint64_t*)malloc((nq + 1) * 8);
         if (!offs) return fail(PN_OOM, "malloc offsets");
         offs[0] = 0;
         uint64_t* hit_buf = nullptr;
         size_t hit_cap = 0, total = 0;
-        const size_t chunk = 1u << 20;
+        const size_t chunk = nq <= (1u << 18) ? std::max<size_t>(nq, 1) : (1u << 17);
+        const size_t n_chunks = (nq + chunk - 1) / chunk;
         const uint32_t wpb = 8;
-        auto bail = [&](int rc) { free(offs); free(hit_buf); return rc; };
-        if (cudaEventRecord(ev[0], st) != cudaSuccess) return bail(fail(PN_CUDA, "cudaEventRecord"));
+        auto bail = [&](int rc) { cudaDeviceSynchronize(); free(offs); free(hit_buf); return rc; };
 #define CUB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(fail(PN_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_))); } while (0)
 #define TRYB(x) do { int r_ = (x); if (r_ != PN_OK) return bail(r_); } while (0)
         last_used_tensor = false;
-        TRYB(w_counters.ensure(32));
-        CUB(cudaMemsetAsync(w_counters.p, 0, 32, st));
-        for (size_t q0 = 0; q0 < nq; q0 += chunk) {
+        if (!pin_tot) CUB(cudaHostAlloc((void**)&pin_tot, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+        TRYB(w_counters.ensure(256));
+        const size_t spitch = std::max<size_t>(stride, ft.d) * sizeof(A);
+        for (int b = 0; b < (n_chunks > 1 ? 2 : 1); ++b) {
+            TRYB(r_qraw[b].ensure(chunk * ft.d * sizeof(A)));
+            TRYB(r_q[b].ensure(chunk * ft.dpad * sizeof(A)));
+            TRYB(r_counts[b].ensure(chunk * 4));
+            TRYB(r_offsets[b].ensure((chunk + 1) * 8));
+        }
+        CUB(cudaMemsetAsync(w_counters.p, 0, 256, st));
+        CUB(cudaEventRecord(ev[0], st));
+        CUB(cudaEventRecord(ev[2], st));
+        for (int b = 0; b < 2; ++b) CUB(cudaStreamWaitEvent(sx[b], ev[0], 0));
+        auto stage_a = [&](size_t c) -> int {
+            const int b = (int)(c & 1);
+            const size_t q0 = c * chunk;
             const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
-            TRYB(w_qraw.ensure((size_t)cq * ft.d * sizeof(A)));
-            CUB(cudaMemcpy2DAsync(w_qraw.p, ft.d * sizeof(A), q + q0 * stride, stride * sizeof(A), ft.d * sizeof(A), cq,
-                                  cudaMemcpyHostToDevice, st));
-            TRYB(stage_queries(w_qraw.as<A>(), cq, ft.d, st, false));
-            TRYB(w_counts.ensure((size_t)cq * 4));
-            TRYB(w_offsets.ensure((size_t)(cq + 1) * 8));
+            cudaStream_t s = sx[b];
+            CU(cudaMemcpy2DAsync(r_qraw[b].p, ft.d * sizeof(A), q + q0 * stride, spitch, ft.d * sizeof(A), cq, cudaMemcpyHostToDevice, s));
+            const size_t tot = (size_t)cq * ft.dpad;
+            pad_queries_kernel<A><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(r_qraw[b].as<A>(), ft.d, cq, ft.d, ft.dpad, r_q[b].as<A>());
+            CU(cudaGetLastError());
             const unsigned blocks = (cq + wpb - 1) / wpb;
-            if (q0 == 0) CUB(cudaEventRecord(ev[2], st));
-            radius_kernel<A><<<blocks, wpb * 32, 0, st>>>(dt, w_q.as<V>(), cq, r, w_counts.as<uint32_t>(), nullptr, nullptr,
-                                                         w_counters.as<unsigned long long>());
-            CUB(cudaGetLastError());
-            offsets_scan_kernel<<<1, 1024, 0, st>>>(w_counts.as<uint32_t>(), w_offsets.as<uint64_t>(), cq);
-            CUB(cudaGetLastError());
-            CUB(cudaMemcpyAsync(offs + q0 + 1, w_offsets.as<uint64_t>() + 1, (size_t)cq * 8, cudaMemcpyDeviceToHost, st));
-            CUB(cudaStreamSynchronize(st));
-            const uint64_t ctotal = offs[q0 + cq];  // chunk-local total
-            TRYB(w_hits.ensure((ctotal ? ctotal : 1) * 4));
-            radius_kernel<A><<<blocks, wpb * 32, 0, st>>>(dt, w_q.as<V>(), cq, r, w_counts.as<uint32_t>(), w_offsets.as<uint64_t>(),
-                                                         w_hits.as<uint32_t>(), nullptr);
-            CUB(cudaGetLastError());
-            segment_sort_kernel<<<blocks, wpb * 32, 0, st>>>(w_offsets.as<uint64_t>(), w_hits.as<uint32_t>(), cq);
-            CUB(cudaGetLastError());
-            if (q0 + chunk >= nq) CUB(cudaEventRecord(ev[3], st));
-            counters.kernel_launches += 4;
+            radius_kernel<A><<<blocks, wpb * 32, 0, s>>>(dt, r_q[b].as<V>(), cq, r, r_counts[b].as<uint32_t>(), nullptr, nullptr,
+                                                        w_counters.as<unsigned long long>());
+            CU(cudaGetLastError());
+            offsets_scan_kernel<<<1, 1024, 0, s>>>(r_counts[b].as<uint32_t>(), r_offsets[b].as<uint64_t>(), cq);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(&pin_tot[b], r_offsets[b].as<uint64_t>() + cq, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaEventRecord(e_in[b], s));
+            counters.kernel_launches += 3;
+            counters.h2d_bytes += (uint64_t)cq * ft.d * sizeof(A);
+            return PN_OK;
+        };
+        if (n_chunks) TRYB(stage_a(0));
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const int b = (int)(c & 1);
+            const size_t q0 = c * chunk;
+            const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
+            cudaStream_t s = sx[b];
+            if (c + 1 < n_chunks) TRYB(stage_a(c + 1));
+            CUB(cudaEventSynchronize(e_in[b]));
+            const uint64_t ctotal = pin_tot[b];  // chunk-local total
             if (total + ctotal > hit_cap) {
-                size_t ncap = std::max<size_t>(total + ctotal, hit_cap * 2);
-                uint64_t* nb = (uint64_t*)realloc(hit_buf, (ncap ? ncap : 1) * 8);
-                if (!nb) return bail(fail(PN_OOM, "realloc indices"));
+                // sized once from the first chunk's density (+12 %); grows only if later chunks are denser
+                size_t ncap = std::max<size_t>(total + ctotal, c == 0 ? (size_t)((double)ctotal * 1.12 * (double)nq / cq) + 1024 : hit_cap + hit_cap / 2);
+                uint64_t* nb = (uint64_t*)result_alloc(ncap * 8);
+                if (!nb) return bail(fail(PN_OOM, "allocating the result indices"));
+                if (hit_buf) { memcpy(nb, hit_buf, total * 8); free(hit_buf); }
                 hit_buf = nb; hit_cap = ncap;
             }
-            TRYB(copy_out_widen(hit_buf + total, w_hits.as<uint32_t>(), ctotal, st));
-            CUB(cudaStreamSynchronize(st));
-            for (uint32_t i = 1; i <= cq; ++i) offs[q0 + i] += total;  // chunk-local -> global offsets
+            TRYB(r_hits[b].ensure((ctotal ? ctotal : 1) * 4));
+            const unsigned blocks = (cq + wpb - 1) / wpb;
+            radius_kernel<A><<<blocks, wpb * 32, 0, s>>>(dt, r_q[b].as<V>(), cq, r, r_counts[b].as<uint32_t>(), r_offsets[b].as<uint64_t>(),
+                                                        r_hits[b].as<uint32_t>(), nullptr);
+            CUB(cudaGetLastError());
+            segment_sort_kernel<<<blocks, wpb * 32, 0, s>>>(r_offsets[b].as<uint64_t>(), r_hits[b].as<uint32_t>(), cq);
+            CUB(cudaGetLastError());
+            counters.kernel_launches += 2;
+            CUB(cudaMemcpyAsync(offs + q0 + 1, r_offsets[b].as<uint64_t>() + 1, (size_t)cq * 8, cudaMemcpyDeviceToHost, s));
+            TRYB(copy_out_widen(hit_buf + total, r_hits[b].as<uint32_t>(), ctotal, s));
+            CUB(cudaStreamSynchronize(s));
+            if (total) for (uint32_t i = 1; i <= cq; ++i) offs[q0 + i] += total;  // chunk-local -> global offsets
             total += ctotal;
-            counters.h2d_bytes += (uint64_t)cq * ft.d * sizeof(A);
             counters.d2h_bytes += (uint64_t)cq * 8 + ctotal * 4;
         }
-        if (nq == 0) { CUB(cudaEventRecord(ev[2], st)); CUB(cudaEventRecord(ev[3], st)); }
+        for (int b = 0; b < 2; ++b) { CUB(cudaEventRecord(e_cmp[b], sx[b])); CUB(cudaStreamWaitEvent(st, e_cmp[b], 0)); }
+        CUB(cudaEventRecord(ev[3], st));
         CUB(cudaEventRecord(ev[1], st));
         if (!hit_buf) hit_buf = (uint64_t*)malloc(8);
         TRYB(fetch_counters(st, nq));

@@ -519,6 +519,18 @@ __global__ void merge_lists_kernel(const A* __restrict__ in_d, const I* __restri
     if (floor_d && k > 0) { floor_d[q] = last_d; floor_i[q] = last_i == ~0ull ? NO_ID : (uint32_t)last_i; }
 }
 
+// k > n: columns [k_eff, k) of every output row are (UINT64_MAX, +inf) -- the reference returns only n results
+// (the heap never fills, src/ball_tree.rs:219-221); the fixed-shape batched output pads instead of scanning again
+template <typename A>
+__global__ void pad_rows_kernel(uint64_t* __restrict__ out_i, A* __restrict__ out_d, uint32_t nq, uint32_t k, uint32_t k_eff) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = k - k_eff;
+    if (i >= (size_t)nq * w) return;
+    const size_t at = (i / w) * k + k_eff + (i % w);
+    out_i[at] = ~0ull;
+    out_d[at] = pos_inf<A>();
+}
+
 // ---- query staging ----------------------------------------------------------------------------
 template <typename A>
 __global__ void pad_queries_kernel(const A* __restrict__ q, size_t q_stride, uint32_t nq, uint32_t d, uint32_t dpad,

@@ -75,3 +75,102 @@ def gaussian_mixture(n: int, d: int, seed: int, n_centers: int = 1024, sigma: fl
             v = np.clip(v, 0.0, np.nextafter(1.0, 0.0))
         out[s:e] = v.astype(dtype)
     return out
+
+
+# ---- the same streams generated with torch (on the GPU: 10M x 128 in well under a second instead of a minute of
+# numpy), bit-identical to the numpy generators above (tests/test_host_side.py).  int64 arithmetic wraps mod 2^64. ----
+def _s64(x: int) -> int:
+    x &= 0xFFFFFFFFFFFFFFFF
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _lsr_t(z, s: int):
+    return (z >> s) & ((1 << (64 - s)) - 1)
+
+
+def _mix_t(z):
+    z = (z ^ _lsr_t(z, 30)) * _s64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr_t(z, 27)) * _s64(0x94D049BB133111EB)
+    return z ^ _lsr_t(z, 31)
+
+
+def _hash_t(seed: int, counters):
+    return _mix_t(counters + _s64(((seed + 1) & 0xFFFFFFFFFFFFFFFF) * 0x9E3779B97F4A7C15))
+
+
+def _to_unit_t(h, dtype):
+    import torch
+    if dtype == torch.float32:
+        return _lsr_t(h, 40).to(torch.float32) * (2.0 ** -24)
+    return _lsr_t(h, 11).to(torch.float64) * (2.0 ** -53)
+
+
+def uniform_torch(n: int, d: int, seed: int, dtype=None, row0: int = 0, device="cuda", chunk: int = 1 << 24, out=None):
+    """uniform() as a torch tensor on `device`."""
+    import torch
+    dtype = dtype or torch.float32
+    if out is None:
+        out = torch.empty((n, d), dtype=dtype, device=device)
+    flat = out.view(-1)
+    total = n * d
+    for s in range(0, total, chunk):
+        e = min(total, s + chunk)
+        c = torch.arange(s + row0 * d, e + row0 * d, dtype=torch.int64, device=out.device)
+        flat[s:e] = _to_unit_t(_hash_t(seed, c), dtype)
+    return out
+
+
+def _umod_t(h, m: int):
+    """h mod m for h an unsigned 64-bit value held in an int64 tensor."""
+    return ((_lsr_t(h, 1) % m) * 2 + (h & 1)) % m
+
+
+def gaussian_mixture_torch(n: int, d: int, seed: int, n_centers: int = 1024, sigma: float = 0.05, center_seed: int = 4,
+                           dtype=None, clip: bool = False, row0: int = 0, device="cuda", chunk_rows: int = 1 << 17):
+    """gaussian_mixture() as a torch tensor on `device`."""
+    import torch
+    dtype = dtype or torch.float32
+    centers = uniform_torch(n_centers, d, center_seed, torch.float64, device=device)
+    out = torch.empty((n, d), dtype=dtype, device=device)
+    cols = torch.arange(d, dtype=torch.int64, device=device)[None, :]
+    hi = float(np.nextafter(1.0, 0.0))
+    for s in range(0, n, chunk_rows):
+        e = min(n, s + chunk_rows)
+        rows = torch.arange(row0 + s, row0 + e, dtype=torch.int64, device=device)
+        comp = _umod_t(_hash_t(seed ^ 0x5EED, rows), n_centers)
+        c = rows[:, None] * d + cols
+        acc = torch.zeros(c.shape, dtype=torch.int64, device=device)
+        for t in range(3):
+            h = _hash_t(seed, c * 3 + t)
+            for lane in range(4):
+                acc += _lsr_t(h, 16 * lane) & 0xFFFF
+        z = (acc.to(torch.float64) + 6.0) / 65536.0 - 6.0
+        v = centers[comp] + sigma * z
+        if clip:
+            v = torch.clamp(v, 0.0, hi)
+        out[s:e] = v.to(dtype)
+    return out
+
+
+def fast_uniform(n, d, seed, dtype=np.float32, row0=0):
+    """uniform() as a numpy array, generated on the GPU when one is present (identical values either way)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+            return uniform_torch(n, d, seed, tdt, row0=row0).cpu().numpy()
+    except ImportError:
+        pass
+    return uniform(n, d, seed, dtype, row0=row0)
+
+
+def fast_gaussian_mixture(n, d, seed, dtype=np.float32, **kw):
+    """gaussian_mixture() as a numpy array, generated on the GPU when one is present (identical values either way)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+            return gaussian_mixture_torch(n, d, seed, dtype=tdt, **kw).cpu().numpy()
+    except ImportError:
+        pass
+    return gaussian_mixture(n, d, seed, dtype=dtype, **kw)

@@ -162,3 +162,31 @@ def test_synth_is_counter_based():
     assert a.min() >= 0 and a.max() < 1
     g = synth.gaussian_mixture(64, 5, 9, n_centers=4, dtype=np.float64)
     assert np.array_equal(g[10:20], synth.gaussian_mixture(10, 5, 9, n_centers=4, dtype=np.float64, row0=10))
+
+
+def test_shards_of_fewer_points_than_shards(pn):
+    """n < 2^shard_depth: every point is owned by exactly one shard, the other shards are Empty (the descent
+    used to stop at one-point ranges, so several shard indices returned the same point)."""
+    for n, depth in ((3, 2), (5, 3), (1, 2)):
+        pts = np.random.default_rng(n).random((n, 4)).astype(np.float32)
+        ids, empty = [], 0
+        for s in range(1 << depth):
+            try:
+                t = pn.BallTree.euclidean(pts, host_only=True, shard_depth=depth, shard_index=s)
+                ids += t.layout()["ids"].tolist()
+            except pn.ArrayError as e:
+                assert e.kind == "Empty"
+                empty += 1
+        assert sorted(ids) == list(range(n)) and empty == (1 << depth) - n
+
+
+def test_torch_generators_match_numpy():
+    import torch
+    import petal_neighbors_b200  # noqa: F401
+    from petal_neighbors_b200 import synth
+    for dt, tdt in ((np.float32, torch.float32), (np.float64, torch.float64)):
+        a = synth.uniform(1000, 7, 3, dt, row0=5)
+        assert np.array_equal(a, synth.uniform_torch(1000, 7, 3, tdt, row0=5, device="cpu").numpy())
+        kw = dict(n_centers=37, sigma=0.05, row0=11, clip=True)
+        g = synth.gaussian_mixture(3000, 9, 5, dtype=dt, **kw)
+        assert np.array_equal(g, synth.gaussian_mixture_torch(3000, 9, 5, dtype=tdt, device="cpu", **kw).numpy())
