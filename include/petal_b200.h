@@ -58,6 +58,12 @@ typedef enum pn_algo {
     PN_ALGO_TENSOR = 2 /* tcgen05 FP16 filter + exact rerank (f32 input; AUTO: every batch size when d >= 16) */
 } pn_algo;
 
+/* Where the tree is built.  Both builders apply the reference's split rule and produce bit-identical flattened
+ * layouts (points of a bucket in ascending original index); AUTO builds on the device when the tree has a device
+ * and at least 32768 points.  (BASELINE.json: "tree construction stays on the host" -- the host builder remains
+ * the default for small trees and the checker of the device builder) */
+typedef enum pn_builder { PN_BUILDER_AUTO = 0, PN_BUILDER_HOST = 1, PN_BUILDER_DEVICE = 2 } pn_builder;
+
 #define PN_FLAG_HOST_ONLY 1u /* build + flatten on the host only (no device; queries fail with
                                 PN_CUDA).  For builder tests on machines without a GPU. */
 
@@ -74,7 +80,8 @@ typedef struct pn_build_opts {
      * (src/ball_tree.rs:535-537 split rule).  Returned indices stay global.  0/0 = all. */
     uint32_t shard_depth;
     uint32_t shard_index;
-    uint32_t reserved[8];
+    uint32_t builder;     /* pn_builder: where the partition is computed (ball trees; VP trees are host-built) */
+    uint32_t reserved[7];
 } pn_build_opts;
 
 typedef struct pn_tree pn_tree; /* opaque: flattened, device-resident tree */
@@ -123,6 +130,12 @@ int32_t pn_vptree_create_f32(const float *points, size_t n, size_t d, size_t row
                              size_t col_stride, const pn_build_opts *opts, pn_tree **out);
 int32_t pn_vptree_create_f64(const double *points, size_t n, size_t d, size_t row_stride,
                              size_t col_stride, const pn_build_opts *opts, pn_tree **out);
+/* The same for points that already live on the device `opts->device` (row-major, unit column stride): the partition
+ * is computed on the GPU (src/ball_tree.rs:445-613 level by level) and nothing crosses PCIe. */
+int32_t pn_balltree_create_dev_f32(const float *points_dev, size_t n, size_t d, size_t row_stride,
+                                   const pn_build_opts *opts, pn_tree **out);
+int32_t pn_balltree_create_dev_f64(const double *points_dev, size_t n, size_t d, size_t row_stride,
+                                   const pn_build_opts *opts, pn_tree **out);
 int32_t pn_tree_destroy(pn_tree *tree); /* Rust Drop */
 
 /* --- BallTree::query (src/ball_tree.rs:102-121), batched: `nq` queries, row stride

@@ -25,10 +25,10 @@ import numpy as np
 
 from . import _ffi
 from . import distance
-from ._ffi import PN_ALGO_AUTO, PN_ALGO_SIMT, PN_ALGO_TENSOR
+from ._ffi import PN_ALGO_AUTO, PN_ALGO_SIMT, PN_ALGO_TENSOR, PN_BUILDER_AUTO, PN_BUILDER_HOST, PN_BUILDER_DEVICE
 
 __all__ = ["BallTree", "VantagePointTree", "ArrayError", "EngineError", "distance", "merge_topk_dev",
-           "PN_ALGO_AUTO", "PN_ALGO_SIMT", "PN_ALGO_TENSOR"]
+           "PN_ALGO_AUTO", "PN_ALGO_SIMT", "PN_ALGO_TENSOR", "PN_BUILDER_AUTO", "PN_BUILDER_HOST", "PN_BUILDER_DEVICE"]
 
 
 class ArrayError(Exception):
@@ -78,19 +78,10 @@ class _Tree:
     _kind = "balltree"
 
     def __init__(self, points, metric=None, *, device=-1, bucket_size=0, algo=PN_ALGO_AUTO, host_threads=0,
-                 host_only=False, shard_depth=0, shard_index=0):
+                 host_only=False, shard_depth=0, shard_index=0, builder=PN_BUILDER_AUTO):
         if metric is not None and not isinstance(metric, distance.Euclidean):
             raise TypeError("only distance.Euclidean is offered by the B200 engine (Cosine is not a metric; "
                             "there is no CPU fallback)")
-        points = np.asarray(points)
-        if points.ndim != 2:
-            raise ValueError("points must be a 2-D array")
-        self.dtype = points.dtype
-        self._sfx = _sfx(points.dtype)
-        n, d = points.shape
-        if n and d and (points.strides[0] < 0 or points.strides[1] < 0):
-            points = np.ascontiguousarray(points)
-        rs, cs = _strides(points) if n else (d, 1)
         opts = _ffi.BuildOpts()
         opts.struct_size = C.sizeof(_ffi.BuildOpts)
         opts.device = device
@@ -100,11 +91,36 @@ class _Tree:
         opts.flags = _ffi.PN_FLAG_HOST_ONLY if host_only else 0
         opts.shard_depth = shard_depth
         opts.shard_index = shard_index
+        opts.builder = builder
         self._h = C.c_void_p()
+        self.metric = metric if metric is not None else distance.Euclidean()
+        if hasattr(points, "data_ptr") and getattr(points, "is_cuda", False):
+            # a CUDA tensor (torch): the points stay on the device and the tree is built there
+            if self._kind != "balltree":
+                raise TypeError("device-resident construction is a BallTree feature")
+            if points.dim() != 2 or (points.shape[1] > 1 and points.stride(1) != 1):
+                raise ValueError("points must be a 2-D tensor with unit column stride")
+            self.dtype = np.dtype(str(points.dtype).replace("torch.", ""))
+            self._sfx = _sfx(self.dtype)
+            n, d = int(points.shape[0]), int(points.shape[1])
+            if opts.device < 0:
+                opts.device = points.device.index
+            fn = getattr(_ffi.lib(), f"pn_balltree_create_dev_{self._sfx}")
+            _check(fn(points.data_ptr(), n, d, int(points.stride(0)) if n > 1 else max(d, 1), C.byref(opts), C.byref(self._h)))
+            self.dim = d
+            return
+        points = np.asarray(points)
+        if points.ndim != 2:
+            raise ValueError("points must be a 2-D array")
+        self.dtype = points.dtype
+        self._sfx = _sfx(points.dtype)
+        n, d = points.shape
+        if n and d and (points.strides[0] < 0 or points.strides[1] < 0):
+            points = np.ascontiguousarray(points)
+        rs, cs = _strides(points) if n else (d, 1)
         L = _ffi.lib()
         fn = getattr(L, f"pn_{self._kind}_create_{self._sfx}")
         _check(fn(points.ctypes.data if n else None, n, d, rs, cs, C.byref(opts), C.byref(self._h)))
-        self.metric = metric if metric is not None else distance.Euclidean()
         self.dim = d
 
     # BallTree::euclidean src/ball_tree.rs:367-373 / VantagePointTree::euclidean src/vantage_point_tree.rs:31-36

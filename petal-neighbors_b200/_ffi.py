@@ -13,12 +13,13 @@ PN_KIND_BALL, PN_KIND_VP = 0, 1
 PN_F32, PN_F64 = 0, 1
 PN_ALGO_AUTO, PN_ALGO_SIMT, PN_ALGO_TENSOR = 0, 1, 2
 PN_FLAG_HOST_ONLY = 1
+PN_BUILDER_AUTO, PN_BUILDER_HOST, PN_BUILDER_DEVICE = 0, 1, 2
 
 # every symbol include/petal_b200.h declares
 EXPORTS = [
     "pn_last_error_message", "pn_abi_version", "pn_device_count",
     "pn_balltree_create_f32", "pn_balltree_create_f64", "pn_vptree_create_f32", "pn_vptree_create_f64",
-    "pn_tree_destroy",
+    "pn_balltree_create_dev_f32", "pn_balltree_create_dev_f64", "pn_tree_destroy",
     "pn_balltree_query_f32", "pn_balltree_query_f64",
     "pn_balltree_query_nearest_f32", "pn_balltree_query_nearest_f64",
     "pn_balltree_query_radius_f32", "pn_balltree_query_radius_f64",
@@ -33,7 +34,8 @@ EXPORTS = [
 class BuildOpts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("bucket_size", C.c_uint32),
                 ("algo", C.c_uint32), ("host_threads", C.c_uint32), ("flags", C.c_uint32),
-                ("shard_depth", C.c_uint32), ("shard_index", C.c_uint32), ("reserved", C.c_uint32 * 8)]
+                ("shard_depth", C.c_uint32), ("shard_index", C.c_uint32), ("builder", C.c_uint32),
+                ("reserved", C.c_uint32 * 7)]
 
 
 class TreeInfo(C.Structure):
@@ -78,6 +80,9 @@ def lib():
             f = getattr(L, f"pn_{kind}_create_{sfx}")
             f.restype = C.c_int32
             f.argtypes = [vp, sz, sz, sz, sz, C.POINTER(BuildOpts), C.POINTER(vp)]
+        f = getattr(L, f"pn_balltree_create_dev_{sfx}")
+        f.restype = C.c_int32
+        f.argtypes = [vp, sz, sz, sz, C.POINTER(BuildOpts), C.POINTER(vp)]
         f = getattr(L, f"pn_balltree_query_{sfx}")
         f.restype = C.c_int32
         f.argtypes = [vp, vp, sz, sz, sz, vp, vp]

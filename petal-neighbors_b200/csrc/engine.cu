@@ -13,6 +13,7 @@
 
 #include "../../include/petal_b200.h"
 #include "flat_tree.hpp"
+#include "gpu_build.hpp"
 #include "kernels.cuh"
 #include "tc_filter.cuh"
 
@@ -106,7 +107,7 @@ struct Engine final : pn_tree {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t e_in[2] = {nullptr, nullptr}, e_cmp[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
     DevBuf w_qraw2[2], w_oi2[2], w_od2[2];
-    DevBuf r_qraw[2], r_q[2], r_counts[2], r_offsets[2], r_hits[2];  // radius pipeline workspaces
+    DevBuf r_qraw[2], r_q[2], r_counts[2], r_offsets[2], r_hits[2], r_slab[2], r_qlist[2], r_nlist[2];  // radius pipeline workspaces
     unsigned long long* pin_tot = nullptr;                            // pinned: chunk totals of the radius count pass
     void* pin_stage[2] = {nullptr, nullptr};  // pinned D2H staging for the variable-length radius output
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
@@ -114,6 +115,7 @@ struct Engine final : pn_tree {
     // tensor path (f32 input only): augmented FP16 operands, see tc_filter.cuh
     DevBuf d_baug, d_center, w_aaug, w_qmargin, w_trace, w_gbound;
     bool tensor_ready = false, last_used_tensor = false;
+    bool gpu_built = false;  // the tree arrays were produced on the device (gpu_build.cu); host copies are fetched on demand
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
     float pmax = 0.f;      // max |s (p - center)|
     float tscale = 1.f;    // s: power of two bringing the centred coordinates into [-1, 1]
@@ -132,6 +134,7 @@ struct Engine final : pn_tree {
                 if (pin_ev[i]) cudaEventDestroy(pin_ev[i]);
                 w_qraw2[i].release(); w_oi2[i].release(); w_od2[i].release();
                 r_qraw[i].release(); r_q[i].release(); r_counts[i].release(); r_offsets[i].release(); r_hits[i].release();
+                r_slab[i].release(); r_qlist[i].release(); r_nlist[i].release();
                 for (cudaEvent_t e : {e_in[i], e_cmp[i], e_out[i]}) if (e) cudaEventDestroy(e);
             }
             if (pin_tot) cudaFreeHost(pin_tot);
@@ -141,12 +144,61 @@ struct Engine final : pn_tree {
         }
     }
 
-    int upload() {
-        DeviceGuard g(device);
-        if (!g.ok) return fail(PN_CUDA, "no usable CUDA device (there is no CPU fallback)");
+    int open_device() {
         CU(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto& e : ev) CU(cudaEventCreate(&e));
+        return PN_OK;
+    }
+
+    // ---- device-side construction (gpu_build.cu): raw rows on the device -> the same arrays upload() would have sent
+    static gb::BallOut<A> alloc_tree_arrays(void* ctx, uint64_t n, const gb::TreeShape& shape) {
+        Engine* e = static_cast<Engine*>(ctx);
+        FlatTree<A>& t = e->ft;
+        t.kind = 0; t.n = n;
+        t.dpad = (uint32_t)((t.d + VT<A>::N - 1) / VT<A>::N * VT<A>::N);
+        t.L = shape.L; t.n_internal = (1u << t.L) - 1; t.n_buckets = 1u << t.L; t.n_nodes = (1u << (t.L + 1)) - 1;
+        const auto& seg = shape.seg[t.L];
+        t.bucket_lo.assign(seg.begin(), seg.end() - 1);
+        t.bucket_hi.assign(seg.begin() + 1, seg.end());
+        t.bucket_max = 0;
+        for (uint32_t b = 0; b < t.n_buckets; ++b) t.bucket_max = std::max(t.bucket_max, t.bucket_hi[b] - t.bucket_lo[b]);
+        gb::BallOut<A> o{nullptr, nullptr, nullptr, nullptr};
+        if (e->d_pts.ensure((size_t)n * t.dpad * sizeof(A)) != PN_OK || e->d_ids.ensure((size_t)n * 4) != PN_OK ||
+            e->d_centers.ensure((size_t)t.n_nodes * t.dpad * sizeof(A)) != PN_OK || e->d_radii.ensure((size_t)t.n_nodes * sizeof(A)) != PN_OK)
+            return o;
+        o.pts = e->d_pts.template as<A>(); o.ids = e->d_ids.template as<uint32_t>();
+        o.centers = e->d_centers.template as<A>(); o.radii = e->d_radii.template as<A>();
+        return o;
+    }
+    int build_on_device(const A* raw_dev, size_t n_all, size_t d, size_t stride, uint32_t bucket, uint32_t shard_depth, uint32_t shard_index) {
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "no usable CUDA device (there is no CPU fallback)");
+        TRY(open_device());
+        ft.d = (uint32_t)d; ft.n_total = n_all;
+        gb::TreeShape shape;
+        uint64_t n = 0;
+        std::string err;
+        const int rc = gb::build_ball_tree<A>(raw_dev, n_all, (uint32_t)d, stride, bucket, shard_depth, shard_index, shape, &n,
+                                              &Engine::alloc_tree_arrays, this, stream, err);
+        if (rc) return fail(rc == (int)cudaErrorMemoryAllocation ? PN_OOM : PN_CUDA, "device tree build: " + err);
+        if (n == 0) return fail(PN_EMPTY, "shard holds no points");
+        gpu_built = true;
+        TRY(d_blo.ensure(ft.bucket_lo.size() * 4));
+        TRY(d_bhi.ensure(ft.bucket_hi.size() * 4));
+        TRY(d_vpids.ensure(16));
+        CU(cudaMemcpy(d_blo.p, ft.bucket_lo.data(), ft.bucket_lo.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_bhi.p, ft.bucket_hi.data(), ft.bucket_hi.size() * 4, cudaMemcpyHostToDevice));
+        info.device_bytes = d_pts.cap + d_ids.cap + d_blo.cap + d_bhi.cap + d_centers.cap + d_radii.cap + d_vpids.cap;
+        fill_dev_tree();
+        TRY(prepare_tensor());
+        return PN_OK;
+    }
+
+    int upload() {
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "no usable CUDA device (there is no CPU fallback)");
+        TRY(open_device());
         auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
             TRY(b.ensure(bytes ? bytes : 16));
             if (bytes) CU(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
@@ -237,45 +289,52 @@ struct Engine final : pn_tree {
         if constexpr (sizeof(A) == 4) {
             if (!tensor_eligible()) return PN_OK;
             kp = (ft.d + tc::NSLOT + tc::KC - 1) / tc::KC * tc::KC;
-            // centre = mean of the stored points (double accumulation on the host), then the largest centred
-            // coordinate.  Both passes run over fixed chunks of 64 Ki rows on the host threads and combine the
-            // chunk partials in chunk order, so the result does not depend on the number of threads.
-            const size_t CH = 65536, n_ch = (ft.n + CH - 1) / CH;
-            const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>({n_ch, 32, std::max(1u, std::thread::hardware_concurrency())}));
-            auto chunks = [&](auto&& body) {  // body(chunk index), chunks dealt round-robin to nt threads
-                std::vector<std::thread> th;
-                for (unsigned w = 1; w < nt; ++w) th.emplace_back([&, w] { for (size_t c = w; c < n_ch; c += nt) body(c); });
-                for (size_t c = 0; c < n_ch; c += nt) body(c);
-                for (auto& t : th) t.join();
-            };
-            std::vector<double> part(n_ch * ft.dpad, 0.0);
-            chunks([&](size_t c) {
-                double* m = &part[c * ft.dpad];
-                for (size_t i = c * CH, e = std::min<size_t>(ft.n, (c + 1) * CH); i < e; ++i)
-                    for (uint32_t j = 0; j < ft.d; ++j) m[j] += (double)ft.pts[i * ft.dpad + j];
-            });
-            std::vector<double> mean(ft.dpad, 0.0);
-            for (size_t c = 0; c < n_ch; ++c)
-                for (uint32_t j = 0; j < ft.d; ++j) mean[j] += part[c * ft.dpad + j];
+            // centre = mean of the stored points (double accumulation), then the largest centred coordinate.  Both passes
+            // run over fixed chunks of 64 Ki rows and combine the chunk partials in chunk order, so the result depends
+            // neither on the number of host threads nor on where it is computed: on the host for host-built trees (the
+            // rows are still there), on the device for device-built ones (gb::centre_and_range_f32, the same sums).
             std::vector<float> c(ft.dpad, 0.f);
-            for (uint32_t j = 0; j < ft.d; ++j) c[j] = (float)(mean[j] / (double)ft.n);
-            std::vector<float> pmaxabs(n_ch, 0.f);
-            chunks([&](size_t ch) {
-                float m = 0.f;
-                for (size_t i = ch * CH, e = std::min<size_t>(ft.n, (ch + 1) * CH); i < e; ++i)
-                    for (uint32_t j = 0; j < ft.d; ++j) m = std::max(m, std::fabs(ft.pts[i * ft.dpad + j] - c[j]));
-                pmaxabs[ch] = m;
-            });
             float maxabs = 0.f;
-            for (size_t ch = 0; ch < n_ch; ++ch) maxabs = std::max(maxabs, pmaxabs[ch]);
+            TRY(d_center.ensure(ft.dpad * 4));
+            if (gpu_built) {
+                std::string err;
+                if (gb::centre_and_range_f32(d_pts.as<float>(), ft.n, ft.d, ft.dpad, d_center.as<float>(), c.data(), &maxabs, stream, err))
+                    return fail(PN_CUDA, "tensor path set-up: " + err);
+            } else {
+                const size_t CH = 65536, n_ch = (ft.n + CH - 1) / CH;
+                const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>({n_ch, 32, std::max(1u, std::thread::hardware_concurrency())}));
+                auto chunks = [&](auto&& body) {  // body(chunk index), chunks dealt round-robin to nt threads
+                    std::vector<std::thread> th;
+                    for (unsigned w = 1; w < nt; ++w) th.emplace_back([&, w] { for (size_t c = w; c < n_ch; c += nt) body(c); });
+                    for (size_t c = 0; c < n_ch; c += nt) body(c);
+                    for (auto& t : th) t.join();
+                };
+                std::vector<double> part(n_ch * ft.dpad, 0.0);
+                chunks([&](size_t c) {
+                    double* m = &part[c * ft.dpad];
+                    for (size_t i = c * CH, e = std::min<size_t>(ft.n, (c + 1) * CH); i < e; ++i)
+                        for (uint32_t j = 0; j < ft.d; ++j) m[j] += (double)ft.pts[i * ft.dpad + j];
+                });
+                std::vector<double> mean(ft.dpad, 0.0);
+                for (size_t c = 0; c < n_ch; ++c)
+                    for (uint32_t j = 0; j < ft.d; ++j) mean[j] += part[c * ft.dpad + j];
+                for (uint32_t j = 0; j < ft.d; ++j) c[j] = (float)(mean[j] / (double)ft.n);
+                std::vector<float> pmaxabs(n_ch, 0.f);
+                chunks([&](size_t ch) {
+                    float m = 0.f;
+                    for (size_t i = ch * CH, e = std::min<size_t>(ft.n, (ch + 1) * CH); i < e; ++i)
+                        for (uint32_t j = 0; j < ft.d; ++j) m = std::max(m, std::fabs(ft.pts[i * ft.dpad + j] - c[j]));
+                    pmaxabs[ch] = m;
+                });
+                for (size_t ch = 0; ch < n_ch; ++ch) maxabs = std::max(maxabs, pmaxabs[ch]);
+                CU(cudaMemcpy(d_center.p, c.data(), ft.dpad * 4, cudaMemcpyHostToDevice));
+            }
             int ex = 0;
             if (maxabs > 0.f && std::isfinite(maxabs)) { std::frexp(maxabs, &ex); }  // maxabs = m 2^ex, m in [0.5, 1)
             tscale = std::ldexp(1.0f, -ex);
             // data spans so small (or so large) that s or s^2 leaves the normal float range: the scaled operands would
             // hold inf/NaN and the filter would silently drop candidates -- such trees stay on the exact scan
             if (!std::isnormal(tscale) || !std::isnormal(tscale * tscale) || !std::isfinite(maxabs)) { tensor_ready = false; return PN_OK; }
-            TRY(d_center.ensure(ft.dpad * 4));
-            CU(cudaMemcpy(d_center.p, c.data(), ft.dpad * 4, cudaMemcpyHostToDevice));
             const size_t baug_bytes = (ft.n + tc::BN - 1) / tc::BN * tc::BN * (size_t)kp * 2;  // whole tiles
             TRY(d_baug.ensure(baug_bytes));
             CU(cudaMemsetAsync(d_baug.p, 0, baug_bytes, stream));
@@ -814,6 +873,9 @@ struct Engine final : pn_tree {
             TRYB(r_q[b].ensure(chunk * ft.dpad * sizeof(A)));
             TRYB(r_counts[b].ensure(chunk * 4));
             TRYB(r_offsets[b].ensure((chunk + 1) * 8));
+            TRYB(r_slab[b].ensure(chunk * RADIUS_CAP * 4));
+            TRYB(r_qlist[b].ensure(chunk * 4));
+            TRYB(r_nlist[b].ensure(16));
         }
         CUB(cudaMemsetAsync(w_counters.p, 0, 256, st));
         CUB(cudaEventRecord(ev[0], st));
@@ -829,8 +891,9 @@ struct Engine final : pn_tree {
             pad_queries_kernel<A><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(r_qraw[b].as<A>(), ft.d, cq, ft.d, ft.dpad, r_q[b].as<A>());
             CU(cudaGetLastError());
             const unsigned blocks = (cq + wpb - 1) / wpb;
-            radius_kernel<A><<<blocks, wpb * 32, 0, s>>>(dt, r_q[b].as<V>(), cq, r, r_counts[b].as<uint32_t>(), nullptr, nullptr,
-                                                        w_counters.as<unsigned long long>());
+            CU(cudaMemsetAsync(r_nlist[b].p, 0, 4, s));
+            radius_kernel<A, 0><<<blocks, wpb * 32, 0, s>>>(dt, r_q[b].as<V>(), cq, r, r_counts[b].as<uint32_t>(), nullptr, r_slab[b].as<uint32_t>(),
+                                                           w_counters.as<unsigned long long>());
             CU(cudaGetLastError());
             offsets_scan_kernel<<<1, 1024, 0, s>>>(r_counts[b].as<uint32_t>(), r_offsets[b].as<uint64_t>(), cq);
             CU(cudaGetLastError());
@@ -859,9 +922,14 @@ struct Engine final : pn_tree {
             }
             TRYB(r_hits[b].ensure((ctotal ? ctotal : 1) * 4));
             const unsigned blocks = (cq + wpb - 1) / wpb;
-            radius_kernel<A><<<blocks, wpb * 32, 0, s>>>(dt, r_q[b].as<V>(), cq, r, r_counts[b].as<uint32_t>(), r_offsets[b].as<uint64_t>(),
-                                                        r_hits[b].as<uint32_t>(), nullptr);
+            compact_hits_kernel<<<blocks, wpb * 32, 0, s>>>(r_slab[b].as<uint32_t>(), r_counts[b].as<uint32_t>(), r_offsets[b].as<uint64_t>(), cq,
+                                                            r_hits[b].as<uint32_t>(), r_qlist[b].as<uint32_t>(), r_nlist[b].as<uint32_t>());
             CUB(cudaGetLastError());
+            // second traversal for the queries that overflowed their slab only (warps past the list length exit at once)
+            radius_kernel<A, 1><<<blocks, wpb * 32, 0, s>>>(dt, r_q[b].as<V>(), cq, r, nullptr, r_offsets[b].as<uint64_t>(), r_hits[b].as<uint32_t>(),
+                                                           nullptr, r_qlist[b].as<uint32_t>(), r_nlist[b].as<uint32_t>());
+            CUB(cudaGetLastError());
+            ++counters.kernel_launches;
             segment_sort_kernel<<<blocks, wpb * 32, 0, s>>>(r_offsets[b].as<uint64_t>(), r_hits[b].as<uint32_t>(), cq);
             CUB(cudaGetLastError());
             counters.kernel_launches += 2;
@@ -885,6 +953,13 @@ struct Engine final : pn_tree {
     }
 
     int layout(uint32_t* ids, uint32_t* blo, uint32_t* bhi, void* rad, void* cen, void* pts) override {
+        if (gpu_built) {
+            DeviceGuard g(device);
+            if (ids) CU(cudaMemcpy(ids, d_ids.p, (size_t)ft.n * 4, cudaMemcpyDeviceToHost));
+            if (rad) CU(cudaMemcpy(rad, d_radii.p, (size_t)ft.n_nodes * sizeof(A), cudaMemcpyDeviceToHost));
+            if (cen) CU(cudaMemcpy(cen, d_centers.p, (size_t)ft.n_nodes * ft.dpad * sizeof(A), cudaMemcpyDeviceToHost));
+            ids = nullptr; rad = nullptr; cen = nullptr;
+        }
         if (ids) memcpy(ids, ft.ids.data(), ft.ids.size() * 4);
         if (blo) memcpy(blo, ft.bucket_lo.data(), ft.bucket_lo.size() * 4);
         if (bhi) memcpy(bhi, ft.bucket_hi.data(), ft.bucket_hi.size() * 4);
@@ -900,6 +975,9 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 };
+
+template <typename A>
+static int finish_create(int kind, std::unique_ptr<Engine<A>>& e, const pn_build_opts& o, std::chrono::steady_clock::time_point t0, pn_tree** out);
 
 template <typename A>
 static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row_stride, size_t col_stride,
@@ -922,29 +1000,60 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
     uint32_t threads = o.host_threads ? o.host_threads : std::max(1u, std::thread::hardware_concurrency());
     auto t0 = std::chrono::steady_clock::now();
     std::unique_ptr<Engine<A>> e;
+    const bool host_only = (o.flags & PN_FLAG_HOST_ONLY) != 0;
+    if (o.builder > PN_BUILDER_DEVICE) return fail(PN_BAD_ARG, "bad builder");
+    if (o.shard_depth && (kind != PN_KIND_BALL || o.shard_depth > 16 || o.shard_index >= (1u << o.shard_depth)))
+        return fail(PN_BAD_ARG, kind != PN_KIND_BALL ? "subtree sharding is a ball-tree option" : "bad shard_depth / shard_index");
+    // ball trees with a device are built there from 32768 points up (bit-identical layout, tests/test_gpu_build.py)
+    const bool on_device = kind == PN_KIND_BALL && !host_only && (o.builder == PN_BUILDER_DEVICE || (o.builder == PN_BUILDER_AUTO && n >= 32768));
+    if (o.builder == PN_BUILDER_DEVICE && !on_device) return fail(PN_BAD_ARG, "the device builder needs a ball tree with a device");
+    int dev = o.device;
+    if (!host_only && dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(PN_CUDA, "no CUDA device available (there is no CPU fallback)");
+        }
+    }
     try {
         e.reset(new Engine<A>());
-        if (kind == PN_KIND_BALL) {
+        e->host_only = host_only;
+        e->device = dev;
+        e->algo = o.algo;
+        if (on_device) {
+            // raw rows to the device (dense n x d), partition and flatten there
+            DeviceGuard g(dev);
+            if (!g.ok) return fail(PN_CUDA, "no usable CUDA device (there is no CPU fallback)");
+            DevBuf raw;
+            TRY(raw.ensure(n * d * sizeof(A)));
+            cudaError_t ce = cudaMemcpy2D(raw.p, d * sizeof(A), points, std::max(row_stride, d) * sizeof(A), d * sizeof(A), n, cudaMemcpyHostToDevice);
+            int rc = ce == cudaSuccess ? e->build_on_device(raw.as<A>(), n, d, d, bucket, o.shard_depth, o.shard_index)
+                                       : fail(PN_CUDA, std::string("uploading the points: ") + cudaGetErrorString(ce));
+            raw.release();
+            TRY(rc);
+        } else if (kind == PN_KIND_BALL) {
             BallBuilder<A> b(points, n, d, row_stride, threads);
             std::vector<uint32_t> idx(n);
             for (size_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
             size_t lo = 0, hi = n;
             if (o.shard_depth) {
-                if (o.shard_depth > 16 || o.shard_index >= (1u << o.shard_depth)) return fail(PN_BAD_ARG, "bad shard_depth / shard_index");
                 b.shard_range(idx, o.shard_depth, o.shard_index, lo, hi);
                 if (hi == lo) return fail(PN_EMPTY, "shard holds no points");
             }
             b.build(idx, lo, hi, bucket, e->ft);
         } else {
-            if (o.shard_depth) return fail(PN_BAD_ARG, "subtree sharding is a ball-tree option");
             VpBuilder<A> b(points, n, d, row_stride, threads);
             b.build(bucket, e->ft);
         }
     } catch (const std::bad_alloc&) {
         return fail(PN_OOM, "host allocation failed while building the tree");
     }
+    if (!host_only && !on_device) TRY(e->upload());
+    return finish_create(kind, e, o, t0, out);
+}
+
+template <typename A>
+static int finish_create(int kind, std::unique_ptr<Engine<A>>& e, const pn_build_opts& o, std::chrono::steady_clock::time_point t0, pn_tree** out) {
     FlatTree<A>& ft = e->ft;
-    e->host_only = (o.flags & PN_FLAG_HOST_ONLY) != 0;
     pn_tree_info& inf = e->info;
     inf.n_points = ft.n; inf.n_points_total = ft.n_total;
     inf.dim = ft.d; inf.dim_padded = ft.dpad;
@@ -952,23 +1061,43 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
     inf.n_levels = ft.L; inf.n_buckets = ft.n_buckets; inf.n_nodes = ft.n_nodes;
     inf.bucket_size_max = ft.bucket_max;
     inf.algo = o.algo;
-    inf.device = -1;
-    if (!e->host_only) {
-        int dev = o.device;
-        if (dev < 0) {
-            if (cudaGetDevice(&dev) != cudaSuccess) {
-                (void)cudaGetLastError();
-                return fail(PN_CUDA, "no CUDA device available (there is no CPU fallback)");
-            }
-        }
-        e->device = dev;
-        inf.device = dev;
-        e->algo = o.algo;
-        TRY(e->upload());
-    }
+    inf.device = e->host_only ? -1 : e->device;
     inf.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     *out = e.release();
     return PN_OK;
+}
+
+// points already on the device: BallTree::new with the partition computed there
+template <typename A>
+static int create_tree_dev(const A* points_dev, size_t n, size_t d, size_t row_stride, const pn_build_opts* opts_in, pn_tree** out) {
+    if (!out) return fail(PN_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (n == 0) return fail(PN_EMPTY, "array is empty");
+    if (!points_dev) return fail(PN_BAD_ARG, "points is null");
+    if (d == 0) return fail(PN_BAD_ARG, "points have zero columns");
+    if (n >= 0xFFFFFFFFull) return fail(PN_BAD_ARG, "n must be < 2^32 - 1 (u32 indices inside the engine)");
+    if (n > 1 && row_stride < d) return fail(PN_BAD_ARG, "row_stride < dimension");
+    pn_build_opts o{};
+    if (opts_in) memcpy(&o, opts_in, std::min<size_t>(sizeof(o), opts_in->struct_size ? opts_in->struct_size : sizeof(o)));
+    else o.device = -1;
+    if (o.flags & PN_FLAG_HOST_ONLY) return fail(PN_BAD_ARG, "device-resident points cannot build a host-only tree");
+    if (o.builder == PN_BUILDER_HOST) return fail(PN_BAD_ARG, "device-resident points are built on the device");
+    if (o.shard_depth && (o.shard_depth > 16 || o.shard_index >= (1u << o.shard_depth))) return fail(PN_BAD_ARG, "bad shard_depth / shard_index");
+    uint32_t bucket = o.bucket_size ? o.bucket_size : 256;
+    if (bucket < 8) bucket = 8;
+    int dev = o.device;
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return fail(PN_CUDA, "no CUDA device available (there is no CPU fallback)"); }
+    auto t0 = std::chrono::steady_clock::now();
+    std::unique_ptr<Engine<A>> e;
+    try {
+        e.reset(new Engine<A>());
+        e->device = dev;
+        e->algo = o.algo;
+        TRY(e->build_on_device(points_dev, n, d, row_stride, bucket, o.shard_depth, o.shard_index));
+    } catch (const std::bad_alloc&) {
+        return fail(PN_OOM, "host allocation failed while building the tree");
+    }
+    return finish_create(PN_KIND_BALL, e, o, t0, out);
 }
 
 template <typename A>
@@ -1053,6 +1182,12 @@ int32_t pn_vptree_create_f32(const float* p, size_t n, size_t d, size_t rs, size
 }
 int32_t pn_vptree_create_f64(const double* p, size_t n, size_t d, size_t rs, size_t cs, const pn_build_opts* o, pn_tree** out) {
     GUARD_BEGIN return create_tree<double>(PN_KIND_VP, p, n, d, rs, cs, o, out); GUARD_END
+}
+int32_t pn_balltree_create_dev_f32(const float* p, size_t n, size_t d, size_t rs, const pn_build_opts* o, pn_tree** out) {
+    GUARD_BEGIN return create_tree_dev<float>(p, n, d, rs, o, out); GUARD_END
+}
+int32_t pn_balltree_create_dev_f64(const double* p, size_t n, size_t d, size_t rs, const pn_build_opts* o, pn_tree** out) {
+    GUARD_BEGIN return create_tree_dev<double>(p, n, d, rs, o, out); GUARD_END
 }
 int32_t pn_tree_destroy(pn_tree* t) {
     GUARD_BEGIN delete t; return PN_OK; GUARD_END

@@ -278,6 +278,9 @@ class BallBuilder {
             uint32_t b = node - t.n_internal;
             t.bucket_lo[b] = (uint32_t)(lo - base_);
             t.bucket_hi[b] = (uint32_t)(hi - base_);
+            // canonical storage order of a bucket: ascending original index (the selection leaves an arbitrary order);
+            // the device builder (gpu_build.cu) produces the same, so the two flattened layouts are bit-identical
+            std::sort(idx.begin() + lo, idx.begin() + hi);
             return;
         }
         if (hi - lo >= 2) split(idx, lo, hi);

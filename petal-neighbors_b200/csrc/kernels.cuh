@@ -606,23 +606,35 @@ __global__ void scatter_order_kernel(const uint32_t* __restrict__ home, uint32_t
 // A node is skipped when its conservative lower bound is >= r and taken whole, without per-point
 // tests (:271-273), when its conservative upper bound is < r.  Pass 1 (out == null) counts,
 // pass 2 writes at offsets[q]. ---------------------------------------------------------------
-template <typename A>
+// Single traversal for the common case: MODE 0 writes the first RADIUS_CAP hits of every query into its slab
+// (slab[qi * RADIUS_CAP + ..]) and the full count into counts[]; compact_hits_kernel then moves the slabs to their CSR
+// positions and lists the queries whose count exceeds the slab, and only those are traversed again (MODE 1: fill at
+// offsets[qi], queries taken from qlist[0 .. *n_list)).
+constexpr uint32_t RADIUS_CAP = 64;
+template <typename A, int MODE>
 __global__ void radius_kernel(const DevTree<A> t, const typename VT<A>::V* __restrict__ q, uint32_t nq, A r,
                               uint32_t* __restrict__ counts, const uint64_t* __restrict__ offsets,
-                              uint32_t* __restrict__ out, unsigned long long* counters) {
+                              uint32_t* __restrict__ out, unsigned long long* counters,
+                              const uint32_t* __restrict__ qlist = nullptr, const uint32_t* __restrict__ n_list = nullptr) {
     using V = typename VT<A>::V;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t warps_per_block = blockDim.x >> 5;
-    const uint32_t qi = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (qi >= nq) return;
+    const uint32_t w = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (w >= nq) return;
+    uint32_t qi = w;
+    if (MODE == 1) {
+        if (w >= *n_list) return;
+        qi = qlist[w];
+    }
+    const uint32_t cap = MODE == 0 ? RADIUS_CAP : 0xffffffffu;  // entries this pass may write
     const V* qr = q + (size_t)qi * t.dv;
     auto dist_to = [&](const V* row) {
         A acc = A(0);
         for (uint32_t jc = 0; jc < t.dv; ++jc) acc = fold(acc, __ldg(qr + jc), __ldg(row + jc));
         return xsqrt(acc);
     };
-    uint64_t base = out ? offsets[qi] : 0;
+    const uint64_t base = MODE == 0 ? (uint64_t)qi * RADIUS_CAP : offsets[qi];
     uint32_t count = 0;
     unsigned long long pairs = 0;
     uint32_t stack[MAX_STACK];
@@ -641,7 +653,7 @@ __global__ void radius_kernel(const DevTree<A> t, const typename VT<A>::V* __res
         while (first < t.n_internal) { first = 2 * first + 1; last = 2 * last + 2; }
         const uint32_t lo = t.bucket_lo[first - t.n_internal], hi = t.bucket_hi[last - t.n_internal];
         if (ub < r) {  // whole node inside the ball
-            if (out) for (uint32_t p = lo + lane; p < hi; p += 32) out[base + count + (p - lo)] = t.ids[p];
+            for (uint32_t p = lo + lane; p < hi && count + (p - lo) < cap; p += 32) out[base + count + (p - lo)] = t.ids[p];
             count += hi - lo;
         } else if (node >= t.n_internal) {
             for (uint32_t p0 = lo; p0 < hi; p0 += 32) {
@@ -649,7 +661,8 @@ __global__ void radius_kernel(const DevTree<A> t, const typename VT<A>::V* __res
                 bool hit = false;
                 if (p < hi) hit = dist_to(t.pts + (size_t)p * t.dv) < r;
                 const unsigned m = __ballot_sync(full, hit);
-                if (out && hit) out[base + count + __popc(m & ((1u << lane) - 1u))] = t.ids[p];
+                const uint32_t pos = count + __popc(m & ((1u << lane) - 1u));
+                if (hit && pos < cap) out[base + pos] = t.ids[p];
                 count += __popc(m);
             }
             pairs += hi - lo;
@@ -658,8 +671,24 @@ __global__ void radius_kernel(const DevTree<A> t, const typename VT<A>::V* __res
             stack[sp++] = 2 * node + 2;
         }
     }
-    if (!out && lane == 0) counts[qi] = count;
-    if (counters && lane == 0 && !out) atomicAdd(&counters[0], pairs);
+    if (MODE == 0 && lane == 0) counts[qi] = count;
+    if (counters && lane == 0) atomicAdd(&counters[0], pairs);
+}
+
+// slabs -> CSR: one warp per query copies its (at most RADIUS_CAP) hits to offsets[qi]; queries that overflowed their
+// slab are appended to qlist for the second traversal
+__global__ void compact_hits_kernel(const uint32_t* __restrict__ slab, const uint32_t* __restrict__ counts, const uint64_t* __restrict__ offsets,
+                                    uint32_t nq, uint32_t* __restrict__ hits, uint32_t* __restrict__ qlist, uint32_t* __restrict__ n_list) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const uint32_t c = counts[qi];
+    if (c > RADIUS_CAP) {
+        if (lane == 0) qlist[atomicAdd(n_list, 1u)] = qi;
+        return;
+    }
+    const uint64_t o = offsets[qi];
+    for (uint32_t i = lane; i < c; i += 32) hits[o + i] = slab[(uint64_t)qi * RADIUS_CAP + i];
 }
 
 // u32 counts -> u64 exclusive offsets (single block)

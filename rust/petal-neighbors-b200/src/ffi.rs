@@ -22,7 +22,8 @@ pub struct pn_build_opts {
     pub flags: u32,
     pub shard_depth: u32,
     pub shard_index: u32,
-    pub reserved: [u32; 8],
+    pub builder: u32, // pn_builder: 0 auto, 1 host, 2 device
+    pub reserved: [u32; 7],
 }
 
 extern "C" {
