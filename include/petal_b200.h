@@ -44,7 +44,7 @@ typedef enum pn_status {
     PN_NOT_CONTIGUOUS = 2, /* ArrayError::NotContiguous, src/lib.rs:14-15, src/ball_tree.rs:47-49 */
     PN_BAD_ARG = 3,        /* null pointer, dtype/kind mismatch, n >= 2^32, bad option */
     PN_CUDA = 4,           /* CUDA runtime error or no device (no CPU fallback) */
-    PN_NCCL = 5,           /* reserved: collectives are driven by the host language binding */
+    PN_NCCL = 5,           /* NCCL could not be loaded, or a collective failed (pn_comm_*, pn_sharded_*, pn_tree_replicate) */
     PN_OOM = 6             /* host or device allocation failed */
 } pn_status;
 
@@ -201,6 +201,55 @@ int32_t pn_tree_query_knn_dev(pn_tree *tree, const void *queries_dev, size_t nq,
 int32_t pn_merge_topk_dev(uint32_t dtype, int32_t device, const uint64_t *idx_lists_dev,
                           const void *dist_lists_dev, size_t n_lists, size_t nq, size_t k,
                           uint64_t *idx_out_dev, void *dist_out_dev, void *stream, int32_t sync);
+
+/* --- multi-GPU inside the library (no reference equivalent: the crate is single-threaded).
+ * A pn_comm is ONE RANK of an NCCL communicator bound to one device.  One process per GPU: rank 0 calls
+ * pn_comm_unique_id, the host language ships the 128 bytes to the other ranks (MPI, torch.distributed, a file ...), every
+ * rank calls pn_comm_create.  One process driving several GPUs: pn_comm_create_all makes all ranks at once
+ * (ncclCommInitAll); calls that communicate must then be issued from one host thread per rank.
+ * NCCL is loaded at run time (libnccl.so.2; PN_NCCL_LIB overrides), so single-GPU users never need it. */
+typedef struct pn_comm pn_comm;
+#define PN_UNIQUE_ID_BYTES 128
+int32_t pn_comm_unique_id(void *id_out);
+int32_t pn_comm_create(const void *unique_id, int32_t world, int32_t rank, int32_t device, pn_comm **out);
+int32_t pn_comm_create_all(const int32_t *devices, int32_t n_dev, pn_comm **out /* n_dev entries */);
+int32_t pn_comm_destroy(pn_comm *comm);
+
+/* How the per-shard lists meet. */
+typedef enum pn_exchange {
+    PN_EXCHANGE_ALLGATHER = 0, /* ncclAllGather: every rank ends with the merged result of ALL queries */
+    PN_EXCHANGE_SLICE = 1      /* grouped ncclSend/ncclRecv: rank r ends with the merged rows of ITS query slice only
+                                  (world x less traffic); slice r = pn_query_slice(nq, r, world) */
+} pn_exchange;
+
+typedef struct pn_shard_stats {
+    double scan_ms;      /* sum over chunks: local tensor/SIMT scan + packing, CUDA events on the compute stream */
+    double exchange_ms;  /* sum over chunks: the NCCL calls, CUDA events on the exchange stream (overlaps the next scan) */
+    double merge_ms;     /* sum over chunks: k-way merge kernels */
+    double total_ms;     /* first enqueue to last merge */
+    uint64_t nccl_bytes_sent; /* payload bytes this rank sent to OTHER ranks */
+    uint64_t nccl_calls;
+    uint64_t rows_out;   /* result rows written on this rank */
+    uint32_t n_chunks, reserved;
+} pn_shard_stats;
+
+/* contiguous slice [*lo, *hi) of a batch of nq queries owned by `rank` (sizes differ by at most one) */
+void pn_query_slice(size_t nq, int32_t rank, int32_t world, size_t *lo, size_t *hi);
+
+/* Point sharding by subtree: `tree` holds subtree `rank` at depth log2(world) (pn_build_opts.shard_depth / shard_index),
+ * `queries_dev` holds ALL nq queries on this rank's device (the same on every rank).  Every rank scans its shard in
+ * chunks of queries; the sorted per-shard lists of chunk i (8-byte (distance, index) keys for f32) cross NVLink through
+ * NCCL on the exchange stream while chunk i+1 is scanned, and a k-way merge kernel produces the final rows:
+ * all nq rows on every rank (ALLGATHER), or the rows of this rank's slice, idx/dist_dev sized for the slice (SLICE).
+ * k <= 255.  Collective: every rank of `comm` must make the same call. */
+int32_t pn_sharded_query_knn_dev(pn_tree *tree, pn_comm *comm, const void *queries_dev, size_t nq,
+                                 size_t q_row_stride, size_t k, uint32_t exchange, uint64_t *idx_dev,
+                                 void *dist_dev, void *stream, pn_shard_stats *stats);
+
+/* Query sharding with the tree replicated: the flattened tree of `root` (all device arrays, including the tensor-path
+ * operand image) is sent to every other rank with ncclBroadcast instead of being rebuilt there.  On `root`, `tree` is the
+ * source and *out = tree; elsewhere `tree` is NULL and *out receives a new handle.  Collective. */
+int32_t pn_tree_replicate(pn_tree *tree, pn_comm *comm, int32_t root, pn_tree **out);
 
 /* --- introspection */
 int32_t pn_tree_get_info(const pn_tree *tree, pn_tree_info *info);

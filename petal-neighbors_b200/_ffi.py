@@ -28,7 +28,17 @@ EXPORTS = [
     "pn_pairwise_f32", "pn_pairwise_f64",
     "pn_free", "pn_tree_query_knn_dev", "pn_merge_topk_dev",
     "pn_tree_get_info", "pn_tree_get_counters", "pn_tree_get_layout",
+    "pn_comm_unique_id", "pn_comm_create", "pn_comm_create_all", "pn_comm_destroy", "pn_query_slice",
+    "pn_sharded_query_knn_dev", "pn_tree_replicate",
 ]
+PN_EXCHANGE_ALLGATHER, PN_EXCHANGE_SLICE = 0, 1
+PN_UNIQUE_ID_BYTES = 128
+
+
+class ShardStats(C.Structure):
+    _fields_ = [("scan_ms", C.c_double), ("exchange_ms", C.c_double), ("merge_ms", C.c_double), ("total_ms", C.c_double),
+                ("nccl_bytes_sent", C.c_uint64), ("nccl_calls", C.c_uint64), ("rows_out", C.c_uint64),
+                ("n_chunks", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class BuildOpts(C.Structure):
@@ -115,6 +125,20 @@ def lib():
     L.pn_tree_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.pn_tree_get_layout.restype = C.c_int32
     L.pn_tree_get_layout.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.pn_comm_unique_id.restype = C.c_int32
+    L.pn_comm_unique_id.argtypes = [vp]
+    L.pn_comm_create.restype = C.c_int32
+    L.pn_comm_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.pn_comm_create_all.restype = C.c_int32
+    L.pn_comm_create_all.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(vp)]
+    L.pn_comm_destroy.restype = C.c_int32
+    L.pn_comm_destroy.argtypes = [vp]
+    L.pn_query_slice.restype = None
+    L.pn_query_slice.argtypes = [sz, C.c_int32, C.c_int32, C.POINTER(sz), C.POINTER(sz)]
+    L.pn_sharded_query_knn_dev.restype = C.c_int32
+    L.pn_sharded_query_knn_dev.argtypes = [vp, vp, vp, sz, sz, sz, C.c_uint32, vp, vp, vp, C.POINTER(ShardStats)]
+    L.pn_tree_replicate.restype = C.c_int32
+    L.pn_tree_replicate.argtypes = [vp, vp, C.c_int32, C.POINTER(vp)]
     _lib = L
     return L
 

@@ -13,6 +13,7 @@
 
 #include "../../include/petal_b200.h"
 #include "flat_tree.hpp"
+#include "comm.hpp"
 #include "gpu_build.hpp"
 #include "kernels.cuh"
 #include "tc_filter.cuh"
@@ -86,6 +87,9 @@ struct pn_tree {
     virtual int radius_host(const void* q, size_t nq, size_t stride, double r, uint64_t** offs, uint64_t** idx) = 0;
     virtual int knn_self(size_t k, uint64_t* idx, void* dist, bool dev, cudaStream_t st, bool sync) = 0;
     virtual int layout(uint32_t* ids, uint32_t* blo, uint32_t* bhi, void* rad, void* cen, void* pts) = 0;
+    virtual int knn_sharded(pn_comm* cm, const void* q, size_t nq, size_t stride, size_t k, uint32_t exchange, uint64_t* idx, void* dist,
+                            cudaStream_t st, pn_shard_stats* stats) = 0;
+    virtual int replicate_send(pn_comm* cm, int root) = 0;
 };
 
 namespace petal {
@@ -107,6 +111,8 @@ struct Engine final : pn_tree {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t e_in[2] = {nullptr, nullptr}, e_cmp[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
     DevBuf w_qraw2[2], w_oi2[2], w_od2[2];
+    DevBuf sh_li[2], sh_ld[2], sh_pack[2], sh_gat[2], sh_gat_d[2];   // sharded k-NN: local lists, packed keys, gathered lists
+    std::vector<cudaEvent_t> sh_ev;                                    // timing events of the sharded pipeline (reused)
     DevBuf r_qraw[2], r_q[2], r_counts[2], r_offsets[2], r_hits[2], r_slab[2], r_qlist[2], r_nlist[2];  // radius pipeline workspaces
     unsigned long long* pin_tot = nullptr;                            // pinned: chunk totals of the radius count pass
     void* pin_stage[2] = {nullptr, nullptr};  // pinned D2H staging for the variable-length radius output
@@ -135,8 +141,10 @@ struct Engine final : pn_tree {
                 w_qraw2[i].release(); w_oi2[i].release(); w_od2[i].release();
                 r_qraw[i].release(); r_q[i].release(); r_counts[i].release(); r_offsets[i].release(); r_hits[i].release();
                 r_slab[i].release(); r_qlist[i].release(); r_nlist[i].release();
+                sh_li[i].release(); sh_ld[i].release(); sh_pack[i].release(); sh_gat[i].release(); sh_gat_d[i].release();
                 for (cudaEvent_t e : {e_in[i], e_cmp[i], e_out[i]}) if (e) cudaEventDestroy(e);
             }
+            for (cudaEvent_t e : sh_ev) cudaEventDestroy(e);
             if (pin_tot) cudaFreeHost(pin_tot);
             if (s_in) cudaStreamDestroy(s_in);
             if (s_out) cudaStreamDestroy(s_out);
@@ -952,6 +960,237 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 
+    // ---- point sharding by subtree: local scan -> NCCL exchange -> k-way merge, pipelined over chunks of queries ----------
+#define NC(x)                                                                                                      \
+    do {                                                                                                           \
+        ncclResult_t r_ = (x);                                                                                     \
+        if (r_ != ncclSuccess) return fail(PN_NCCL, std::string(#x) + ": " + cm->api->GetErrorString(r_));         \
+    } while (0)
+    int knn_sharded(pn_comm* cm, const void* qv, size_t nq, size_t stride, size_t k, uint32_t exchange, uint64_t* idx_out, void* dist_outv,
+                    cudaStream_t st, pn_shard_stats* stats) override {
+        TRY(check_query_args(qv, nq, stride));
+        if (!cm || !cm->comm) return fail(PN_BAD_ARG, "comm is null");
+        if (cm->device != device) return fail(PN_BAD_ARG, "the communicator rank and the tree live on different devices");
+        if (k > 255) return fail(PN_BAD_ARG, "sharded k-NN serves k <= 255");
+        if (exchange > PN_EXCHANGE_SLICE) return fail(PN_BAD_ARG, "bad exchange mode");
+        if (cm->world > 64) return fail(PN_BAD_ARG, "at most 64 ranks");
+        if (stats) *stats = pn_shard_stats{};
+        if (k == 0 || nq == 0) return PN_OK;
+        if (!idx_out || !dist_outv) return fail(PN_BAD_ARG, "output buffer is null");
+        std::lock_guard<std::mutex> lk(mu);
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        if (!st) st = stream;
+        TRY(use_stream(st));
+        TRY(ensure_io());
+        counters = pn_counters{};
+        const A* q = (const A*)qv;
+        A* dist_out = (A*)dist_outv;
+        const int W = cm->world, R = cm->rank;
+        constexpr bool PACKED = sizeof(A) == 4;
+        const size_t chunk = host_chunk(nq), n_chunks = (nq + chunk - 1) / chunk;
+        auto slice = [&](int r, size_t& lo, size_t& hi) { pn_query_slice(nq, r, W, &lo, &hi); };
+        size_t my_lo = 0, my_hi = nq;
+        if (exchange == PN_EXCHANGE_SLICE) slice(R, my_lo, my_hi);
+        for (int b = 0; b < (n_chunks > 1 ? 2 : 1); ++b) {
+            TRY(sh_li[b].ensure(chunk * k * 8));
+            TRY(sh_ld[b].ensure(chunk * k * sizeof(A)));
+            TRY(sh_gat[b].ensure((size_t)W * chunk * k * 8));
+            if (PACKED) TRY(sh_pack[b].ensure(chunk * k * 8)); else TRY(sh_gat_d[b].ensure((size_t)W * chunk * k * sizeof(A)));
+        }
+        TRY(w_counters.ensure(256));
+        while (sh_ev.size() < 6 * n_chunks) { cudaEvent_t e; CU(cudaEventCreate(&e)); sh_ev.push_back(e); }
+        auto EV = [&](size_t c, int i) { return sh_ev[6 * c + i]; };  // 0,1 scan; 2,3 exchange; 4,5 merge
+        cudaStream_t cs = cm->stream;
+        CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
+        CU(cudaEventRecord(ev[0], st));
+        unsigned long long bytes = 0, calls = 0, rows_out = 0;
+        // rows of chunk [c0, c1) owned by rank r (SLICE) / all of them (ALLGATHER)
+        auto owned = [&](int r, size_t c0, size_t c1, size_t& lo, size_t& cnt) {
+            size_t slo = 0, shi = nq;
+            if (exchange == PN_EXCHANGE_SLICE) slice(r, slo, shi);
+            lo = std::max(c0, slo);
+            const size_t hi = std::min(c1, shi);
+            cnt = hi > lo ? hi - lo : 0;
+        };
+        auto merge_chunk = [&](size_t c) -> int {
+            const int b = (int)(c & 1);
+            const size_t c0 = c * chunk, c1 = std::min(nq, c0 + chunk);
+            size_t lo, cnt;
+            owned(R, c0, c1, lo, cnt);
+            CU(cudaStreamWaitEvent(st, EV(c, 3), 0));
+            CU(cudaEventRecord(EV(c, 4), st));
+            if (cnt) {
+                const size_t orow = lo - my_lo;
+                if constexpr (PACKED) {
+                    merge_packed_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(sh_gat[b].as<unsigned long long>(), (uint32_t)W, cnt * k, (uint32_t)cnt,
+                                                                                       (uint32_t)k, idx_out + orow * k, (float*)dist_out + orow * k);
+                } else {
+                    merge_lists_kernel<A, uint64_t><<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(sh_gat_d[b].as<A>(), sh_gat[b].as<uint64_t>(), (uint32_t)W,
+                                                                                                  (uint32_t)cnt, (uint32_t)k, idx_out + orow * k,
+                                                                                                  dist_out + orow * k, (uint32_t)k, 0, nullptr, nullptr);
+                }
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+                rows_out += cnt;
+            }
+            CU(cudaEventRecord(EV(c, 5), st));
+            return PN_OK;
+        };
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const int b = (int)(c & 1);
+            const size_t c0 = c * chunk, c1 = std::min(nq, c0 + chunk);
+            const uint32_t cq = (uint32_t)(c1 - c0);
+            // scan: the local lists of chunk c (the buffers of chunk c-2 have been sent: the exchange of c-2 is awaited)
+            if (c >= 2) CU(cudaStreamWaitEvent(st, EV(c - 2, 3), 0));
+            CU(cudaEventRecord(EV(c, 0), st));
+            TRY(knn_device(q + c0 * stride, cq, stride, (uint32_t)k, sh_li[b].as<uint64_t>(), sh_ld[b].as<A>(), st));
+            if constexpr (PACKED) {
+                const size_t cnt = (size_t)cq * k;
+                pack_lists_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(sh_li[b].as<uint64_t>(), (const float*)sh_ld[b].p, cnt,
+                                                                                 sh_pack[b].as<unsigned long long>());
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+            }
+            CU(cudaEventRecord(EV(c, 1), st));
+            // exchange on the communicator's stream: runs under the scan of chunk c+1 (the gather buffer of chunk c-2 must
+            // have been merged)
+            CU(cudaStreamWaitEvent(cs, EV(c, 1), 0));
+            if (c >= 2) CU(cudaStreamWaitEvent(cs, EV(c - 2, 5), 0));
+            CU(cudaEventRecord(EV(c, 2), cs));
+            if (exchange == PN_EXCHANGE_ALLGATHER) {
+                if constexpr (PACKED) {
+                    NC(cm->api->AllGather(sh_pack[b].p, sh_gat[b].p, (size_t)cq * k, ncclUint64, cm->comm, cs));
+                    bytes += (unsigned long long)(W - 1) * cq * k * 8; ++calls;
+                } else {
+                    NC(cm->api->GroupStart());
+                    NC(cm->api->AllGather(sh_li[b].p, sh_gat[b].p, (size_t)cq * k, ncclUint64, cm->comm, cs));
+                    NC(cm->api->AllGather(sh_ld[b].p, sh_gat_d[b].p, (size_t)cq * k, ncclFloat64, cm->comm, cs));
+                    NC(cm->api->GroupEnd());
+                    bytes += (unsigned long long)(W - 1) * cq * k * 16; calls += 2;
+                }
+            } else {
+                size_t mlo, mcnt;
+                owned(R, c0, c1, mlo, mcnt);
+                NC(cm->api->GroupStart());
+                for (int p = 0; p < W; ++p) {
+                    size_t plo, pcnt;
+                    owned(p, c0, c1, plo, pcnt);
+                    if (pcnt) {  // rows of this chunk that rank p merges: my lists for them go to p
+                        const size_t off = (plo - c0) * k;
+                        if constexpr (PACKED) {
+                            NC(cm->api->Send(sh_pack[b].as<unsigned long long>() + off, pcnt * k, ncclUint64, p, cm->comm, cs));
+                        } else {
+                            NC(cm->api->Send(sh_li[b].as<uint64_t>() + off, pcnt * k, ncclUint64, p, cm->comm, cs));
+                            NC(cm->api->Send(sh_ld[b].as<A>() + off, pcnt * k, ncclFloat64, p, cm->comm, cs));
+                        }
+                        if (p != R) bytes += (unsigned long long)pcnt * k * (PACKED ? 8 : 16);
+                        calls += PACKED ? 1 : 2;
+                    }
+                    if (mcnt) {  // and every rank's lists for my rows arrive here, list p at [p][mcnt][k]
+                        if constexpr (PACKED) {
+                            NC(cm->api->Recv(sh_gat[b].as<unsigned long long>() + (size_t)p * mcnt * k, mcnt * k, ncclUint64, p, cm->comm, cs));
+                        } else {
+                            NC(cm->api->Recv(sh_gat[b].as<uint64_t>() + (size_t)p * mcnt * k, mcnt * k, ncclUint64, p, cm->comm, cs));
+                            NC(cm->api->Recv(sh_gat_d[b].as<A>() + (size_t)p * mcnt * k, mcnt * k, ncclFloat64, p, cm->comm, cs));
+                        }
+                    }
+                }
+                NC(cm->api->GroupEnd());
+            }
+            CU(cudaEventRecord(EV(c, 3), cs));
+            if (c >= 1) TRY(merge_chunk(c - 1));   // after the scan of chunk c is queued, so the exchange of c-1 had time to run
+        }
+        TRY(merge_chunk(n_chunks - 1));
+        CU(cudaEventRecord(ev[1], st));
+        CU(cudaStreamSynchronize(st));
+        cm->bytes_sent += bytes; cm->collectives += calls;
+        if (stats) {
+            float ms = 0.f;
+            for (size_t c = 0; c < n_chunks; ++c) {
+                if (cudaEventElapsedTime(&ms, EV(c, 0), EV(c, 1)) == cudaSuccess) stats->scan_ms += ms;
+                if (cudaEventElapsedTime(&ms, EV(c, 2), EV(c, 3)) == cudaSuccess) stats->exchange_ms += ms;
+                if (cudaEventElapsedTime(&ms, EV(c, 4), EV(c, 5)) == cudaSuccess) stats->merge_ms += ms;
+            }
+            if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stats->total_ms = ms;
+            (void)cudaGetLastError();
+            stats->nccl_bytes_sent = bytes; stats->nccl_calls = calls; stats->rows_out = rows_out; stats->n_chunks = (uint32_t)n_chunks;
+        }
+        return fetch_counters(st, nq);
+    }
+
+    // ---- replication of the flattened tree over NCCL (query sharding: build once, broadcast) ------------------------------
+    struct ReplicaHeader {
+        uint64_t n, n_total;
+        uint32_t d, dpad, L, n_internal, n_buckets, n_nodes, bucket_max, kp;
+        int32_t kind;
+        uint32_t algo, tensor_ready, pad;
+        float pmax, tscale;
+    };
+    std::vector<std::pair<DevBuf*, size_t>> replica_arrays() {
+        std::vector<std::pair<DevBuf*, size_t>> v = {
+            {&d_pts, (size_t)ft.n * ft.dpad * sizeof(A)}, {&d_ids, (size_t)ft.n * 4}, {&d_blo, (size_t)ft.n_buckets * 4}, {&d_bhi, (size_t)ft.n_buckets * 4},
+            {&d_centers, (size_t)std::max<uint32_t>(ft.n_nodes, 1) * ft.dpad * sizeof(A)}, {&d_radii, (size_t)std::max<uint32_t>(ft.n_nodes, 1) * sizeof(A)},
+            {&d_vpids, ft.kind == 1 ? (size_t)std::max<uint32_t>(ft.n_nodes, 1) * 4 : 16}};
+        if (tensor_ready) {
+            v.push_back({&d_center, (size_t)ft.dpad * 4});
+            v.push_back({&d_baug, (ft.n + tc::BN - 1) / tc::BN * tc::BN * (size_t)kp * 2});
+        }
+        return v;
+    }
+    int replicate_send(pn_comm* cm, int root) override {
+        if (host_only) return fail(PN_BAD_ARG, "a host-only tree has nothing to replicate");
+        if (cm->device != device) return fail(PN_BAD_ARG, "the communicator rank and the tree live on different devices");
+        std::lock_guard<std::mutex> lk(mu);
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        ReplicaHeader h{ft.n, ft.n_total, ft.d, ft.dpad, ft.L, ft.n_internal, ft.n_buckets, ft.n_nodes, ft.bucket_max, kp, ft.kind, algo,
+                        tensor_ready ? 1u : 0u, 0u, pmax, tscale};
+        DevBuf hb;
+        TRY(hb.ensure(sizeof(h)));
+        CU(cudaMemcpyAsync(hb.p, &h, sizeof(h), cudaMemcpyHostToDevice, cm->stream));
+        NC(cm->api->Broadcast(hb.p, hb.p, sizeof(h), ncclUint8, root, cm->comm, cm->stream));
+        for (auto& a : replica_arrays()) NC(cm->api->Broadcast(a.first->p, a.first->p, a.second, ncclUint8, root, cm->comm, cm->stream));
+        CU(cudaStreamSynchronize(cm->stream));
+        hb.release();
+        return PN_OK;
+    }
+    int replicate_recv(pn_comm* cm, int root) {
+        device = cm->device;
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        TRY(open_device());
+        ReplicaHeader h{};
+        DevBuf hb;
+        TRY(hb.ensure(sizeof(h)));
+        NC(cm->api->Broadcast(hb.p, hb.p, sizeof(h), ncclUint8, root, cm->comm, cm->stream));
+        CU(cudaMemcpyAsync(&h, hb.p, sizeof(h), cudaMemcpyDeviceToHost, cm->stream));
+        CU(cudaStreamSynchronize(cm->stream));
+        hb.release();
+        ft.n = h.n; ft.n_total = h.n_total; ft.d = h.d; ft.dpad = h.dpad; ft.L = h.L; ft.n_internal = h.n_internal; ft.n_buckets = h.n_buckets;
+        ft.n_nodes = h.n_nodes; ft.bucket_max = h.bucket_max; ft.kind = h.kind; kp = h.kp; algo = h.algo; tensor_ready = h.tensor_ready != 0;
+        pmax = h.pmax; tscale = h.tscale;
+        gpu_built = true;  // no host copies: layout() reads the device arrays
+        info.device_bytes = 0;
+        for (auto& a : replica_arrays()) {
+            TRY(a.first->ensure(a.second));
+            NC(cm->api->Broadcast(a.first->p, a.first->p, a.second, ncclUint8, root, cm->comm, cm->stream));
+            info.device_bytes += a.first->cap;
+        }
+        CU(cudaStreamSynchronize(cm->stream));
+        ft.bucket_lo.resize(ft.n_buckets); ft.bucket_hi.resize(ft.n_buckets);
+        CU(cudaMemcpy(ft.bucket_lo.data(), d_blo.p, (size_t)ft.n_buckets * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(ft.bucket_hi.data(), d_bhi.p, (size_t)ft.n_buckets * 4, cudaMemcpyDeviceToHost));
+        if (ft.kind == 1) {
+            ft.vp_ids.resize(std::max<uint32_t>(ft.n_nodes, 1));
+            CU(cudaMemcpy(ft.vp_ids.data(), d_vpids.p, ft.vp_ids.size() * 4, cudaMemcpyDeviceToHost));
+        }
+        fill_dev_tree();
+        TRY(w_counters.ensure(256));
+        return PN_OK;
+    }
+#undef NC
+
     int layout(uint32_t* ids, uint32_t* blo, uint32_t* bhi, void* rad, void* cen, void* pts) override {
         if (gpu_built) {
             DeviceGuard g(device);
@@ -1249,6 +1488,134 @@ int32_t pn_merge_topk_dev(uint32_t dtype, int32_t device, const uint64_t* il, co
     if (dtype == PN_F32) return merge_topk_dev<float>(device, il, (const float*)dl, n_lists, nq, k, io, (float*)dd, (cudaStream_t)stream, sync != 0);
     if (dtype == PN_F64) return merge_topk_dev<double>(device, il, (const double*)dl, n_lists, nq, k, io, (double*)dd, (cudaStream_t)stream, sync != 0);
     return fail(PN_BAD_ARG, "bad dtype");
+    GUARD_END
+}
+
+// ---- multi-GPU: communicator ranks, sharded k-NN, replication ---------------------------------------------------------
+void pn_query_slice(size_t nq, int32_t rank, int32_t world, size_t* lo, size_t* hi) {
+    if (world < 1) world = 1;
+    const size_t base = nq / (size_t)world, rem = nq % (size_t)world, r = (size_t)std::max(rank, 0);
+    const size_t l = r * base + std::min(r, rem);
+    if (lo) *lo = l;
+    if (hi) *hi = l + base + (r < rem ? 1 : 0);
+}
+int32_t pn_comm_unique_id(void* id_out) {
+    GUARD_BEGIN
+    if (!id_out) return fail(PN_BAD_ARG, "id_out is null");
+    std::string err;
+    NcclApi* api = NcclApi::get(&err);
+    if (!api) return fail(PN_NCCL, err);
+    static_assert(sizeof(ncclUniqueId) == PN_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(PN_NCCL, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+    memcpy(id_out, &id, sizeof(id));
+    return PN_OK;
+    GUARD_END
+}
+static int finish_comm(pn_comm* c) {
+    DeviceGuard g(c->device);
+    if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    return PN_OK;
+}
+int32_t pn_comm_create(const void* unique_id, int32_t world, int32_t rank, int32_t device, pn_comm** out) {
+    GUARD_BEGIN
+    if (!out) return fail(PN_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (!unique_id || world < 1 || rank < 0 || rank >= world) return fail(PN_BAD_ARG, "bad unique id / world / rank");
+    std::string err;
+    NcclApi* api = NcclApi::get(&err);
+    if (!api) return fail(PN_NCCL, err);
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) { (void)cudaGetLastError(); return fail(PN_CUDA, "no CUDA device available"); }
+    std::unique_ptr<pn_comm> c(new pn_comm());
+    c->api = api; c->world = world; c->rank = rank; c->device = device;
+    {
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        ncclUniqueId id;
+        memcpy(&id, unique_id, sizeof(id));
+        ncclResult_t r = api->CommInitRank(&c->comm, world, id, rank);
+        if (r != ncclSuccess) return fail(PN_NCCL, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
+    }
+    TRY(finish_comm(c.get()));
+    *out = c.release();
+    return PN_OK;
+    GUARD_END
+}
+int32_t pn_comm_create_all(const int32_t* devices, int32_t n_dev, pn_comm** out) {
+    GUARD_BEGIN
+    if (!out || !devices || n_dev < 1 || n_dev > 64) return fail(PN_BAD_ARG, "bad device list");
+    std::string err;
+    NcclApi* api = NcclApi::get(&err);
+    if (!api) return fail(PN_NCCL, err);
+    std::vector<ncclComm_t> comms(n_dev);
+    std::vector<int> devs(devices, devices + n_dev);
+    ncclResult_t r = api->CommInitAll(comms.data(), n_dev, devs.data());
+    if (r != ncclSuccess) return fail(PN_NCCL, std::string("ncclCommInitAll: ") + api->GetErrorString(r));
+    for (int i = 0; i < n_dev; ++i) {
+        pn_comm* c = new pn_comm();
+        c->api = api; c->comm = comms[i]; c->world = n_dev; c->rank = i; c->device = devs[i];
+        out[i] = c;
+        TRY(finish_comm(c));
+    }
+    return PN_OK;
+    GUARD_END
+}
+int32_t pn_comm_destroy(pn_comm* c) {
+    GUARD_BEGIN
+    if (!c) return PN_OK;
+    DeviceGuard g(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->comm) c->api->CommDestroy(c->comm);
+    delete c;
+    return PN_OK;
+    GUARD_END
+}
+int32_t pn_sharded_query_knn_dev(pn_tree* t, pn_comm* comm, const void* q, size_t nq, size_t qs, size_t k, uint32_t exchange, uint64_t* io,
+                                 void* dd, void* stream, pn_shard_stats* stats) {
+    GUARD_BEGIN
+    if (!t) return fail(PN_BAD_ARG, "tree is null");
+    if (t->info.kind != PN_KIND_BALL) return fail(PN_BAD_ARG, "point sharding by subtree is a ball-tree feature");
+    return t->knn_sharded(comm, q, nq, qs, k, exchange, io, dd, (cudaStream_t)stream, stats);
+    GUARD_END
+}
+int32_t pn_tree_replicate(pn_tree* t, pn_comm* cm, int32_t root, pn_tree** out) {
+    GUARD_BEGIN
+    if (!cm || !out) return fail(PN_BAD_ARG, "null pointer");
+    if (root < 0 || root >= cm->world) return fail(PN_BAD_ARG, "bad root");
+    *out = nullptr;
+    const bool is_root = cm->rank == root;
+    if (is_root && !t) return fail(PN_BAD_ARG, "the root rank needs a tree");
+    DeviceGuard g(cm->device);
+    if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+    // element type and kind first: the receivers need them to make their handle
+    int32_t meta[2] = {is_root ? (int32_t)t->info.dtype : 0, is_root ? (int32_t)t->info.kind : 0};
+    DevBuf mb;
+    TRY(mb.ensure(sizeof(meta)));
+    CU(cudaMemcpyAsync(mb.p, meta, sizeof(meta), cudaMemcpyHostToDevice, cm->stream));
+    ncclResult_t r = cm->api->Broadcast(mb.p, mb.p, sizeof(meta), ncclUint8, root, cm->comm, cm->stream);
+    if (r != ncclSuccess) { mb.release(); return fail(PN_NCCL, std::string("ncclBroadcast: ") + cm->api->GetErrorString(r)); }
+    CU(cudaMemcpyAsync(meta, mb.p, sizeof(meta), cudaMemcpyDeviceToHost, cm->stream));
+    CU(cudaStreamSynchronize(cm->stream));
+    mb.release();
+    if (is_root) {
+        TRY(t->replicate_send(cm, root));
+        *out = t;
+        return PN_OK;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    pn_build_opts o{};
+    if (meta[0] == PN_F32) {
+        std::unique_ptr<Engine<float>> e(new Engine<float>());
+        TRY(e->replicate_recv(cm, root));
+        o.algo = e->algo;
+        return finish_create<float>(meta[1], e, o, t0, out);
+    }
+    std::unique_ptr<Engine<double>> e(new Engine<double>());
+    TRY(e->replicate_recv(cm, root));
+    o.algo = e->algo;
+    return finish_create<double>(meta[1], e, o, t0, out);
     GUARD_END
 }
 

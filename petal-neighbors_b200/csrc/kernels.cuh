@@ -531,6 +531,38 @@ __global__ void pad_rows_kernel(uint64_t* __restrict__ out_i, A* __restrict__ ou
     out_d[at] = pos_inf<A>();
 }
 
+// ---- exchange format of the sharded k-NN (f32): one 64-bit key per entry, (distance bits << 32) | index.  Distances
+// are non-negative, so unsigned order of the keys is the (distance, index) order; an empty slot (+inf, NO_ID) is the
+// largest key.  8 bytes per entry cross NVLink instead of 12. ----------------------------------------------------------
+__global__ void pack_lists_kernel(const uint64_t* __restrict__ idx, const float* __restrict__ dist, size_t count,
+                                  unsigned long long* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t id = idx[i];
+    out[i] = ((unsigned long long)__float_as_uint(dist[i]) << 32) | (id == ~0ull ? (unsigned long long)NO_ID : (id & 0xffffffffull));
+}
+// k-way merge of n_lists sorted packed lists per query (K7 of SURVEY.md 2 after the exchange); lists[l * list_stride + q * k + i]
+__global__ void merge_packed_kernel(const unsigned long long* __restrict__ lists, uint32_t n_lists, size_t list_stride, uint32_t nq,
+                                    uint32_t k, uint64_t* __restrict__ out_i, float* __restrict__ out_d) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint8_t head[64];
+    for (uint32_t l = 0; l < n_lists; ++l) head[l] = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        unsigned long long best = ~0ull;
+        int bl = -1;
+        for (uint32_t l = 0; l < n_lists; ++l) {
+            if (head[l] >= k) continue;
+            const unsigned long long key = lists[(size_t)l * list_stride + (size_t)q * k + head[l]];
+            if (bl < 0 || key < best) { best = key; bl = (int)l; }
+        }
+        if (bl >= 0) ++head[bl];
+        const uint32_t id = (uint32_t)best;
+        out_d[(size_t)q * k + i] = __uint_as_float((uint32_t)(best >> 32));
+        out_i[(size_t)q * k + i] = (bl < 0 || id == NO_ID) ? ~0ull : (uint64_t)id;
+    }
+}
+
 // ---- query staging ----------------------------------------------------------------------------
 template <typename A>
 __global__ void pad_queries_kernel(const A* __restrict__ q, size_t q_stride, uint32_t nq, uint32_t d, uint32_t dpad,
