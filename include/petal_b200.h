@@ -64,6 +64,11 @@ typedef enum pn_algo {
  * the default for small trees and the checker of the device builder) */
 typedef enum pn_builder { PN_BUILDER_AUTO = 0, PN_BUILDER_HOST = 1, PN_BUILDER_DEVICE = 2 } pn_builder;
 
+/* Pruning of (query group, point tile) pairs on the tensor path (k <= 16): AUTO turns it on when a build-time estimate
+ * says at least a quarter of those pairs are out of reach (clustered data); uniform data in d >= 16 prunes nothing and
+ * skips the set-up passes.  Results are identical either way. */
+typedef enum pn_prune { PN_PRUNE_AUTO = 0, PN_PRUNE_ON = 1, PN_PRUNE_OFF = 2 } pn_prune;
+
 #define PN_FLAG_HOST_ONLY 1u /* build + flatten on the host only (no device; queries fail with
                                 PN_CUDA).  For builder tests on machines without a GPU. */
 
@@ -81,7 +86,8 @@ typedef struct pn_build_opts {
     uint32_t shard_depth;
     uint32_t shard_index;
     uint32_t builder;     /* pn_builder: where the partition is computed (ball trees; VP trees are host-built) */
-    uint32_t reserved[7];
+    uint32_t prune;       /* pn_prune: triangle-inequality pruning in front of the tensor filter */
+    uint32_t reserved[6];
 } pn_build_opts;
 
 typedef struct pn_tree pn_tree; /* opaque: flattened, device-resident tree */

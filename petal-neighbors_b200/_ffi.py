@@ -14,6 +14,7 @@ PN_F32, PN_F64 = 0, 1
 PN_ALGO_AUTO, PN_ALGO_SIMT, PN_ALGO_TENSOR = 0, 1, 2
 PN_FLAG_HOST_ONLY = 1
 PN_BUILDER_AUTO, PN_BUILDER_HOST, PN_BUILDER_DEVICE = 0, 1, 2
+PN_PRUNE_AUTO, PN_PRUNE_ON, PN_PRUNE_OFF = 0, 1, 2
 
 # every symbol include/petal_b200.h declares
 EXPORTS = [
@@ -45,7 +46,7 @@ class BuildOpts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("bucket_size", C.c_uint32),
                 ("algo", C.c_uint32), ("host_threads", C.c_uint32), ("flags", C.c_uint32),
                 ("shard_depth", C.c_uint32), ("shard_index", C.c_uint32), ("builder", C.c_uint32),
-                ("reserved", C.c_uint32 * 7)]
+                ("prune", C.c_uint32), ("reserved", C.c_uint32 * 6)]
 
 
 class TreeInfo(C.Structure):

@@ -121,6 +121,11 @@ struct Engine final : pn_tree {
     // tensor path (f32 input only): augmented FP16 operands, see tc_filter.cuh
     DevBuf d_baug, d_center, w_aaug, w_qmargin, w_trace, w_gbound;
     bool tensor_ready = false, last_used_tensor = false;
+    // pruned tensor scan (tc_prune.cuh): tile balls, the build-time estimate of what pruning can do, per-call workspaces
+    DevBuf d_tcen, d_trad, w_qs, w_seed, w_bits, w_tcnt;
+    double prune_frac = 0.0;      // estimated fraction of (query group, tile) pairs that are out of reach
+    bool prune_on = false, last_pruned = false;
+    uint32_t prune_opt = 0;       // pn_prune
     bool gpu_built = false;  // the tree arrays were produced on the device (gpu_build.cu); host copies are fetched on demand
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
     float pmax = 0.f;      // max |s (p - center)|
@@ -132,7 +137,8 @@ struct Engine final : pn_tree {
             DeviceGuard g(device);
             for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &w_qraw, &w_q, &w_home,
                               &w_hist, &w_cursor, &w_order, &w_part_d, &w_part_i, &w_floor_d, &w_floor_i, &w_counters,
-                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin, &w_trace, &w_gbound})
+                              &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin, &w_trace, &w_gbound,
+                              &d_tcen, &d_trad, &w_qs, &w_seed, &w_bits, &w_tcnt})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             for (int i = 0; i < 2; ++i) {
@@ -357,6 +363,23 @@ struct Engine final : pn_tree {
             memcpy(&pmax, &bits, 4);
             info.device_bytes += d_baug.cap;
             tensor_ready = true;
+            // tile balls for the pruned scan, and the estimate that decides whether pruning is worth its set-up passes
+            const uint32_t n_tiles = (uint32_t)((ft.n + tc::BN - 1) / tc::BN);
+            TRY(d_tcen.ensure((size_t)n_tiles * ft.dpad * 4));
+            TRY(d_trad.ensure((size_t)n_tiles * 4));
+            tc::tile_balls_kernel<<<n_tiles, 128, ft.dpad * 4, stream>>>(d_pts.as<float>(), (uint32_t)ft.n, ft.d, ft.dpad, d_tcen.as<float>(), d_trad.as<float>());
+            CU(cudaGetLastError());
+            CU(cudaMemsetAsync(w_counters.p, 0, 256, stream));
+            const uint32_t n_samples = std::min<uint32_t>(64u, n_tiles);
+            tc::prune_estimate_kernel<<<n_samples, 256, 0, stream>>>(d_tcen.as<float>(), d_trad.as<float>(), n_tiles, ft.dpad, n_samples,
+                                                                     w_counters.as<unsigned long long>());
+            CU(cudaGetLastError());
+            unsigned long long est[2] = {0, 0};
+            CU(cudaMemcpyAsync(est, w_counters.p, 16, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            prune_frac = est[1] ? (double)est[0] / (double)est[1] : 0.0;
+            prune_on = ft.n_buckets > 1 && n_tiles > 4 && (prune_opt == PN_PRUNE_ON || (prune_opt == PN_PRUNE_AUTO && prune_frac >= 0.25));
+            info.device_bytes += d_tcen.cap + d_trad.cap;
         }
         return PN_OK;
     }
@@ -367,15 +390,16 @@ struct Engine final : pn_tree {
     }
     template <int DVR, int K, int MT, int NACC, int SW = tc::BN>
     int launch_filter_t(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
-        return fa.g_bound ? launch_filter_s<DVR, K, MT, NACC, true, SW>(map_a, fa, st) : launch_filter_s<DVR, K, MT, NACC, false, SW>(map_a, fa, st);
+        if (fa.tile_bits) return launch_filter_s<DVR, K, MT, NACC, false, SW, true>(map_a, fa, st);
+        return fa.g_bound ? launch_filter_s<DVR, K, MT, NACC, true, SW, false>(map_a, fa, st) : launch_filter_s<DVR, K, MT, NACC, false, SW, false>(map_a, fa, st);
     }
-    template <int DVR, int K, int MT, int NACC, bool SHARED, int SW>
+    template <int DVR, int K, int MT, int NACC, bool SHARED, int SW, bool PRUNE>
     int launch_filter_s(const CUtensorMap& map_a, const tc::FilterArgs& fa, cudaStream_t st) {
         const size_t smem = filter_fixed_smem(MT, fa.k) + (size_t)MT * fa.nkc * tc::A_CHUNK_BYTES + (size_t)fa.stages * fa.gs * tc::CHUNK_BYTES;
-        auto kern = tc::knn_filter_kernel<DVR, K, MT, NACC, SHARED, SW>;
+        auto kern = tc::knn_filter_kernel<DVR, K, MT, NACC, SHARED, SW, PRUNE>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned gx = (fa.nq - fa.row0 + MT * tc::BM - 1) / (MT * tc::BM);
-        const unsigned gy = (fa.n_tiles + fa.tiles_per_split - 1) / fa.tiles_per_split;
+        const unsigned gy = PRUNE ? 1u : (fa.n_tiles + fa.tiles_per_split - 1) / fa.tiles_per_split;
         kern<<<dim3(gx, gy), (5 * MT + 2) * 32, smem, st>>>(map_a, d_baug.as<unsigned char>(), fa);
         CU(cudaGetLastError());
         return PN_OK;
@@ -431,17 +455,97 @@ struct Engine final : pn_tree {
         return launch_filter_t<0, K, 1, 2>(map_a, fa, st);
     }
 
+    // Pruned tensor k-NN (tc_prune.cuh; k <= 16): queries sorted by home bucket, seed bounds from the home bucket, one tile
+    // bitmap per CTA, then ONE launch of the filter over all query groups -- the groups have lists of very different
+    // lengths, so the hardware block scheduler does the load balancing that whole waves do for the dense scan.
+    int knn_device_pruned(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint32_t kstride, uint64_t* idx_out, A* dist_out, cudaStream_t st,
+                          bool self_query) {
+        if constexpr (sizeof(A) == 4) {
+            const bool k1 = (k == 1);
+            const uint32_t KP = k1 ? 1 : 16;
+            const uint32_t n_tiles = (uint32_t)((ft.n + tc::BN - 1) / tc::BN), words = (n_tiles + 31) / 32;
+            const uint32_t QT = 128u * (uint32_t)filter_subtiles(kp / tc::KC), n_qt = (nq + QT - 1) / QT;
+            const float4* qsorted;
+            const uint32_t* order = nullptr;
+            TRY(w_home.ensure((size_t)nq * 4));
+            if (self_query) {
+                // the stored points are their own queries and already sit in bucket order
+                TRY(w_hist.ensure((size_t)ft.n_buckets * 4));
+                home_bucket_kernel<A><<<(nq + 127) / 128, 128, 0, st>>>(dt, d_pts.as<V>(), nq, w_home.as<uint32_t>(), w_hist.as<uint32_t>());
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+                qsorted = d_pts.as<float4>();
+            } else {
+                TRY(stage_queries(qraw, nq, stride, st, true));  // padded rows, home buckets, counting sort -> w_order
+                TRY(w_qs.ensure((size_t)nq * ft.dpad * 4));
+                const size_t tot = (size_t)nq * dt.dv;
+                tc::gather_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w_q.as<float4>(), w_order.as<uint32_t>(), nq, dt.dv, w_qs.as<float4>());
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+                qsorted = w_qs.as<float4>();
+                order = w_order.as<uint32_t>();
+            }
+            TRY(w_seed.ensure((size_t)nq * 4));
+            TRY(w_aaug.ensure((size_t)nq * kp * 2));
+            TRY(w_qmargin.ensure((size_t)nq * 4));
+            TRY(w_bits.ensure((size_t)n_qt * words * 4));
+            TRY(w_tcnt.ensure((size_t)n_qt * 4));
+            TRY(w_part_d.ensure((size_t)nq * KP * 4));
+            TRY(w_part_i.ensure((size_t)nq * KP * 4));
+            const DevTree<float>& dtf = *reinterpret_cast<DevTree<float>*>(&dt);
+            if (k1) tc::seed_bound_kernel<1><<<(nq + 127) / 128, 128, 0, st>>>(dtf, qsorted, order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
+            else tc::seed_bound_kernel<16><<<(nq + 127) / 128, 128, 0, st>>>(dtf, qsorted, order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
+            CU(cudaGetLastError());
+            tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(qsorted), d_center.as<float>(), tscale, nq, ft.d, ft.dpad,
+                                                                    kp, pmax, w_aaug.as<__half>(), w_qmargin.as<float>());
+            CU(cudaGetLastError());
+            tc::tile_bitmap_kernel<<<n_qt, 256, (size_t)(QT / 32) * dt.dv * 16, st>>>(
+                qsorted, w_seed.as<float>(), nq, QT, d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
+                w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>(), w_counters.as<unsigned long long>() + 3);
+            CU(cudaGetLastError());
+            counters.kernel_launches += 3;
+            alignas(64) CUtensorMap map_a;
+            TRY(make_map(&map_a, w_aaug.p, nq, tc::BM));
+            CU(cudaEventRecord(ev[2], st));
+            tc::FilterArgs fa{};
+            fa.t = dtf;
+            fa.q = qsorted; fa.q_margin = w_qmargin.as<float>();
+            fa.k = k; fa.n_tiles = n_tiles; fa.tiles_per_split = n_tiles;
+            fa.nkc = kp / tc::KC;
+            fa.last_steps = ((ft.d + tc::NSLOT - 1) % tc::KC) / 16 + 1;
+            fa.t2_scale = tscale * tscale * (1.0f + (float)(ft.d + 4) * 1.1920928955078125e-07f);
+            fa.part_d = w_part_d.as<float>(); fa.part_i = w_part_i.as<uint32_t>();
+            fa.counters = w_counters.as<unsigned long long>();
+            fa.row0 = 0; fa.nq = nq; fa.g_bound = nullptr;
+            fa.tile_bits = w_bits.as<uint32_t>(); fa.tile_cnt = w_tcnt.as<uint32_t>(); fa.tile_words = words; fa.seed_t2 = w_seed.as<float>();
+            TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
+            // results of sorted slot i belong to query order[i] (self query: to the original row of stored point i)
+            merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, nq, k, idx_out, dist_out, kstride,
+                                                                            0, nullptr, nullptr, self_query ? d_ids.as<uint32_t>() : order);
+            CU(cudaGetLastError());
+            counters.kernel_launches += 2;
+            counters.filter_pairs += (uint64_t)ft.n * nq;  // replaced by the device-side count of scanned pairs in fetch_counters
+            CU(cudaEventRecord(ev[3], st));
+            return PN_OK;
+        } else {
+            (void)qraw; (void)nq; (void)stride; (void)k; (void)kstride; (void)idx_out; (void)dist_out; (void)st; (void)self_query;
+            return fail(PN_BAD_ARG, "the tensor path is f32 only");
+        }
+    }
+
     // tensor k-NN: same contract as knn_device
     int knn_device_tensor(const A* qraw, uint32_t nq, size_t stride, uint32_t k, uint32_t kstride, uint64_t* idx_out, A* dist_out,
                           cudaStream_t st, bool self_query = false) {
         if constexpr (sizeof(A) == 4) {
+            const bool k1 = (k == 1);
+            const uint32_t KP = k1 ? 1 : 16;
+            const uint32_t n_pass = (k + KP - 1) / KP;
+            last_pruned = prune_on && n_pass == 1;
+            if (last_pruned) return knn_device_pruned(qraw, nq, stride, k, kstride, idx_out, dist_out, st, self_query);
             if (!self_query) TRY(stage_queries(qraw, nq, stride, st, false));
             const float* qpad = self_query ? d_pts.as<float>() : w_q.as<float>();
             TRY(w_aaug.ensure((size_t)nq * kp * 2));
             TRY(w_qmargin.ensure((size_t)nq * 4));
-            const bool k1 = (k == 1);
-            const uint32_t KP = k1 ? 1 : 16;
-            const uint32_t n_pass = (k + KP - 1) / KP;
             // Launch plan.  A CTA serves QT = 128 x subtiles queries against the whole point stream, so whole waves of
             // n_sms CTAs keep every SM busy; what is left (fewer query tiles than SMs: the tail of a large batch, or
             // all of a small one) runs as a second launch whose grid.y splits the point stream S ways -- each CTA scans
@@ -483,6 +587,7 @@ struct Engine final : pn_tree {
                 fa.k = kk;
                 fa.n_tiles = n_tiles;
                 fa.nkc = kp / tc::KC;
+                fa.last_steps = ((ft.d + tc::NSLOT - 1) % tc::KC) / 16 + 1;
                 fa.t2_scale = tscale * tscale * (1.0f + (float)(ft.d + 4) * 1.1920928955078125e-07f);
                 fa.part_d = w_part_d.as<float>(); fa.part_i = w_part_i.as<uint32_t>();
                 fa.floor_d = p ? w_floor_d.as<float>() : nullptr; fa.floor_i = p ? w_floor_i.as<uint32_t>() : nullptr;
@@ -636,6 +741,10 @@ struct Engine final : pn_tree {
 #endif
         counters.queries = nq;
         counters.pairs = last_used_tensor ? counters.filter_pairs : c[0];
+        if (last_used_tensor && last_pruned) {  // the pruned scan counts the (query, point) pairs of the tiles it really visits
+            counters.pairs = std::min<uint64_t>(c[3], counters.filter_pairs);
+            counters.filter_pairs = counters.pairs;
+        }
         counters.node_visits = c[1];
         counters.rerank_pairs = c[2];
         float ms = 0.f;
@@ -872,7 +981,7 @@ struct Engine final : pn_tree {
         auto bail = [&](int rc) { cudaDeviceSynchronize(); free(offs); free(hit_buf); return rc; };
 #define CUB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(fail(PN_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_))); } while (0)
 #define TRYB(x) do { int r_ = (x); if (r_ != PN_OK) return bail(r_); } while (0)
-        last_used_tensor = false;
+        last_used_tensor = false; last_pruned = false;
         if (!pin_tot) CUB(cudaHostAlloc((void**)&pin_tot, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
         TRYB(w_counters.ensure(256));
         const size_t spitch = std::max<size_t>(stride, ft.d) * sizeof(A);
@@ -1124,7 +1233,7 @@ struct Engine final : pn_tree {
         uint64_t n, n_total;
         uint32_t d, dpad, L, n_internal, n_buckets, n_nodes, bucket_max, kp;
         int32_t kind;
-        uint32_t algo, tensor_ready, pad;
+        uint32_t algo, tensor_ready, prune_on;
         float pmax, tscale;
     };
     std::vector<std::pair<DevBuf*, size_t>> replica_arrays() {
@@ -1135,6 +1244,9 @@ struct Engine final : pn_tree {
         if (tensor_ready) {
             v.push_back({&d_center, (size_t)ft.dpad * 4});
             v.push_back({&d_baug, (ft.n + tc::BN - 1) / tc::BN * tc::BN * (size_t)kp * 2});
+            const size_t n_tiles = (ft.n + tc::BN - 1) / tc::BN;
+            v.push_back({&d_tcen, n_tiles * ft.dpad * 4});
+            v.push_back({&d_trad, n_tiles * 4});
         }
         return v;
     }
@@ -1145,7 +1257,7 @@ struct Engine final : pn_tree {
         DeviceGuard g(device);
         if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
         ReplicaHeader h{ft.n, ft.n_total, ft.d, ft.dpad, ft.L, ft.n_internal, ft.n_buckets, ft.n_nodes, ft.bucket_max, kp, ft.kind, algo,
-                        tensor_ready ? 1u : 0u, 0u, pmax, tscale};
+                        tensor_ready ? 1u : 0u, prune_on ? 1u : 0u, pmax, tscale};
         DevBuf hb;
         TRY(hb.ensure(sizeof(h)));
         CU(cudaMemcpyAsync(hb.p, &h, sizeof(h), cudaMemcpyHostToDevice, cm->stream));
@@ -1169,7 +1281,7 @@ struct Engine final : pn_tree {
         hb.release();
         ft.n = h.n; ft.n_total = h.n_total; ft.d = h.d; ft.dpad = h.dpad; ft.L = h.L; ft.n_internal = h.n_internal; ft.n_buckets = h.n_buckets;
         ft.n_nodes = h.n_nodes; ft.bucket_max = h.bucket_max; ft.kind = h.kind; kp = h.kp; algo = h.algo; tensor_ready = h.tensor_ready != 0;
-        pmax = h.pmax; tscale = h.tscale;
+        pmax = h.pmax; tscale = h.tscale; prune_on = h.prune_on != 0;
         gpu_built = true;  // no host copies: layout() reads the device arrays
         info.device_bytes = 0;
         for (auto& a : replica_arrays()) {
@@ -1241,6 +1353,7 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
     std::unique_ptr<Engine<A>> e;
     const bool host_only = (o.flags & PN_FLAG_HOST_ONLY) != 0;
     if (o.builder > PN_BUILDER_DEVICE) return fail(PN_BAD_ARG, "bad builder");
+    if (o.prune > PN_PRUNE_OFF) return fail(PN_BAD_ARG, "bad prune option");
     if (o.shard_depth && (kind != PN_KIND_BALL || o.shard_depth > 16 || o.shard_index >= (1u << o.shard_depth)))
         return fail(PN_BAD_ARG, kind != PN_KIND_BALL ? "subtree sharding is a ball-tree option" : "bad shard_depth / shard_index");
     // ball trees with a device are built there from 32768 points up (bit-identical layout, tests/test_gpu_build.py)
@@ -1258,6 +1371,7 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
         e->host_only = host_only;
         e->device = dev;
         e->algo = o.algo;
+        e->prune_opt = o.prune;
         if (on_device) {
             // raw rows to the device (dense n x d), partition and flatten there
             DeviceGuard g(dev);
@@ -1332,6 +1446,7 @@ static int create_tree_dev(const A* points_dev, size_t n, size_t d, size_t row_s
         e.reset(new Engine<A>());
         e->device = dev;
         e->algo = o.algo;
+        e->prune_opt = o.prune;
         TRY(e->build_on_device(points_dev, n, d, row_stride, bucket, o.shard_depth, o.shard_index));
     } catch (const std::bad_alloc&) {
         return fail(PN_OOM, "host allocation failed while building the tree");

@@ -40,6 +40,7 @@
 #include <stdint.h>
 
 #include "kernels.cuh"
+#include "tc_prune.cuh"
 
 namespace petal {
 namespace tc {
@@ -237,6 +238,7 @@ struct FilterArgs {
     uint32_t tiles_per_split;  // grid.y splits the point stream: CTA (x, y) scans tiles [y tps, min(n_tiles, (y+1) tps))
                                // and writes list y; the lists are merged by merge_lists_kernel
     uint32_t nkc;          // K chunks (Kp / 32)
+    uint32_t last_steps;   // K steps of 16 that the last chunk really holds (1 or 2): (d + 6) mod 32 in 1..16 -> 1
     uint32_t stages;       // B ring depth in groups
     uint32_t gs;           // chunks per ring group (one full/empty barrier pair per group)
     float t2_scale;        // s^2 (1 + (d+4) 2^-23): exact squared threshold -> scaled filter units
@@ -246,6 +248,12 @@ struct FilterArgs {
     const float* floor_d;
     const uint32_t* floor_i;
     unsigned long long* counters;  // [2] filter hits (elements passed to the exact rerank)
+    // pruned scan (tc_prune.cuh): CTA x scans only the tiles whose bit is set in its bitmap, and every query starts from
+    // its seed threshold
+    const uint32_t* tile_bits;     // [grid.x][tile_words]
+    const uint32_t* tile_cnt;      // [grid.x] set bits
+    const float* seed_t2;          // [nq] thresh2 of the seed k-th distance (exact squared units)
+    uint32_t tile_words;
 #ifdef PN_TC_PROFILE
     uint32_t dbg;          // diagnostic leg isolation: 1 = epilogue skips the scan, 2 = producer skips the copies
     long long* trace;      // optional timeline of CTA 0, 12 roles x 64 tiles x 4 events
@@ -283,12 +291,14 @@ __global__ void build_baug_kernel(const float* __restrict__ pts, const float* __
         nrm = nrm + v * v;
         baug[baug_offset(i, j, nkc)] = __float2half_rn(-2.0f * v);
     }
-    for (uint32_t j = d; j < kp - NSLOT; ++j) baug[baug_offset(i, j, nkc)] = __float2half_rn(0.f);
+    // the six norm slots follow the data dimensions directly (K = d .. d+5) and the zero padding comes last, so that the
+    // K steps of 16 that hold nothing but padding are never issued (d = 128: 9 MMAs per tile instead of 10)
+    for (uint32_t j = d + NSLOT; j < kp; ++j) baug[baug_offset(i, j, nkc)] = __float2half_rn(0.f);
     __half h1, h2, h3;
     split3_f16(nrm, h1, h2, h3);
     const __half one = __float2half_rn(1.f);
-    baug[baug_offset(i, kp - 6, nkc)] = one; baug[baug_offset(i, kp - 5, nkc)] = one; baug[baug_offset(i, kp - 4, nkc)] = one;
-    baug[baug_offset(i, kp - 3, nkc)] = h1;  baug[baug_offset(i, kp - 2, nkc)] = h2;  baug[baug_offset(i, kp - 1, nkc)] = h3;
+    baug[baug_offset(i, d, nkc)] = one;     baug[baug_offset(i, d + 1, nkc)] = one; baug[baug_offset(i, d + 2, nkc)] = one;
+    baug[baug_offset(i, d + 3, nkc)] = h1;  baug[baug_offset(i, d + 4, nkc)] = h2;  baug[baug_offset(i, d + 5, nkc)] = h3;
     atomicMax(pmax_bits, __float_as_uint(sqrtf(nrm) * 1.000001f));
 }
 
@@ -308,11 +318,11 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
     const float qn = sqrtf(nrm) * 1.000001f;
     const bool in_range = qn <= 200.f;  // every coordinate and the norm stay finite in fp16
     for (uint32_t j = 0; j < d; ++j) o[j] = __float2half_rn(in_range ? (p[j] - center[j]) * scale : 0.f);
-    for (uint32_t j = d; j < kp - NSLOT; ++j) o[j] = __float2half_rn(0.f);
+    for (uint32_t j = d + NSLOT; j < kp; ++j) o[j] = __float2half_rn(0.f);
     __half h1, h2, h3;
     split3_f16(in_range ? nrm : 0.f, h1, h2, h3);
     const __half one = __float2half_rn(1.f);
-    o[kp - 6] = h1; o[kp - 5] = h2; o[kp - 4] = h3; o[kp - 3] = one; o[kp - 2] = one; o[kp - 1] = one;
+    o[d] = h1; o[d + 1] = h2; o[d + 2] = h3; o[d + 3] = one; o[d + 4] = one; o[d + 5] = one;
     const float sn = qn + pmax;
     const float e = 1.01f * 0.001953125f * qn * pmax + 6.2e-05f * sqrtf((float)d) * (qn + 2.f * pmax) +
                     (float)(kp + 8) * 4.76837158203125e-07f * sn * sn;
@@ -327,7 +337,7 @@ __global__ void build_aaug_kernel(const float* __restrict__ q, const float* __re
 // file allows 93 registers per thread, so a stage is read out and tested in two halves of 64 columns.
 // SHARED: the launch splits the point stream (grid.y > 1) and the splits of a query share their k-th bounds; compiled
 // out of the whole-stream launch, where the extra state costs registers the 80-register configuration does not have.
-template <int DVR, int K, int MT, int NUM_ACC, bool SHARED, int SW = BN>
+template <int DVR, int K, int MT, int NUM_ACC, bool SHARED, int SW = BN, bool PRUNE = false>
 __global__ void __launch_bounds__((5 * MT + 2) * 32, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char* __restrict__ baug, const FilterArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -376,8 +386,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
 
     const uint32_t row_base = a.row0 + blockIdx.x * (MT * BM);
     // this CTA's share of the point stream (every split is non-empty: the host guarantees grid.y tps < n_tiles + tps)
-    const uint32_t j_begin = blockIdx.y * a.tiles_per_split;
-    const uint32_t n_my = min(a.n_tiles - j_begin, a.tiles_per_split);
+    // (pruned scan: the set bits of this CTA's tile bitmap instead, walked by every role on its own)
+    static_assert(!(PRUNE && SHARED), "the pruned scan does not split the point stream");
+    const uint32_t j_begin = PRUNE ? 0u : blockIdx.y * a.tiles_per_split;
+    const uint32_t n_my = PRUNE ? a.tile_cnt[blockIdx.x] : min(a.n_tiles - j_begin, a.tiles_per_split);
+    const uint32_t* my_bits = PRUNE ? a.tile_bits + (size_t)blockIdx.x * a.tile_words : nullptr;
 
     if (warp == EPI_WARPS || warp == EPI_WARPS + MT + 1) {
         // ================= TMA producers: two warps, alternate ring groups (stages is even) =================
@@ -395,6 +408,25 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             const uint32_t n_groups = (total + a.gs - 1) / a.gs;
             const unsigned char* bsrc = baug + (size_t)j_begin * a.nkc * CHUNK_BYTES;
             PROF_DECL;
+            if (PRUNE) {
+                // the tiles of the list are not contiguous in the image: one bulk copy per 8 KB chunk, the chunks of a ring
+                // group still complete on the group's one barrier
+                TileIter it;
+                if (n_my) it.init(my_bits);
+                for (uint32_t i = 0, ch = 0; i < n_my; ++i) {
+                    const uint32_t tile = it.next();
+                    for (uint32_t c = 0; c < a.nkc; ++c, ++ch) {
+                        const uint32_t g = ch / a.gs, gi = ch % a.gs;
+                        if ((g & 1u) != pid) continue;
+                        const uint32_t s = g % a.stages, ph = (g / a.stages) & 1u;
+                        if (gi == 0) {
+                            mbar_wait(&empty_bar[s], ph ^ 1u);
+                            mbar_expect_tx(&full_bar[s], min(a.gs, total - ch) * CHUNK_BYTES);
+                        }
+                        bulk_copy(smem_b + (size_t)(s * a.gs + gi) * CHUNK_BYTES, baug + ((size_t)tile * a.nkc + c) * CHUNK_BYTES, CHUNK_BYTES, &full_bar[s]);
+                    }
+                }
+            } else
             for (uint32_t g = pid; g < n_groups; g += 2) {
                 const uint32_t s = g % a.stages, ph = (g / a.stages) & 1u;
                 const uint32_t first = g * a.gs, cnt = min(a.gs, total - first);
@@ -464,12 +496,13 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                         const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
                         const bool last = gi + 1 == a.gs || it + 1 == total;
                         if (elect_one()) {
+                            const bool two = c + 1 < a.nkc || a.last_steps > 1;  // the upper half of the last chunk may be padding only
                             if (TS) {
                                 tc_mma_f16_ts(d_tmem, a_tmem + c * 16, bd, idesc_u, c > 0 ? 1u : 0u);
-                                tc_mma_f16_ts(d_tmem, a_tmem + c * 16 + 8, bd + 2, idesc_u, 1u);
+                                if (two) tc_mma_f16_ts(d_tmem, a_tmem + c * 16 + 8, bd + 2, idesc_u, 1u);
                             } else {
                                 tc_mma_f16(d_tmem, ad, bd, idesc_u, c > 0 ? 1u : 0u);
-                                tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc_u, 1u);
+                                if (two) tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc_u, 1u);
                             }
                             if (last && h == U - 1) tc_commit(&empty_bar[s]);  // group consumed by this subtile
                         }
@@ -505,13 +538,17 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         if (a.floor_d && active) topk.set_floor(a.floor_d[qrow], a.floor_i[qrow]);
         const float margin = active ? a.q_margin[qrow] : 0.f;  // E_q (scaled units)
         const float t2s = a.t2_scale;
-        float theta = active ? pos_inf<float>() : -pos_inf<float>();
+        const float seed2 = PRUNE && active ? a.seed_t2[qrow] : pos_inf<float>();  // an upper bound of the final k-th distance
+        TileIter titer;
+        if (PRUNE && n_my) titer.init(my_bits);
+        float theta = active ? (PRUNE ? xadd(xmul(seed2, t2s), margin) : pos_inf<float>()) : -pos_inf<float>();
         // Theta_q from the best known k-th bound.  When the point stream is split over several CTAs, the k-th distance
         // of ANY split's list is an upper bound of the final k-th distance, so the splits of a query publish theirs
         // (atomicMin on the float bits: the bounds are non-negative) and each filters with the smallest one.
         float* gb = SHARED && active ? a.g_bound + (qrow - a.row0) : nullptr;
         auto refresh_theta = [&](bool publish) {
             float b = topk.t2;
+            if (PRUNE) b = fminf(b, seed2);
             if (SHARED && gb) {
                 if (publish) atomicMin(reinterpret_cast<int*>(gb), __float_as_int(b));
                 b = fminf(b, __ldcg(gb));
@@ -682,7 +719,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
             PROF_DECL;
             for (uint32_t jr = 0; jr < n_my; ++jr) {
-                const uint32_t j = j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
+                const uint32_t j = PRUNE ? titer.next() : j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
                 const uint32_t as = jr % NUM_ACC, aph = (jr / NUM_ACC) & 1u;
                 PROF_ADD(3);
                 mbar_wait(&tfull_bar[as * MT + mt], aph);
@@ -704,7 +741,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 for (int g = 0; g < G; ++g) scan32(r[g], j, g * 32);
                 PROF_ADD(2);
                 // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
-                if ((j & 31u) == 31u) {
+                if (((PRUNE ? jr : j) & 31u) == 31u) {
                     if (qn > 0) { drain(qn); qn = 0; __syncwarp(); }
                     if (SHARED && gb) refresh_theta(false);  // pick up the other splits' progress
                 }
@@ -721,7 +758,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             uint32_t u = 0;
             PROF_DECL;
             for (uint32_t jr = 0; jr < n_my; ++jr) {
-                const uint32_t j = j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
+                const uint32_t j = PRUNE ? titer.next() : j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
 #pragma unroll
                 for (int h = 0; h < U; ++h, ++u) {
                     const uint32_t as = u % NUM_ACC, aph = (u / NUM_ACC) & 1u;
@@ -756,7 +793,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 }
                 if (lane == 0) TRACE(warp, j, 2);
                 // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
-                if ((j & 31u) == 31u) {
+                if (((PRUNE ? jr : j) & 31u) == 31u) {
                     if (qn > 0) { drain(qn); qn = 0; __syncwarp(); }
                     if (SHARED && gb) refresh_theta(false);  // pick up the other splits' progress
                 }
@@ -770,7 +807,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
             PROF_DECL;
             for (uint32_t jr = 0; jr < n_my; ++jr) {
-                const uint32_t j = j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
+                const uint32_t j = PRUNE ? titer.next() : j_begin + jr;  // absolute tile (point rows); stage and phase follow the CTA's own count
                 const uint32_t as = jr % NUM_ACC, aph = (jr / NUM_ACC) & 1u;
                 PROF_ADD(3);
                 mbar_wait(&tfull_bar[as * MT + mt], aph);
@@ -811,7 +848,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
                 PROF_ADD(2);
                 if (lane == 0) TRACE(warp, j, 2);
                 // scheduled drain: every warp of the CTA drains in the same tile, so the stalls coincide
-                if ((j & 31u) == 31u) {
+                if (((PRUNE ? jr : j) & 31u) == 31u) {
                     if (qn > 0) { drain(qn); qn = 0; __syncwarp(); }
                     if (SHARED && gb) refresh_theta(false);  // pick up the other splits' progress
                 }

@@ -23,7 +23,8 @@ pub struct pn_build_opts {
     pub shard_depth: u32,
     pub shard_index: u32,
     pub builder: u32, // pn_builder: 0 auto, 1 host, 2 device
-    pub reserved: [u32; 7],
+    pub prune: u32,   // pn_prune: 0 auto, 1 on, 2 off
+    pub reserved: [u32; 6],
 }
 
 extern "C" {

@@ -38,12 +38,12 @@ def operands(P, Q):
     pmax = np.float32(np.sqrt(np2).max() * np.float32(1.000001))
     B = np.zeros((n, kp), np.float16)
     B[:, :d] = (np.float32(-2.0) * Vp).astype(np.float16)
-    B[:, kp - 6:kp - 3] = np.float16(1)
-    B[:, kp - 3], B[:, kp - 2], B[:, kp - 1] = split3(np2)
+    B[:, d:d + 3] = np.float16(1)               # the six norm slots follow the data dimensions, zero padding last
+    B[:, d + 3], B[:, d + 4], B[:, d + 5] = split3(np2)
     A = np.zeros((len(Q), kp), np.float16)
     A[:, :d] = Vq.astype(np.float16)
-    A[:, kp - 6], A[:, kp - 5], A[:, kp - 4] = split3(nq2)
-    A[:, kp - 3:] = np.float16(1)
+    A[:, d], A[:, d + 1], A[:, d + 2] = split3(nq2)
+    A[:, d + 3:d + 6] = np.float16(1)
     qn = (np.sqrt(nq2) * np.float32(1.000001)).astype(np.float32)
     sn = qn + pmax
     E = (np.float32(1.01 * 0.001953125) * qn * pmax + np.float32(6.2e-05) * np.float32(np.sqrt(d)) * (qn + 2 * pmax)

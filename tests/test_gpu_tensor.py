@@ -26,7 +26,8 @@ def check(pn, oracle, pts, Q, k, expect_tensor=True, **opts):
     assert np.array_equal(bits(dist), bits(od)), "distances are not bit-identical"
     c = bt.counters()
     if pts.shape[1] + 6 <= 384 and expect_tensor:
-        assert c["filter_pairs"] == pts.shape[0] * Q.shape[0] * max(1, -(-k // 16))
+        # every pair, unless the build-time estimate turned pruning on for this data (clusters): then at most every pair
+        assert 0 < c["filter_pairs"] <= pts.shape[0] * Q.shape[0] * max(1, -(-k // 16))
     else:
         assert c["filter_pairs"] == 0
     return bt, c
