@@ -107,14 +107,19 @@ __global__ void seed_bound_kernel(const DevTree<float> t, const float4* __restri
     seed_t2[i] = topk.t2;  // thresh2 of the k-th distance so far; +inf until k points have been seen
 }
 
-// One block per query group (QT = 32 * n_sub sorted queries): balls of the group's 32-query warps, then one bit per
-// point tile.  bits[g * words + w] bit b <-> tile 32 w + b; cnt[g] = tiles to scan; total[0] += pairs the group will see.
+// One block per query group (QT = 32 * n_sub sorted queries): one bit per point tile.  Two levels: (1) the ball of each
+// 32-query warp of the group against the tile ball -- one distance per (warp, tile); (2) only where that ball test cannot
+// exclude the tile, the warp's 32 queries one by one (lane = query), each against its own seed; a tile confirmed by one
+// query is not examined further.  With dense queries (1) decides almost everything; with sparse queries, whose warps span
+// several clusters, (2) keeps the lists short.  bits[g * words + w] bit b <-> tile 32 w + b; cnt[g] = tiles to scan;
+// total[0] += pairs the group will see.
 __global__ void __launch_bounds__(256) tile_bitmap_kernel(const float4* __restrict__ qs, const float* __restrict__ seed_t2, uint32_t nq, uint32_t qt,
                                                           const float* __restrict__ tcen, const float* __restrict__ trad, uint32_t n_tiles,
                                                           uint32_t dv, float slack, uint32_t words, uint32_t* __restrict__ bits,
                                                           uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total) {
     extern __shared__ float4 sm4[];            // [n_sub][dv] warp centres
     __shared__ float s_r[16], s_theta[16];     // warp radius, largest seed (as a distance)
+    __shared__ float s_qtheta[512];            // every query's own seed as a distance (-inf: no such query)
     __shared__ uint32_t s_cnt;
     const uint32_t g = blockIdx.x, n_sub = qt / 32;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -137,16 +142,18 @@ __global__ void __launch_bounds__(256) tile_bitmap_kernel(const float4* __restri
         float acc = 0.f;
         if (act) for (uint32_t j = 0; j < dv; ++j) acc = fold(acc, __ldg(qr + j), sm4[w * dv + j]);
         float r = act ? xsqrt(acc) : 0.f;
-        // largest seed of the warp as a DISTANCE bound: sqrt of the squared-domain threshold, rounded up
-        float th = act ? seed_t2[qi] : 0.f;
-        for (int o = 16; o; o >>= 1) { r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o)); th = fmaxf(th, __shfl_xor_sync(0xffffffffu, th, o)); }
-        if (lane == 0) { s_r[w] = r; s_theta[w] = n_act ? xmul(xsqrt(th), 1.0000002f) : -pos_inf<float>(); }  // no live query: needs nothing
+        // the seed as a DISTANCE bound: sqrt of the squared-domain threshold, rounded up
+        const float th = act ? xmul(xsqrt(seed_t2[qi]), 1.0000002f) : -pos_inf<float>();
+        s_qtheta[w * 32 + lane] = th;
+        float thm = th;
+        for (int o = 16; o; o >>= 1) { r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o)); thm = fmaxf(thm, __shfl_xor_sync(0xffffffffu, thm, o)); }
+        if (lane == 0) { s_r[w] = r; s_theta[w] = thm; }   // a warp without a live query has theta = -inf: it needs nothing
     }
     __syncthreads();
     uint32_t mine = 0;
     for (uint32_t t0 = warp * 32; t0 < words * 32; t0 += n_warps * 32) {
         const uint32_t t = t0 + lane;
-        bool need = false;
+        uint32_t wmask = 0;  // warps of the group whose ball cannot exclude tile t
         if (t < n_tiles) {
             const float4* ct = reinterpret_cast<const float4*>(tcen) + (size_t)t * dv;
             const float rt = trad[t];
@@ -165,12 +172,32 @@ __global__ void __launch_bounds__(256) tile_bitmap_kernel(const float4* __restri
                     const float cd = xsqrt(acc[w]);
                     const float sum = xadd(xadd(cd, s_r[w]), rt);
                     const float lb = xsub(xsub(xsub(cd, s_r[w]), rt), xmul(slack, sum));
-                    need |= !(lb > s_theta[w]);
+                    wmask |= (lb > s_theta[w]) ? 0u : 1u << w;
                 }
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, need);
-        if (lane == 0) { bits[(size_t)g * words + (t0 >> 5)] = m; mine += __popc(m); }
+        // level 2: lane = query of warp w, one candidate tile at a time (warp-uniform loop)
+        unsigned needed = 0;  // lanes (tiles) confirmed
+        for (uint32_t w = 0; w < n_sub; ++w) {
+            unsigned cand = __ballot_sync(0xffffffffu, (wmask >> w) & 1u) & ~needed;
+            if (!cand) continue;
+            const uint32_t qi = g * qt + w * 32 + lane;
+            const float4* qr = qs + (size_t)min(qi, nq - 1) * dv;
+            const float qth = s_qtheta[w * 32 + lane];
+            while (cand) {
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const uint32_t tt = t0 + src;
+                const float4* ct = reinterpret_cast<const float4*>(tcen) + (size_t)tt * dv;
+                const float rt = trad[tt];
+                float acc = 0.f;
+                for (uint32_t j = 0; j < dv; ++j) acc = fold(acc, __ldg(qr + j), __ldg(ct + j));
+                const float cd = xsqrt(acc);
+                const float lb = xsub(xsub(cd, rt), xmul(slack, xadd(cd, rt)));
+                if (__ballot_sync(0xffffffffu, !(lb > qth))) needed |= 1u << src;
+            }
+        }
+        if (lane == 0) { bits[(size_t)g * words + (t0 >> 5)] = needed; mine += __popc(needed); }
     }
     if (lane == 0 && mine) atomicAdd(&s_cnt, mine);
     __syncthreads();

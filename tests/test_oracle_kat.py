@@ -74,10 +74,21 @@ def test_ball_tree_6(oracle):
 
 
 def test_ball_tree_identical_points(oracle):
-    # src/ball_tree.rs:718-740 (asserts the distance only).  The idx permutation equals the
-    # survey model's.  The returned index is 7 by a hand trace of
-    # :184-193 (equal bounds -> child2 first; the second child's Some overrides on equality),
-    # not the 5 SURVEY.md quotes; the reference pins neither.
+    # src/ball_tree.rs:718-740 (the reference asserts the distance only).  The idx permutation equals the survey model's
+    # (SURVEY.md 7 step 1).  The returned index is 7, not the 5 SURVEY.md quotes.  Hand trace of :149-196 for q = [1, 2]:
+    #   n = 8 -> height 4, 15 nodes, leaves 7..14 hold idx[0..8] = [7, 2, 1, 0, 3, 4, 6, 5], one point each; every centroid
+    #   is [1, 1] with radius 0, so every node's lower bound is exactly 1.
+    #   * `lb1 < lb2` is false on equal bounds (:183-187), so at every internal node child2 is searched FIRST:
+    #     root -> node 2 -> node 6 -> leaf 14 = idx[7] = 5 : Some((5, 1)).
+    #   * the sibling is then searched with radius = 1 (:189-191).  `lower_bound > radius` is 1 > 1 = false (:156), the leaf
+    #     returns Some because `min_dist <= radius` is 1 <= 1 (:174), and `.map_or(Some(neighbor), Some)` (:191) maps a Some
+    #     result through `Some`, i.e. the SECOND child's answer replaces the first on equality:
+    #     leaf 13 = idx[6] = 6 replaces 5; node 5 -> (leaf 12 = 4, then leaf 11 = 3) -> 3 replaces 6 at node 2;
+    #     node 1 -> node 4 -> (leaf 10 = 0, then leaf 9 = 1) -> 1; node 3 -> (leaf 8 = 2, then leaf 7 = 7) -> 7 replaces 1;
+    #     at the root 7 replaces 3.
+    #   The last leaf visited wins, and that is leaf 7 = idx[0] = 7.  (5 is what comes out if the first answer is kept on
+    #   equality -- the survey's throwaway model evidently read map_or the other way round.)  The engine itself breaks ties
+    #   by index (0 here), which the north star asks for; the reference pins neither.
     t = oracle.BallTree.euclidean(np.ones((8, 2)))
     assert t.idx.tolist() == [7, 2, 1, 0, 3, 4, 6, 5]
     i, d = t.query_nearest(np.array([1., 2.]))
