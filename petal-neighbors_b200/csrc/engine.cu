@@ -124,8 +124,15 @@ struct Engine final : pn_tree {
     // pruned tensor scan (tc_prune.cuh): tile balls, the build-time estimate of what pruning can do, per-call workspaces
     DevBuf d_tcen, d_trad, w_qs, w_seed, w_bits, w_tcnt;
     double prune_frac = 0.0;      // estimated fraction of (query group, tile) pairs that are out of reach
-    bool prune_on = false, last_pruned = false;
+    double seed_candidates = 0.0; // estimated candidates per query that survive a seed threshold
+    bool prune_on = false, tiles_on = false, last_pruned = false;   // prune_on: sorted + seeded scan; tiles_on: with tile bitmaps
     uint32_t prune_opt = 0;       // pn_prune
+    // Vantage-point trees: the tensor path never used the VP bounds (a dense scan over the stored order), and the VP order
+    // -- shells around vantage points -- gives tiles that no ball can bound tightly.  A VP handle with a device therefore
+    // also keeps the BALL partition of the same points (built on the device) and answers tensor-path queries from it:
+    // exact 1-NN does not depend on the partition; the VP arrays serve the pruned SIMT traversal (PN_ALGO_SIMT), the layout
+    // accessors and trees the tensor path does not take (f64, d < 16).
+    std::unique_ptr<Engine<A>> aux;
     bool gpu_built = false;  // the tree arrays were produced on the device (gpu_build.cu); host copies are fetched on demand
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
     float pmax = 0.f;      // max |s (p - center)|
@@ -304,7 +311,7 @@ struct Engine final : pn_tree {
             if (!tensor_eligible()) return PN_OK;
             kp = (ft.d + tc::NSLOT + tc::KC - 1) / tc::KC * tc::KC;
             // centre = mean of the stored points (double accumulation), then the largest centred coordinate.  Both passes
-            // run over fixed chunks of 64 Ki rows and combine the chunk partials in chunk order, so the result depends
+            // run over fixed chunks of 4096 rows and combine the chunk partials in chunk order, so the result depends
             // neither on the number of host threads nor on where it is computed: on the host for host-built trees (the
             // rows are still there), on the device for device-built ones (gb::centre_and_range_f32, the same sums).
             std::vector<float> c(ft.dpad, 0.f);
@@ -315,7 +322,7 @@ struct Engine final : pn_tree {
                 if (gb::centre_and_range_f32(d_pts.as<float>(), ft.n, ft.d, ft.dpad, d_center.as<float>(), c.data(), &maxabs, stream, err))
                     return fail(PN_CUDA, "tensor path set-up: " + err);
             } else {
-                const size_t CH = 65536, n_ch = (ft.n + CH - 1) / CH;
+                const size_t CH = 4096, n_ch = (ft.n + CH - 1) / CH;
                 const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>({n_ch, 32, std::max(1u, std::thread::hardware_concurrency())}));
                 auto chunks = [&](auto&& body) {  // body(chunk index), chunks dealt round-robin to nt threads
                     std::vector<std::thread> th;
@@ -378,7 +385,36 @@ struct Engine final : pn_tree {
             CU(cudaMemcpyAsync(est, w_counters.p, 16, cudaMemcpyDeviceToHost, stream));
             CU(cudaStreamSynchronize(stream));
             prune_frac = est[1] ? (double)est[0] / (double)est[1] : 0.0;
-            prune_on = ft.n_buckets > 1 && n_tiles > 4 && (prune_opt == PN_PRUNE_ON || (prune_opt == PN_PRUNE_AUTO && prune_frac >= 0.25));
+            // ... and whether seeding is: candidates a query still reranks when it starts from its home-bucket seed
+            {
+                const uint32_t S = std::min<uint32_t>(128u, (uint32_t)ft.n), M = (uint32_t)std::min<uint64_t>(16384u, ft.n);
+                std::vector<uint32_t> rows(S), bks(S);
+                for (uint32_t i = 0; i < S; ++i) {
+                    rows[i] = (uint32_t)(((uint64_t)i * ft.n) / S);
+                    // the bucket that stores the row; vantage points sit between buckets and use the next one
+                    const uint32_t b = (uint32_t)(std::upper_bound(ft.bucket_hi.begin(), ft.bucket_hi.end(), rows[i]) - ft.bucket_hi.begin());
+                    bks[i] = std::min(b, ft.n_buckets - 1);
+                }
+                DevBuf sr, sb;
+                TRY(sr.ensure(S * 4)); TRY(sb.ensure(S * 4));
+                CU(cudaMemcpyAsync(sr.p, rows.data(), S * 4, cudaMemcpyHostToDevice, stream));
+                CU(cudaMemcpyAsync(sb.p, bks.data(), S * 4, cudaMemcpyHostToDevice, stream));
+                tc::seed_estimate_kernel<<<S, 256, 0, stream>>>(*reinterpret_cast<DevTree<float>*>(&dt), sr.as<uint32_t>(), sb.as<uint32_t>(), M,
+                                                               w_counters.as<unsigned long long>());
+                cudaError_t ke = cudaGetLastError();
+                unsigned long long se[2] = {0, 0};
+                if (ke == cudaSuccess) ke = cudaMemcpyAsync(se, (char*)w_counters.p + 16, 16, cudaMemcpyDeviceToHost, stream);
+                if (ke == cudaSuccess) ke = cudaStreamSynchronize(stream);
+                sr.release(); sb.release();
+                if (ke != cudaSuccess) return fail(PN_CUDA, std::string("seed estimate: ") + cudaGetErrorString(ke));
+                seed_candidates = se[1] ? (double)se[0] / (double)se[1] * (double)ft.n : (double)ft.n;
+            }
+            // the streaming threshold alone leaves ~k ln(n/k) + 128 candidates per query (k = 10); seeding is worth its sort
+            // and bucket pass when it gets within a small multiple of that
+            const double stream_candidates = 10.0 * std::log(std::max(2.0, (double)ft.n / 10.0)) + 128.0;
+            const bool can = ft.n_buckets > 1 && n_tiles > 4;
+            tiles_on = can && (prune_opt == PN_PRUNE_ON || (prune_opt == PN_PRUNE_AUTO && prune_frac >= 0.25));
+            prune_on = can && (tiles_on || (prune_opt == PN_PRUNE_AUTO && seed_candidates <= 4.0 * stream_candidates));
             info.device_bytes += d_tcen.cap + d_trad.cap;
         }
         return PN_OK;
@@ -499,9 +535,14 @@ struct Engine final : pn_tree {
             tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(qsorted), d_center.as<float>(), tscale, nq, ft.d, ft.dpad,
                                                                     kp, pmax, w_aaug.as<__half>(), w_qmargin.as<float>());
             CU(cudaGetLastError());
-            tc::tile_bitmap_kernel<<<n_qt, 256, (size_t)(QT / 32) * dt.dv * 16, st>>>(
-                qsorted, w_seed.as<float>(), nq, QT, d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
-                w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>(), w_counters.as<unsigned long long>() + 3);
+            if (tiles_on) {
+                tc::tile_bitmap_kernel<<<n_qt, 256, (size_t)(QT / 32) * dt.dv * 16, st>>>(
+                    qsorted, w_seed.as<float>(), nq, QT, d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
+                    w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>(), w_counters.as<unsigned long long>() + 3);
+            } else {  // seeds only: every group scans every tile
+                const size_t tot = (size_t)n_qt * words;
+                tc::fill_bitmap_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n_qt, n_tiles, words, w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>());
+            }
             CU(cudaGetLastError());
             counters.kernel_launches += 3;
             alignas(64) CUtensorMap map_a;
@@ -673,6 +714,10 @@ struct Engine final : pn_tree {
     // order (perfect tile coherence); results are written to the ORIGINAL row of each point
     int knn_device(const A* qraw, uint32_t nq, size_t stride, uint32_t k_req, uint64_t* idx_out, A* dist_out, cudaStream_t st,
                    bool self_query = false) {
+        if (aux && aux->tensor_ready && !self_query) {
+            aux_used = true;
+            return aux->knn_device(qraw, nq, stride, k_req, idx_out, dist_out, st, false);
+        }
         // k > n: only n neighbours exist; scan for those and pad the remaining columns directly
         const uint32_t kstride = k_req, k = (uint32_t)std::min<uint64_t>(k_req, ft.n);
         if (k < kstride) {
@@ -721,7 +766,32 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 
+    // start of an API call: device-side work counters to zero (also those of the auxiliary ball engine of a VP handle)
+    int begin_call(cudaStream_t st) {
+        TRY(w_counters.ensure(256));
+        CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
+        if (aux) {
+            TRY(aux->w_counters.ensure(256));
+            CU(cudaMemsetAsync(aux->w_counters.p, 0, 256, st));
+            aux->counters = pn_counters{};
+        }
+        aux_used = false;
+        return PN_OK;
+    }
+    bool aux_used = false;
+
     int fetch_counters(cudaStream_t st, uint64_t nq) {
+        if (aux_used) {  // the scan ran in the auxiliary ball engine: its counters and scan events are the call's
+            const uint64_t h2d = counters.h2d_bytes, d2h = counters.d2h_bytes, kl = counters.kernel_launches;
+            TRY(aux->fetch_counters(st, nq));
+            float ms = 0.f;
+            const double dev_ms = cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess ? ms : 0.0;
+            (void)cudaGetLastError();
+            counters = aux->counters;
+            counters.h2d_bytes = h2d; counters.d2h_bytes = d2h; counters.kernel_launches += kl; counters.device_ms = dev_ms;
+            last_used_tensor = aux->last_used_tensor; last_pruned = aux->last_pruned;
+            return PN_OK;
+        }
         unsigned long long c[4] = {0, 0, 0, 0};
         CU(cudaMemcpyAsync(c, w_counters.p, 32, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -741,7 +811,7 @@ struct Engine final : pn_tree {
 #endif
         counters.queries = nq;
         counters.pairs = last_used_tensor ? counters.filter_pairs : c[0];
-        if (last_used_tensor && last_pruned) {  // the pruned scan counts the (query, point) pairs of the tiles it really visits
+        if (last_used_tensor && last_pruned && tiles_on) {  // the pruned scan counts the (query, point) pairs of the tiles it really visits
             counters.pairs = std::min<uint64_t>(c[3], counters.filter_pairs);
             counters.filter_pairs = counters.pairs;
         }
@@ -804,8 +874,7 @@ struct Engine final : pn_tree {
             TRY(w_oi2[b].ensure(chunk * k * 8));
             TRY(w_od2[b].ensure(chunk * k * sizeof(A)));
         }
-        TRY(w_counters.ensure(256));
-        CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
+        TRY(begin_call(st));
         CU(cudaEventRecord(ev[0], st));
         CU(cudaStreamWaitEvent(s_in, ev[0], 0));
         // Enqueue order: H2D(c), kernels(c), then D2H(c-1).  With pageable host memory a D2H copy blocks the host until it
@@ -856,8 +925,7 @@ struct Engine final : pn_tree {
         if (!st) st = stream;
         TRY(use_stream(st));
         counters = pn_counters{};
-        TRY(w_counters.ensure(256));
-        CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
+        TRY(begin_call(st));
         CU(cudaEventRecord(ev[0], st));
         TRY(knn_device((const A*)qv, (uint32_t)nq, stride, (uint32_t)k, idx, (A*)distv, st));
         CU(cudaEventRecord(ev[1], st));
@@ -923,8 +991,7 @@ struct Engine final : pn_tree {
             TRY(w_out_d.ensure((size_t)nq * k * sizeof(A)));
             oi = w_out_i.as<uint64_t>(); od = w_out_d.as<A>();
         }
-        TRY(w_counters.ensure(256));
-        CU(cudaMemsetAsync(w_counters.p, 0, 256, st));
+        TRY(begin_call(st));
         CU(cudaEventRecord(ev[0], st));
         TRY(knn_device(d_pts.as<A>(), nq, ft.dpad, (uint32_t)k, oi, od, st, true));
         if (!dev) {
@@ -1257,7 +1324,7 @@ struct Engine final : pn_tree {
         DeviceGuard g(device);
         if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
         ReplicaHeader h{ft.n, ft.n_total, ft.d, ft.dpad, ft.L, ft.n_internal, ft.n_buckets, ft.n_nodes, ft.bucket_max, kp, ft.kind, algo,
-                        tensor_ready ? 1u : 0u, prune_on ? 1u : 0u, pmax, tscale};
+                        tensor_ready ? 1u : 0u, (prune_on ? 1u : 0u) | (tiles_on ? 2u : 0u), pmax, tscale};
         DevBuf hb;
         TRY(hb.ensure(sizeof(h)));
         CU(cudaMemcpyAsync(hb.p, &h, sizeof(h), cudaMemcpyHostToDevice, cm->stream));
@@ -1281,7 +1348,7 @@ struct Engine final : pn_tree {
         hb.release();
         ft.n = h.n; ft.n_total = h.n_total; ft.d = h.d; ft.dpad = h.dpad; ft.L = h.L; ft.n_internal = h.n_internal; ft.n_buckets = h.n_buckets;
         ft.n_nodes = h.n_nodes; ft.bucket_max = h.bucket_max; ft.kind = h.kind; kp = h.kp; algo = h.algo; tensor_ready = h.tensor_ready != 0;
-        pmax = h.pmax; tscale = h.tscale; prune_on = h.prune_on != 0;
+        pmax = h.pmax; tscale = h.tscale; prune_on = (h.prune_on & 1u) != 0; tiles_on = (h.prune_on & 2u) != 0;
         gpu_built = true;  // no host copies: layout() reads the device arrays
         info.device_bytes = 0;
         for (auto& a : replica_arrays()) {
@@ -1401,6 +1468,21 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
         return fail(PN_OOM, "host allocation failed while building the tree");
     }
     if (!host_only && !on_device) TRY(e->upload());
+    if (kind == PN_KIND_VP && !host_only && e->tensor_ready && n >= 1024) {
+        // the ball partition of the same points for the tensor path (see Engine::aux); a failure here only loses the speed-up
+        std::unique_ptr<Engine<A>> ax(new Engine<A>());
+        ax->device = dev; ax->algo = o.algo; ax->prune_opt = o.prune;
+        DeviceGuard g(dev);
+        DevBuf raw;
+        if (g.ok && raw.ensure(n * d * sizeof(A)) == PN_OK &&
+            cudaMemcpy2D(raw.p, d * sizeof(A), points, std::max(row_stride, d) * sizeof(A), d * sizeof(A), n, cudaMemcpyHostToDevice) == cudaSuccess &&
+            ax->build_on_device(raw.as<A>(), n, d, d, bucket, 0, 0) == PN_OK && ax->tensor_ready) {
+            e->info.device_bytes += ax->info.device_bytes;
+            e->aux = std::move(ax);
+        }
+        (void)cudaGetLastError();
+        raw.release();
+    }
     return finish_create(kind, e, o, t0, out);
 }
 

@@ -543,7 +543,7 @@ template int build_ball_tree<double>(const double*, uint64_t, uint32_t, uint64_t
                                      BallOut<double> (*)(void*, uint64_t, const TreeShape&), void*, cudaStream_t, std::string&);
 
 // ---- centre and range of the stored points for the tensor path --------------------------------------------------------
-constexpr uint32_t CH_ROWS = 65536;
+constexpr uint32_t CH_ROWS = 4096;
 __global__ void chunk_sums_kernel(const float* __restrict__ pts, uint64_t n, uint32_t d, uint32_t dpad, double* __restrict__ part) {
     const uint32_t ch = blockIdx.x;
     const uint64_t lo = (uint64_t)ch * CH_ROWS, hi = min(n, lo + CH_ROWS);

@@ -76,6 +76,59 @@ __global__ void prune_estimate_kernel(const float* __restrict__ centers, const f
     atomicAdd(&out[1], tot);
 }
 
+// Build-time estimate of what SEEDING can do: sample stored points stand in for queries; the seed is the distance of the
+// 11-th nearest point of the own bucket (the sample itself is one of them); counted is the share of a fixed sample of
+// all points that lies within the seed.  share x n = candidates a query would still hand to the exact rerank when it
+// starts from its seed: a few hundred on clustered data, tens of thousands on uniform data in d >= 16 (where the running
+// threshold of the stream is just as good and the set-up passes are not worth it).
+__global__ void __launch_bounds__(256) seed_estimate_kernel(const DevTree<float> t, const uint32_t* __restrict__ sample_row,
+                                                            const uint32_t* __restrict__ sample_bucket, uint32_t m_points,
+                                                            unsigned long long* __restrict__ out /* [2] within, [3] examined */) {
+    __shared__ float sd[1024];
+    __shared__ float s_seed;
+    __shared__ unsigned int s_cnt;
+    const uint32_t row = sample_row[blockIdx.x], b = sample_bucket[blockIdx.x];
+    const uint32_t lo = t.bucket_lo[b], m = min(t.bucket_hi[b] - lo, 1024u);
+    const float4* qr = t.pts + (size_t)row * t.dv;
+    if (threadIdx.x == 0) { s_seed = pos_inf<float>(); s_cnt = 0; }
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const float4* pr = t.pts + (size_t)(lo + i) * t.dv;
+        float acc = 0.f;
+        for (uint32_t j = 0; j < t.dv; ++j) acc = fold(acc, __ldg(qr + j), __ldg(pr + j));
+        sd[i] = acc;
+    }
+    __syncthreads();
+    // the squared distance of rank 10 (0-based) among the bucket's points: the smallest value with at least 10 smaller ones
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < m; ++j) rank += sd[j] < sd[i] ? 1u : 0u;
+        if (rank >= 10) atomicMin(reinterpret_cast<unsigned int*>(&s_seed), __float_as_uint(sd[i]));
+    }
+    __syncthreads();
+    const float seed = s_seed;  // +inf when the bucket has fewer than 11 points
+    unsigned int c = 0;
+    for (uint32_t i = threadIdx.x; i < m_points; i += blockDim.x) {
+        const uint32_t p = (uint32_t)(((unsigned long long)i * t.n) / m_points);
+        const float4* pr = t.pts + (size_t)p * t.dv;
+        float acc = 0.f;
+        for (uint32_t j = 0; j < t.dv; ++j) acc = fold(acc, __ldg(qr + j), __ldg(pr + j));
+        c += acc <= seed ? 1u : 0u;
+    }
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) { atomicAdd(&out[2], (unsigned long long)s_cnt); atomicAdd(&out[3], (unsigned long long)m_points); }
+}
+
+// every tile for every group (seeding without tile pruning)
+__global__ void fill_bitmap_kernel(uint32_t n_groups, uint32_t n_tiles, uint32_t words, uint32_t* __restrict__ bits, uint32_t* __restrict__ cnt) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n_groups * words) return;
+    const uint32_t w = (uint32_t)(e % words);
+    const uint32_t rest = n_tiles - w * 32;
+    bits[e] = rest >= 32 ? 0xffffffffu : ((1u << rest) - 1u);
+    if (w == 0) cnt[e / words] = n_tiles;
+}
+
 // sorted query rows: out[i] = q[order[i]] (padded rows), so that CTA x of the filter serves sorted slots [x QT, (x+1) QT)
 __global__ void gather_queries_kernel(const float4* __restrict__ q, const uint32_t* __restrict__ order, uint32_t nq, uint32_t dv,
                                       float4* __restrict__ out) {
@@ -118,7 +171,7 @@ __global__ void __launch_bounds__(256) tile_bitmap_kernel(const float4* __restri
                                                           uint32_t dv, float slack, uint32_t words, uint32_t* __restrict__ bits,
                                                           uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total) {
     extern __shared__ float4 sm4[];            // [n_sub][dv] warp centres
-    __shared__ float s_r[16], s_theta[16];     // warp radius, largest seed (as a distance)
+    __shared__ float s_r[16], s_mu[16];        // warp radius; max over the warp's queries of (seed + distance to the warp centre)
     __shared__ float s_qtheta[512];            // every query's own seed as a distance (-inf: no such query)
     __shared__ uint32_t s_cnt;
     const uint32_t g = blockIdx.x, n_sub = qt / 32;
@@ -145,12 +198,14 @@ __global__ void __launch_bounds__(256) tile_bitmap_kernel(const float4* __restri
         // the seed as a DISTANCE bound: sqrt of the squared-domain threshold, rounded up
         const float th = act ? xmul(xsqrt(seed_t2[qi]), 1.0000002f) : -pos_inf<float>();
         s_qtheta[w * 32 + lane] = th;
-        float thm = th;
-        for (int o = 16; o; o >>= 1) { r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o)); thm = fmaxf(thm, __shfl_xor_sync(0xffffffffu, thm, o)); }
-        if (lane == 0) { s_r[w] = r; s_theta[w] = thm; }   // a warp without a live query has theta = -inf: it needs nothing
+        // |q - p| >= |c_w - c_T| - |q - c_w| - R_T for every point p of tile T, so query q can skip T when
+        // |c_w - c_T| - R_T - slack > seed_q + |q - c_w|; the warp needs T unless that holds for its largest seed_q + |q - c_w|
+        float mu = act ? xmul(xadd(th, r), 1.0000002f) : -pos_inf<float>();
+        for (int o = 16; o; o >>= 1) { r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o)); mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o)); }
+        if (lane == 0) { s_r[w] = r; s_mu[w] = mu; }   // a warp without a live query has mu = -inf: it needs nothing
     }
     __syncthreads();
-    uint32_t mine = 0;
+    uint32_t mine = 0, tried = 0, rejected = 0;
     for (uint32_t t0 = warp * 32; t0 < words * 32; t0 += n_warps * 32) {
         const uint32_t t = t0 + lane;
         uint32_t wmask = 0;  // warps of the group whose ball cannot exclude tile t
@@ -171,16 +226,18 @@ __global__ void __launch_bounds__(256) tile_bitmap_kernel(const float4* __restri
                 if (w < (int)n_sub) {
                     const float cd = xsqrt(acc[w]);
                     const float sum = xadd(xadd(cd, s_r[w]), rt);
-                    const float lb = xsub(xsub(xsub(cd, s_r[w]), rt), xmul(slack, sum));
-                    wmask |= (lb > s_theta[w]) ? 0u : 1u << w;
+                    const float lb = xsub(xsub(cd, rt), xmul(slack, sum));
+                    wmask |= (lb > s_mu[w]) ? 0u : 1u << w;
                 }
             }
         }
-        // level 2: lane = query of warp w, one candidate tile at a time (warp-uniform loop)
+        // level 2: lane = query of warp w, one candidate tile at a time (warp-uniform loop).  It only pays where it rejects
+        // tiles: once 64 refinements of this warp have rejected fewer than a quarter, level 1's verdicts are taken as they are.
         unsigned needed = 0;  // lanes (tiles) confirmed
         for (uint32_t w = 0; w < n_sub; ++w) {
             unsigned cand = __ballot_sync(0xffffffffu, (wmask >> w) & 1u) & ~needed;
             if (!cand) continue;
+            if (tried >= 64 && rejected * 4 < tried) { needed |= cand; continue; }
             const uint32_t qi = g * qt + w * 32 + lane;
             const float4* qr = qs + (size_t)min(qi, nq - 1) * dv;
             const float qth = s_qtheta[w * 32 + lane];
@@ -194,7 +251,8 @@ __global__ void __launch_bounds__(256) tile_bitmap_kernel(const float4* __restri
                 for (uint32_t j = 0; j < dv; ++j) acc = fold(acc, __ldg(qr + j), __ldg(ct + j));
                 const float cd = xsqrt(acc);
                 const float lb = xsub(xsub(cd, rt), xmul(slack, xadd(cd, rt)));
-                if (__ballot_sync(0xffffffffu, !(lb > qth))) needed |= 1u << src;
+                ++tried;
+                if (__ballot_sync(0xffffffffu, !(lb > qth))) needed |= 1u << src; else ++rejected;
             }
         }
         if (lane == 0) { bits[(size_t)g * words + (t0 >> 5)] = needed; mine += __popc(needed); }
