@@ -257,6 +257,23 @@ int32_t pn_sharded_query_knn_dev(pn_tree *tree, pn_comm *comm, const void *queri
  * source and *out = tree; elsewhere `tree` is NULL and *out receives a new handle.  Collective. */
 int32_t pn_tree_replicate(pn_tree *tree, pn_comm *comm, int32_t root, pn_tree **out);
 
+/* --- one process driving several GPUs: the survey's pn_ctx.  A pn_multi owns one rank per device (ncclCommInitAll),
+ * one host thread per rank for every call, and either a replica of the tree on every device (PN_SHARD_REPLICATE: built
+ * once on the first device, sent to the others with ncclBroadcast; a batch of queries is split into contiguous slices,
+ * no data-path collective) or one subtree per device (PN_SHARD_BY_SUBTREE: n_dev a power of two; every device scans all
+ * queries on its shard, lists exchanged slice-wise over NCCL and merged on the owning device).  Host buffers in and out,
+ * same result layout and semantics as pn_balltree_query_*.  This is what a Rust or C++ host calls to use a whole box
+ * through the C ABI. */
+typedef struct pn_multi pn_multi;
+typedef enum pn_shard_mode { PN_SHARD_REPLICATE = 0, PN_SHARD_BY_SUBTREE = 1 } pn_shard_mode;
+int32_t pn_multi_balltree_create_f32(const int32_t *devices, int32_t n_dev, uint32_t shard_mode, const float *points,
+                                     size_t n, size_t d, size_t row_stride, const pn_build_opts *opts, pn_multi **out);
+int32_t pn_multi_balltree_query_f32(pn_multi *m, const float *queries, size_t nq, size_t q_row_stride, size_t k,
+                                    uint64_t *idx_out, float *dist_out);
+/* per-device statistics of the last query: stats[n_dev] (BY_SUBTREE: the exchange; REPLICATE: zeros but rows_out) */
+int32_t pn_multi_get_stats(const pn_multi *m, pn_shard_stats *stats, int32_t n_stats);
+int32_t pn_multi_destroy(pn_multi *m);
+
 /* --- introspection */
 int32_t pn_tree_get_info(const pn_tree *tree, pn_tree_info *info);
 int32_t pn_tree_get_counters(const pn_tree *tree, pn_counters *counters);

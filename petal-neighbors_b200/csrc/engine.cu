@@ -1816,6 +1816,131 @@ int32_t pn_tree_replicate(pn_tree* t, pn_comm* cm, int32_t root, pn_tree** out) 
     GUARD_END
 }
 
+// ---- one process, several GPUs ---------------------------------------------------------------------------------------
+}  // extern "C"
+struct pn_multi {
+    int n_dev = 0;
+    uint32_t mode = PN_SHARD_REPLICATE;
+    size_t d = 0;
+    std::vector<int> devices;
+    std::vector<pn_comm*> comms;
+    std::vector<pn_tree*> trees;
+    std::vector<pn_shard_stats> stats;
+    std::vector<DevBuf> q_dev, idx_dev, dist_dev;  // BY_SUBTREE: all queries / this device's result slice
+    ~pn_multi() {
+        for (size_t i = 0; i < trees.size(); ++i) {
+            if (!trees[i]) continue;
+            bool dup = false;
+            for (size_t j = 0; j < i; ++j) dup |= trees[j] == trees[i];
+            if (!dup) delete trees[i];
+        }
+        for (int r = 0; r < n_dev; ++r) {
+            if (r < (int)devices.size()) {
+                DeviceGuard g(devices[r]);
+                if (r < (int)q_dev.size()) { q_dev[r].release(); idx_dev[r].release(); dist_dev[r].release(); }
+            }
+        }
+        for (pn_comm* c : comms) pn_comm_destroy(c);
+    }
+};
+// fn(rank) on one host thread per rank; the first failure (status + message) is reported in the caller's thread
+template <typename F>
+static int on_every_rank(int n, F fn) {
+    std::vector<int> rc(n, PN_OK);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n; ++r)
+        th.emplace_back([&, r] {
+            try { rc[r] = fn(r); } catch (const std::exception& ex) { rc[r] = fail(PN_BAD_ARG, ex.what()); } catch (...) { rc[r] = fail(PN_BAD_ARG, "unknown error"); }
+            if (rc[r] != PN_OK) msg[r] = g_err;
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n; ++r)
+        if (rc[r] != PN_OK) return fail(rc[r], "device rank " + std::to_string(r) + ": " + msg[r]);
+    return PN_OK;
+}
+extern "C" {
+int32_t pn_multi_balltree_create_f32(const int32_t* devices, int32_t n_dev, uint32_t mode, const float* points, size_t n, size_t d, size_t rs,
+                                     const pn_build_opts* opts_in, pn_multi** out) {
+    GUARD_BEGIN
+    if (!out) return fail(PN_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (!devices || n_dev < 1 || n_dev > 64) return fail(PN_BAD_ARG, "bad device list");
+    if (mode > PN_SHARD_BY_SUBTREE) return fail(PN_BAD_ARG, "bad shard mode");
+    uint32_t depth = 0;
+    while ((1 << depth) < n_dev) ++depth;
+    if (mode == PN_SHARD_BY_SUBTREE && (1 << depth) != n_dev) return fail(PN_BAD_ARG, "sharding by subtree needs a power-of-two number of devices");
+    pn_build_opts o{};
+    if (opts_in) memcpy(&o, opts_in, std::min<size_t>(sizeof(o), opts_in->struct_size ? opts_in->struct_size : sizeof(o)));
+    o.struct_size = sizeof(o);
+    if (o.flags & PN_FLAG_HOST_ONLY) return fail(PN_BAD_ARG, "a multi-GPU tree cannot be host-only");
+    std::unique_ptr<pn_multi> m(new pn_multi());
+    m->n_dev = n_dev; m->mode = mode; m->d = d;
+    m->devices.assign(devices, devices + n_dev);
+    m->comms.assign(n_dev, nullptr);
+    m->trees.assign(n_dev, nullptr);
+    m->stats.assign(n_dev, pn_shard_stats{});
+    m->q_dev.resize(n_dev); m->idx_dev.resize(n_dev); m->dist_dev.resize(n_dev);
+    TRY(pn_comm_create_all(devices, n_dev, m->comms.data()));
+    if (mode == PN_SHARD_REPLICATE) {
+        pn_build_opts o0 = o;
+        o0.device = devices[0]; o0.shard_depth = 0; o0.shard_index = 0;
+        TRY(pn_balltree_create_f32(points, n, d, rs, 1, &o0, &m->trees[0]));
+        TRY(on_every_rank(n_dev, [&](int r) { return (int)pn_tree_replicate(r == 0 ? m->trees[0] : nullptr, m->comms[r], 0, &m->trees[r]); }));
+    } else {
+        TRY(on_every_rank(n_dev, [&](int r) {
+            pn_build_opts orr = o;
+            orr.device = devices[r]; orr.shard_depth = depth; orr.shard_index = (uint32_t)r;
+            return (int)pn_balltree_create_f32(points, n, d, rs, 1, &orr, &m->trees[r]);
+        }));
+    }
+    *out = m.release();
+    return PN_OK;
+    GUARD_END
+}
+int32_t pn_multi_balltree_query_f32(pn_multi* m, const float* q, size_t nq, size_t qs, size_t k, uint64_t* idx_out, float* dist_out) {
+    GUARD_BEGIN
+    if (!m) return fail(PN_BAD_ARG, "handle is null");
+    if (nq == 0 || k == 0) return PN_OK;
+    if (!q || !idx_out || !dist_out) return fail(PN_BAD_ARG, "null pointer");
+    if (nq > 1 && qs < m->d) return fail(PN_BAD_ARG, "q_row_stride < dimension");
+    const int W = m->n_dev;
+    return on_every_rank(W, [&](int r) -> int {
+        size_t lo, hi;
+        pn_query_slice(nq, r, W, &lo, &hi);
+        m->stats[r] = pn_shard_stats{};
+        m->stats[r].rows_out = hi - lo;
+        if (m->mode == PN_SHARD_REPLICATE) {
+            if (hi == lo) return PN_OK;
+            return pn_balltree_query_f32(m->trees[r], q + lo * qs, hi - lo, qs, k, idx_out + lo * k, dist_out + lo * k);
+        }
+        // BY_SUBTREE: all queries on every device, the merged rows of this device's slice come back
+        DeviceGuard g(m->devices[r]);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        const size_t d = m->d, rows = hi - lo;
+        TRY(m->q_dev[r].ensure(nq * d * 4));
+        TRY(m->idx_dev[r].ensure(std::max<size_t>(rows, 1) * k * 8));
+        TRY(m->dist_dev[r].ensure(std::max<size_t>(rows, 1) * k * 4));
+        CU(cudaMemcpy2D(m->q_dev[r].p, d * 4, q, std::max(qs, d) * 4, d * 4, nq, cudaMemcpyHostToDevice));
+        TRY(pn_sharded_query_knn_dev(m->trees[r], m->comms[r], m->q_dev[r].p, nq, d, k, PN_EXCHANGE_SLICE, m->idx_dev[r].as<uint64_t>(),
+                                     m->dist_dev[r].p, nullptr, &m->stats[r]));
+        if (rows) {
+            CU(cudaMemcpy(idx_out + lo * k, m->idx_dev[r].p, rows * k * 8, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(dist_out + lo * k, m->dist_dev[r].p, rows * k * 4, cudaMemcpyDeviceToHost));
+        }
+        return PN_OK;
+    });
+    GUARD_END
+}
+int32_t pn_multi_get_stats(const pn_multi* m, pn_shard_stats* stats, int32_t n_stats) {
+    if (!m || !stats) return fail(PN_BAD_ARG, "null pointer");
+    for (int r = 0; r < std::min<int>(n_stats, m->n_dev); ++r) stats[r] = m->stats[r];
+    return PN_OK;
+}
+int32_t pn_multi_destroy(pn_multi* m) {
+    GUARD_BEGIN delete m; return PN_OK; GUARD_END
+}
+
 int32_t pn_tree_get_info(const pn_tree* t, pn_tree_info* info) {
     if (!t || !info) return fail(PN_BAD_ARG, "null pointer");
     *info = t->info;

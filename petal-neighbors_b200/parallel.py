@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import BallTree, _Tree, _check, _ffi, merge_topk_dev  # noqa: F401
-from ._ffi import PN_EXCHANGE_ALLGATHER, PN_EXCHANGE_SLICE
+from ._ffi import PN_EXCHANGE_ALLGATHER, PN_EXCHANGE_SLICE, PN_SHARD_BY_SUBTREE, PN_SHARD_REPLICATE
 
 
 def query_slice(n_queries: int, rank: int, world: int):
@@ -155,3 +155,48 @@ class ShardedBallTree:
         q_dev = torch.from_numpy(np.ascontiguousarray(Q, dtype=self.dtype)).cuda(self.device)
         oi, od = self.query_batch_dev(q_dev, k)
         return oi.cpu().numpy().astype(np.uint64), od.cpu().numpy()
+
+
+class MultiGpuBallTree:
+    """pn_multi_*: ONE process driving several GPUs through the C ABI -- one rank and one host thread per device inside
+    the library (ncclCommInitAll), tree replicated over ncclBroadcast or sharded by subtree.  Host buffers in and out."""
+
+    def __init__(self, points, devices, mode=PN_SHARD_REPLICATE, **opts):
+        points = np.ascontiguousarray(points, dtype=np.float32)
+        self.dim = points.shape[1]
+        self.devices = list(devices)
+        o = _ffi.BuildOpts()
+        o.struct_size = C.sizeof(_ffi.BuildOpts)
+        o.device = -1
+        for key, val in opts.items():
+            setattr(o, key, val)
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        _check(_ffi.lib().pn_multi_balltree_create_f32(arr, len(self.devices), mode, points.ctypes.data, points.shape[0], self.dim, self.dim,
+                                                      C.byref(o), C.byref(self._h)))
+
+    def query_batch(self, Q, k: int):
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        if Q.ndim != 2 or Q.shape[1] != self.dim:
+            raise ValueError("queries must be nq x d")
+        nq = Q.shape[0]
+        idx = np.empty((nq, k), np.uint64)
+        dist = np.empty((nq, k), np.float32)
+        _check(_ffi.lib().pn_multi_balltree_query_f32(self._h, Q.ctypes.data, nq, self.dim, k, idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
+
+    def stats(self):
+        arr = (_ffi.ShardStats * len(self.devices))()
+        _check(_ffi.lib().pn_multi_get_stats(self._h, arr, len(self.devices)))
+        return [_ffi._struct_dict(x) for x in arr]
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _ffi.lib().pn_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -106,3 +106,26 @@ def test_two_or_more_gpus_in_one_process(pn, oracle):
         assert inf["device"] == r and inf["n_points"] == n
         assert np.array_equal(ri, oi.astype(np.uint64)) and np.array_equal(bits(rd), bits(od))
     [c.close() for c in comms]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_multi_gpu_handle(pn, oracle, mode):
+    """pn_multi_*: the whole box from one process through the C ABI (one GPU here means one rank; the 2+ GPU case runs when
+    the box has them), host buffers in and out, both shard modes."""
+    import torch
+    from petal_neighbors_b200 import parallel, synth
+    ng = torch.cuda.device_count()
+    world = 1 << (min(ng, 8).bit_length() - 1)
+    n, d, nq, k = 120000, 24, 90000, 10
+    pts = synth.fast_gaussian_mixture(n, d, 9, n_centers=128, sigma=0.05)
+    Q = synth.fast_gaussian_mixture(nq, d, 10, n_centers=128, sigma=0.05)
+    m = parallel.MultiGpuBallTree(pts, list(range(world)), mode=mode)
+    idx, dist = m.query_batch(Q, k)
+    sample = np.arange(0, nq, nq // 300)[:300]
+    oi, od = oracle.brute_knn(pts, Q[sample], k)
+    assert np.array_equal(idx[sample], oi.astype(np.uint64)) and np.array_equal(bits(dist[sample]), bits(od))
+    st = m.stats()
+    assert sum(s["rows_out"] for s in st) == nq
+    if mode == 1 and world > 1:
+        assert all(s["nccl_bytes_sent"] > 0 for s in st)
+    m.close()

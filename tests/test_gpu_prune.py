@@ -31,7 +31,7 @@ def check(pn, oracle, tree, pts, Q, k, vp=False):
 
 
 @pytest.mark.parametrize("n,d,nq,k,centers,sigma,strong", [
-    (60000, 64, 3000, 1, 64, 0.05, False), (60000, 64, 3000, 10, 64, 0.05, False), (50000, 16, 5000, 10, 64, 0.004, True),
+    (60000, 64, 3000, 1, 64, 0.05, False), (60000, 64, 3000, 10, 64, 0.05, False), (50000, 16, 20000, 10, 64, 0.004, True),
     (40000, 32, 700, 16, 32, 0.03, False), (30000, 128, 1500, 10, 16, 0.05, False), (20000, 20, 1, 5, 8, 0.02, False),
 ])
 def test_pruned_scan_on_clusters(pn, oracle, n, d, nq, k, centers, sigma, strong):
