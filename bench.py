@@ -456,6 +456,8 @@ def main():
         run_reference_arm(args)
         return
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout; stdout carries the one JSON line
     import torch
     import torch.distributed as dist
     import petal_neighbors_b200 as pn
@@ -616,6 +618,8 @@ def main():
             "config": config_dict(wl, world, nq, k),
             "engine": {"bucket_size_max": info["bucket_size_max"], "tree_levels": info["n_levels"], "algo": args.algo,
                        "tree_build_seconds": info["build_seconds"], "tree_seconds_incl_replication": tree_s,
+                       "seeded_scan": bool(info["prune_seeded"]), "tile_bitmaps": bool(info["prune_tiles"]),
+                       "est_seed_candidates": info["est_seed_candidates"], "est_tile_frac": info["est_tile_frac"],
                        "tree": "built on the device on rank 0" + (", replicated with ncclBroadcast (pn_tree_replicate)" if world > 1 else "")},
             "e2e": {"value": world * nq * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(ctr_host["h2d_bytes"]), "d2h_bytes_per_step": int(ctr_host["d2h_bytes"]),

@@ -103,7 +103,13 @@ typedef struct pn_tree_info {
     int32_t device;
     uint32_t algo;
     uint64_t device_bytes;
-    double build_seconds;  /* host build + flatten + upload */
+    double build_seconds;  /* build + flatten + upload + tensor-path set-up */
+    /* pruning decisions of the tensor path and the build-time estimates behind them (0 when the tensor path is off) */
+    uint32_t prune_seeded;      /* queries are sorted by home bucket and start from a seed threshold */
+    uint32_t prune_tiles;       /* per-CTA tile bitmaps are computed and tiles skipped */
+    double est_seed_candidates; /* candidates a query still reranks when it starts from its seed */
+    double est_tile_frac;       /* share of tile balls beyond a single query's seed */
+    double est_group_tile_frac; /* share of tile balls out of reach of a whole tile of queries */
 } pn_tree_info;
 
 /* Work counters of the most recent query call. */

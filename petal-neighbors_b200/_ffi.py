@@ -56,7 +56,9 @@ class TreeInfo(C.Structure):
                 ("dim_padded", C.c_uint32), ("kind", C.c_uint32), ("dtype", C.c_uint32),
                 ("n_levels", C.c_uint32), ("n_buckets", C.c_uint32), ("n_nodes", C.c_uint32),
                 ("bucket_size_max", C.c_uint32), ("device", C.c_int32), ("algo", C.c_uint32),
-                ("device_bytes", C.c_uint64), ("build_seconds", C.c_double)]
+                ("device_bytes", C.c_uint64), ("build_seconds", C.c_double),
+                ("prune_seeded", C.c_uint32), ("prune_tiles", C.c_uint32), ("est_seed_candidates", C.c_double),
+                ("est_tile_frac", C.c_double), ("est_group_tile_frac", C.c_double)]
 
 
 class Counters(C.Structure):

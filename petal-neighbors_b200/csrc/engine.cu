@@ -125,6 +125,7 @@ struct Engine final : pn_tree {
     DevBuf d_tcen, d_trad, w_qs, w_seed, w_bits, w_tcnt;
     double prune_frac = 0.0;      // estimated fraction of (query group, tile) pairs that are out of reach
     double seed_candidates = 0.0; // estimated candidates per query that survive a seed threshold
+    double tile_frac = 0.0;       // estimated share of tiles beyond a single query's seed
     bool prune_on = false, tiles_on = false, last_pruned = false;   // prune_on: sorted + seeded scan; tiles_on: with tile bitmaps
     uint32_t prune_opt = 0;       // pn_prune
     // Vantage-point trees: the tensor path never used the VP bounds (a dense scan over the stored order), and the VP order
@@ -400,20 +401,22 @@ struct Engine final : pn_tree {
                 CU(cudaMemcpyAsync(sr.p, rows.data(), S * 4, cudaMemcpyHostToDevice, stream));
                 CU(cudaMemcpyAsync(sb.p, bks.data(), S * 4, cudaMemcpyHostToDevice, stream));
                 tc::seed_estimate_kernel<<<S, 256, 0, stream>>>(*reinterpret_cast<DevTree<float>*>(&dt), sr.as<uint32_t>(), sb.as<uint32_t>(), M,
-                                                               w_counters.as<unsigned long long>());
+                                                               d_tcen.as<float>(), d_trad.as<float>(), n_tiles, w_counters.as<unsigned long long>());
                 cudaError_t ke = cudaGetLastError();
-                unsigned long long se[2] = {0, 0};
-                if (ke == cudaSuccess) ke = cudaMemcpyAsync(se, (char*)w_counters.p + 16, 16, cudaMemcpyDeviceToHost, stream);
+                unsigned long long se[4] = {0, 0, 0, 0};
+                if (ke == cudaSuccess) ke = cudaMemcpyAsync(se, (char*)w_counters.p + 16, 32, cudaMemcpyDeviceToHost, stream);
                 if (ke == cudaSuccess) ke = cudaStreamSynchronize(stream);
                 sr.release(); sb.release();
                 if (ke != cudaSuccess) return fail(PN_CUDA, std::string("seed estimate: ") + cudaGetErrorString(ke));
                 seed_candidates = se[1] ? (double)se[0] / (double)se[1] * (double)ft.n : (double)ft.n;
+                tile_frac = se[3] ? (double)se[2] / (double)se[3] : 0.0;
             }
             // the streaming threshold alone leaves ~k ln(n/k) + 128 candidates per query (k = 10); seeding is worth its sort
             // and bucket pass when it gets within a small multiple of that
             const double stream_candidates = 10.0 * std::log(std::max(2.0, (double)ft.n / 10.0)) + 128.0;
             const bool can = ft.n_buckets > 1 && n_tiles > 4;
-            tiles_on = can && (prune_opt == PN_PRUNE_ON || (prune_opt == PN_PRUNE_AUTO && prune_frac >= 0.25));
+            // tile bitmaps: worth their pass when a single query could skip most tiles (a CTA needs the union over its queries)
+            tiles_on = can && (prune_opt == PN_PRUNE_ON || (prune_opt == PN_PRUNE_AUTO && (prune_frac >= 0.25 || tile_frac >= 0.6)));
             prune_on = can && (tiles_on || (prune_opt == PN_PRUNE_AUTO && seed_candidates <= 4.0 * stream_candidates));
             info.device_bytes += d_tcen.cap + d_trad.cap;
         }
@@ -1497,6 +1500,11 @@ static int finish_create(int kind, std::unique_ptr<Engine<A>>& e, const pn_build
     inf.bucket_size_max = ft.bucket_max;
     inf.algo = o.algo;
     inf.device = e->host_only ? -1 : e->device;
+    {
+        const Engine<A>* pe = e->aux ? e->aux.get() : e.get();   // a VP handle reports the ball partition its tensor path uses
+        inf.prune_seeded = pe->prune_on ? 1u : 0u; inf.prune_tiles = pe->tiles_on ? 1u : 0u;
+        inf.est_seed_candidates = pe->seed_candidates; inf.est_tile_frac = pe->tile_frac; inf.est_group_tile_frac = pe->prune_frac;
+    }
     inf.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     *out = e.release();
     return PN_OK;

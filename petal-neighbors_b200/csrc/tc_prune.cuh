@@ -81,9 +81,13 @@ __global__ void prune_estimate_kernel(const float* __restrict__ centers, const f
 // all points that lies within the seed.  share x n = candidates a query would still hand to the exact rerank when it
 // starts from its seed: a few hundred on clustered data, tens of thousands on uniform data in d >= 16 (where the running
 // threshold of the stream is just as good and the set-up passes are not worth it).
+// The same sample also measures what TILE skipping can do for a single query: the share of tile balls that lie beyond the
+// seed, |q - c_T| - R_T > seed (out[4] of out[5]).  A CTA needs the union over its queries, so this is an upper bound of
+// what the bitmaps will skip.
 __global__ void __launch_bounds__(256) seed_estimate_kernel(const DevTree<float> t, const uint32_t* __restrict__ sample_row,
                                                             const uint32_t* __restrict__ sample_bucket, uint32_t m_points,
-                                                            unsigned long long* __restrict__ out /* [2] within, [3] examined */) {
+                                                            const float* __restrict__ tcen, const float* __restrict__ trad, uint32_t n_tiles,
+                                                            unsigned long long* __restrict__ out /* [2] within, [3] examined, [4] tiles out of reach, [5] tiles */) {
     __shared__ float sd[1024];
     __shared__ float s_seed;
     __shared__ unsigned int s_cnt;
@@ -116,7 +120,20 @@ __global__ void __launch_bounds__(256) seed_estimate_kernel(const DevTree<float>
     }
     atomicAdd(&s_cnt, c);
     __syncthreads();
-    if (threadIdx.x == 0) { atomicAdd(&out[2], (unsigned long long)s_cnt); atomicAdd(&out[3], (unsigned long long)m_points); }
+    if (threadIdx.x == 0) { atomicAdd(&out[2], (unsigned long long)s_cnt); atomicAdd(&out[3], (unsigned long long)m_points); s_cnt = 0; }
+    __syncthreads();
+    const float seed_d = xmul(xsqrt(seed), 1.0000002f);
+    c = 0;
+    for (uint32_t tt = threadIdx.x; tt < n_tiles; tt += blockDim.x) {
+        const float4* ct = reinterpret_cast<const float4*>(tcen) + (size_t)tt * t.dv;
+        float acc = 0.f;
+        for (uint32_t j = 0; j < t.dv; ++j) acc = fold(acc, __ldg(qr + j), __ldg(ct + j));
+        const float cd = xsqrt(acc), rt = trad[tt];
+        c += (xsub(xsub(cd, rt), xmul(t.slack, xadd(cd, rt))) > seed_d) ? 1u : 0u;
+    }
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) { atomicAdd(&out[4], (unsigned long long)s_cnt); atomicAdd(&out[5], (unsigned long long)n_tiles); }
 }
 
 // every tile for every group (seeding without tile pruning)
