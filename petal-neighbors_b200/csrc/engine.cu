@@ -494,6 +494,43 @@ struct Engine final : pn_tree {
         return launch_filter_t<0, K, 1, 2>(map_a, fa, st);
     }
 
+    // Prepass of the seeded scans (k <= 16): queries sorted by home bucket (self query: the stored order is that order
+    // already) and every query's seed threshold from its home bucket.  *qsorted: padded query rows in sorted order; *order:
+    // sorted slot -> query id (null for the self query).
+    int sort_and_seed(const A* qraw, uint32_t nq, size_t stride, uint32_t k, cudaStream_t st, bool self_query, const float4** qsorted,
+                      const uint32_t** order) {
+        if constexpr (sizeof(A) == 4) {
+            *order = nullptr;
+            TRY(w_home.ensure((size_t)nq * 4));
+            if (self_query) {
+                TRY(w_hist.ensure((size_t)ft.n_buckets * 4));
+                home_bucket_kernel<A><<<(nq + 127) / 128, 128, 0, st>>>(dt, d_pts.as<V>(), nq, w_home.as<uint32_t>(), w_hist.as<uint32_t>());
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+                *qsorted = d_pts.as<float4>();
+            } else {
+                TRY(stage_queries(qraw, nq, stride, st, true));  // padded rows, home buckets, counting sort -> w_order
+                TRY(w_qs.ensure((size_t)nq * ft.dpad * 4));
+                const size_t tot = (size_t)nq * dt.dv;
+                tc::gather_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w_q.as<float4>(), w_order.as<uint32_t>(), nq, dt.dv, w_qs.as<float4>());
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+                *qsorted = w_qs.as<float4>();
+                *order = w_order.as<uint32_t>();
+            }
+            TRY(w_seed.ensure((size_t)nq * 4));
+            const DevTree<float>& dtf = *reinterpret_cast<DevTree<float>*>(&dt);
+            if (k == 1) tc::seed_bound_kernel<1><<<(nq + 127) / 128, 128, 0, st>>>(dtf, *qsorted, *order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
+            else tc::seed_bound_kernel<16><<<(nq + 127) / 128, 128, 0, st>>>(dtf, *qsorted, *order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
+            CU(cudaGetLastError());
+            ++counters.kernel_launches;
+            return PN_OK;
+        } else {
+            (void)qraw; (void)nq; (void)stride; (void)k; (void)st; (void)self_query; (void)qsorted; (void)order;
+            return fail(PN_BAD_ARG, "the tensor path is f32 only");
+        }
+    }
+
     // Pruned tensor k-NN (tc_prune.cuh; k <= 16): queries sorted by home bucket, seed bounds from the home bucket, one tile
     // bitmap per CTA, then ONE launch of the filter over all query groups -- the groups have lists of very different
     // lengths, so the hardware block scheduler does the load balancing that whole waves do for the dense scan.
@@ -506,25 +543,7 @@ struct Engine final : pn_tree {
             const uint32_t QT = 128u * (uint32_t)filter_subtiles(kp / tc::KC), n_qt = (nq + QT - 1) / QT;
             const float4* qsorted;
             const uint32_t* order = nullptr;
-            TRY(w_home.ensure((size_t)nq * 4));
-            if (self_query) {
-                // the stored points are their own queries and already sit in bucket order
-                TRY(w_hist.ensure((size_t)ft.n_buckets * 4));
-                home_bucket_kernel<A><<<(nq + 127) / 128, 128, 0, st>>>(dt, d_pts.as<V>(), nq, w_home.as<uint32_t>(), w_hist.as<uint32_t>());
-                CU(cudaGetLastError());
-                ++counters.kernel_launches;
-                qsorted = d_pts.as<float4>();
-            } else {
-                TRY(stage_queries(qraw, nq, stride, st, true));  // padded rows, home buckets, counting sort -> w_order
-                TRY(w_qs.ensure((size_t)nq * ft.dpad * 4));
-                const size_t tot = (size_t)nq * dt.dv;
-                tc::gather_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w_q.as<float4>(), w_order.as<uint32_t>(), nq, dt.dv, w_qs.as<float4>());
-                CU(cudaGetLastError());
-                ++counters.kernel_launches;
-                qsorted = w_qs.as<float4>();
-                order = w_order.as<uint32_t>();
-            }
-            TRY(w_seed.ensure((size_t)nq * 4));
+            TRY(sort_and_seed(qraw, nq, stride, k, st, self_query, &qsorted, &order));
             TRY(w_aaug.ensure((size_t)nq * kp * 2));
             TRY(w_qmargin.ensure((size_t)nq * 4));
             TRY(w_bits.ensure((size_t)n_qt * words * 4));
@@ -532,22 +551,14 @@ struct Engine final : pn_tree {
             TRY(w_part_d.ensure((size_t)nq * KP * 4));
             TRY(w_part_i.ensure((size_t)nq * KP * 4));
             const DevTree<float>& dtf = *reinterpret_cast<DevTree<float>*>(&dt);
-            if (k1) tc::seed_bound_kernel<1><<<(nq + 127) / 128, 128, 0, st>>>(dtf, qsorted, order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
-            else tc::seed_bound_kernel<16><<<(nq + 127) / 128, 128, 0, st>>>(dtf, qsorted, order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
-            CU(cudaGetLastError());
             tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(qsorted), d_center.as<float>(), tscale, nq, ft.d, ft.dpad,
                                                                     kp, pmax, w_aaug.as<__half>(), w_qmargin.as<float>());
             CU(cudaGetLastError());
-            if (tiles_on) {
-                tc::tile_bitmap_kernel<<<n_qt, 256, (size_t)(QT / 32) * dt.dv * 16, st>>>(
-                    qsorted, w_seed.as<float>(), nq, QT, d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
-                    w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>(), w_counters.as<unsigned long long>() + 3);
-            } else {  // seeds only: every group scans every tile
-                const size_t tot = (size_t)n_qt * words;
-                tc::fill_bitmap_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n_qt, n_tiles, words, w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>());
-            }
+            tc::tile_bitmap_kernel<<<n_qt, 256, (size_t)(QT / 32) * dt.dv * 16, st>>>(
+                qsorted, w_seed.as<float>(), nq, QT, d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
+                w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>(), w_counters.as<unsigned long long>() + 3);
             CU(cudaGetLastError());
-            counters.kernel_launches += 3;
+            counters.kernel_launches += 2;
             alignas(64) CUtensorMap map_a;
             TRY(make_map(&map_a, w_aaug.p, nq, tc::BM));
             CU(cudaEventRecord(ev[2], st));
@@ -585,9 +596,14 @@ struct Engine final : pn_tree {
             const uint32_t KP = k1 ? 1 : 16;
             const uint32_t n_pass = (k + KP - 1) / KP;
             last_pruned = prune_on && n_pass == 1;
-            if (last_pruned) return knn_device_pruned(qraw, nq, stride, k, kstride, idx_out, dist_out, st, self_query);
-            if (!self_query) TRY(stage_queries(qraw, nq, stride, st, false));
-            const float* qpad = self_query ? d_pts.as<float>() : w_q.as<float>();
+            if (last_pruned && tiles_on) return knn_device_pruned(qraw, nq, stride, k, kstride, idx_out, dist_out, st, self_query);
+            // seeded scan without tile bitmaps: the dense launch plan below over the SORTED queries, every query starting
+            // from its seed threshold; results return to their rows through the merge kernel's row map
+            const float4* qsorted = nullptr;
+            const uint32_t* order = nullptr;
+            if (last_pruned) TRY(sort_and_seed(qraw, nq, stride, k, st, self_query, &qsorted, &order));
+            else if (!self_query) TRY(stage_queries(qraw, nq, stride, st, false));
+            const float* qpad = last_pruned ? reinterpret_cast<const float*>(qsorted) : (self_query ? d_pts.as<float>() : w_q.as<float>());
             TRY(w_aaug.ensure((size_t)nq * kp * 2));
             TRY(w_qmargin.ensure((size_t)nq * 4));
             // Launch plan.  A CTA serves QT = 128 x subtiles queries against the whole point stream, so whole waves of
@@ -647,7 +663,8 @@ struct Engine final : pn_tree {
 #endif
                 A* fl_d = n_pass > 1 ? w_floor_d.as<A>() : nullptr;
                 uint32_t* fl_i = n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr;
-                const uint32_t* rmap = self_query ? d_ids.as<uint32_t>() : nullptr;
+                const uint32_t* rmap = self_query ? d_ids.as<uint32_t>() : order;
+                fa.seed_t2 = last_pruned ? w_seed.as<float>() : nullptr;
                 if (q_main) {
                     fa.row0 = 0; fa.nq = q_main; fa.tiles_per_split = n_tiles; fa.g_bound = nullptr;
                     TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));

@@ -252,7 +252,7 @@ struct FilterArgs {
     // its seed threshold
     const uint32_t* tile_bits;     // [grid.x][tile_words]
     const uint32_t* tile_cnt;      // [grid.x] set bits
-    const float* seed_t2;          // [nq] thresh2 of the seed k-th distance (exact squared units)
+    const float* seed_t2;          // [nq] or null: thresh2 of the seed k-th distance (exact squared units); also used by the dense scan
     uint32_t tile_words;
 #ifdef PN_TC_PROFILE
     uint32_t dbg;          // diagnostic leg isolation: 1 = epilogue skips the scan, 2 = producer skips the copies
@@ -538,17 +538,16 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         if (a.floor_d && active) topk.set_floor(a.floor_d[qrow], a.floor_i[qrow]);
         const float margin = active ? a.q_margin[qrow] : 0.f;  // E_q (scaled units)
         const float t2s = a.t2_scale;
-        const float seed2 = PRUNE && active ? a.seed_t2[qrow] : pos_inf<float>();  // an upper bound of the final k-th distance
+        const float seed2 = a.seed_t2 && active ? a.seed_t2[qrow] : pos_inf<float>();  // an upper bound of the final k-th distance
         TileIter titer;
         if (PRUNE && n_my) titer.init(my_bits);
-        float theta = active ? (PRUNE ? xadd(xmul(seed2, t2s), margin) : pos_inf<float>()) : -pos_inf<float>();
+        float theta = active ? xadd(xmul(seed2, t2s), margin) : -pos_inf<float>();   // +inf without a seed
         // Theta_q from the best known k-th bound.  When the point stream is split over several CTAs, the k-th distance
         // of ANY split's list is an upper bound of the final k-th distance, so the splits of a query publish theirs
         // (atomicMin on the float bits: the bounds are non-negative) and each filters with the smallest one.
         float* gb = SHARED && active ? a.g_bound + (qrow - a.row0) : nullptr;
         auto refresh_theta = [&](bool publish) {
-            float b = topk.t2;
-            if (PRUNE) b = fminf(b, seed2);
+            float b = fminf(topk.t2, seed2);
             if (SHARED && gb) {
                 if (publish) atomicMin(reinterpret_cast<int*>(gb), __float_as_int(b));
                 b = fminf(b, __ldcg(gb));

@@ -57,7 +57,20 @@ extern "C" {
     pub fn pn_balltree_query_self_f32(t: *mut pn_tree, k: usize, idx: *mut u64, dist: *mut f32) -> i32;
     pub fn pn_balltree_query_self_f64(t: *mut pn_tree, k: usize, idx: *mut u64, dist: *mut f64) -> i32;
     pub fn pn_free(p: *mut std::ffi::c_void);
+    // one process, several GPUs (include/petal_b200.h: pn_multi_*)
+    pub fn pn_multi_balltree_create_f32(devices: *const i32, n_dev: i32, shard_mode: u32, p: *const f32, n: usize, d: usize,
+                                        row_stride: usize, opts: *const pn_build_opts, out: *mut *mut pn_multi) -> i32;
+    pub fn pn_multi_balltree_query_f32(m: *mut pn_multi, q: *const f32, nq: usize, q_row_stride: usize, k: usize,
+                                       idx: *mut u64, dist: *mut f32) -> i32;
+    pub fn pn_multi_destroy(m: *mut pn_multi) -> i32;
 }
+
+#[repr(C)]
+pub struct pn_multi {
+    _private: [u8; 0],
+}
+pub const PN_SHARD_REPLICATE: u32 = 0;
+pub const PN_SHARD_BY_SUBTREE: u32 = 1;
 
 /// Element types the engine is instantiated for (the reference is generic over `A: Float`).
 pub trait Element: Copy + num_traits::Float + 'static {

@@ -252,6 +252,55 @@ impl<'a, A: Element> VantagePointTree<'a, A, Euclidean> {
     }
 }
 
+/// How a [`MultiGpuBallTree`] spreads over the devices.
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum ShardMode {
+    /// the tree is replicated (built once, sent with ncclBroadcast), a batch of queries is split into slices
+    Replicate,
+    /// one depth-log2(n) subtree per device; per-shard lists are exchanged over NCCL and merged
+    BySubtree,
+}
+
+/// Ball tree over several GPUs of one box, driven from this one process (`pn_multi_*`).  An addition to the reference
+/// API: `query_batch` has the same result layout as [`BallTree::query_batch`].
+pub struct MultiGpuBallTree {
+    handle: *mut ffi::pn_multi,
+    d: usize,
+}
+unsafe impl Send for MultiGpuBallTree {}
+
+impl MultiGpuBallTree {
+    pub fn euclidean(devices: &[i32], points: &ArrayView2<f32>, mode: ShardMode) -> Result<Self, ArrayError> {
+        let p = points.as_standard_layout();
+        let (n, d) = (p.nrows(), p.ncols());
+        let mut h = std::ptr::null_mut();
+        let m = if mode == ShardMode::Replicate { ffi::PN_SHARD_REPLICATE } else { ffi::PN_SHARD_BY_SUBTREE };
+        check_create(unsafe {
+            ffi::pn_multi_balltree_create_f32(devices.as_ptr(), devices.len() as i32, m, p.as_ptr(), n, d, d.max(1), std::ptr::null(), &mut h)
+        })?;
+        Ok(Self { handle: h, d })
+    }
+
+    pub fn query_batch(&mut self, queries: &ArrayView2<f32>, k: usize) -> (Array2<usize>, Array2<f32>) {
+        check_dim(queries.ncols(), self.d, "query batch");
+        let q = queries.as_standard_layout();
+        let nq = q.nrows();
+        let mut idx = vec![0u64; nq * k];
+        let mut dist = vec![0f32; nq * k];
+        check(unsafe { ffi::pn_multi_balltree_query_f32(self.handle, q.as_ptr(), nq, self.d, k, idx.as_mut_ptr(), dist.as_mut_ptr()) });
+        (
+            Array2::from_shape_vec((nq, k), idx.into_iter().map(|i| i as usize).collect()).unwrap(),
+            Array2::from_shape_vec((nq, k), dist).unwrap(),
+        )
+    }
+}
+
+impl Drop for MultiGpuBallTree {
+    fn drop(&mut self) {
+        unsafe { ffi::pn_multi_destroy(self.handle) };
+    }
+}
+
 #[cfg(test)]
 mod test {
     // The reference's own doctests / unit tests, unchanged, run against the GPU crate.
