@@ -543,6 +543,7 @@ struct Engine final : pn_tree {
             const uint32_t QT = 128u * (uint32_t)filter_subtiles(kp / tc::KC), n_qt = (nq + QT - 1) / QT;
             const float4* qsorted;
             const uint32_t* order = nullptr;
+            CU(cudaEventRecord(ev[2], st));   // scan_ms covers the whole scan: sort + seeds, bitmaps, filter, merge
             TRY(sort_and_seed(qraw, nq, stride, k, st, self_query, &qsorted, &order));
             TRY(w_aaug.ensure((size_t)nq * kp * 2));
             TRY(w_qmargin.ensure((size_t)nq * 4));
@@ -561,7 +562,6 @@ struct Engine final : pn_tree {
             counters.kernel_launches += 2;
             alignas(64) CUtensorMap map_a;
             TRY(make_map(&map_a, w_aaug.p, nq, tc::BM));
-            CU(cudaEventRecord(ev[2], st));
             tc::FilterArgs fa{};
             fa.t = dtf;
             fa.q = qsorted; fa.q_margin = w_qmargin.as<float>();
@@ -601,6 +601,7 @@ struct Engine final : pn_tree {
             // from its seed threshold; results return to their rows through the merge kernel's row map
             const float4* qsorted = nullptr;
             const uint32_t* order = nullptr;
+            CU(cudaEventRecord(ev[2], st));   // scan_ms covers the whole scan: staging, sort + seeds, filter, merge
             if (last_pruned) TRY(sort_and_seed(qraw, nq, stride, k, st, self_query, &qsorted, &order));
             else if (!self_query) TRY(stage_queries(qraw, nq, stride, st, false));
             const float* qpad = last_pruned ? reinterpret_cast<const float*>(qsorted) : (self_query ? d_pts.as<float>() : w_q.as<float>());
@@ -638,7 +639,6 @@ struct Engine final : pn_tree {
             ++counters.kernel_launches;
             alignas(64) CUtensorMap map_a;
             TRY(make_map(&map_a, w_aaug.p, nq, tc::BM));
-            CU(cudaEventRecord(ev[2], st));
             for (uint32_t p = 0; p < n_pass; ++p) {
                 const uint32_t kk = std::min(KP, k - p * KP);
                 tc::FilterArgs fa{};
@@ -864,12 +864,14 @@ struct Engine final : pn_tree {
             for (cudaEvent_t* e : {&e_in[i], &e_cmp[i], &e_out[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         return PN_OK;
     }
-    // queries per chunk of a host-buffer call: whole waves of the tensor scan (n_sms CTAs x 512 queries), at most four
-    // of them, so that a large batch becomes >= 4 chunks whose copies hide under the neighbouring chunks' kernels
+    // queries per chunk of a host-buffer call: whole waves of the tensor scan (n_sms CTAs x 512 queries).  Two chunks are
+    // enough to hide the copies (H2D of the second and D2H of the first run under the other's kernels) and keep the per-chunk
+    // set-up (query staging, sort, seeds, a partial last wave) small; chunks are capped at 2^20 queries (workspace size).
     size_t host_chunk(size_t nq) const {
         const size_t wave = (size_t)n_sms * 512;
-        if (nq < 2 * wave) return nq;
-        return std::min<size_t>(4, std::max<size_t>(1, nq / (4 * wave))) * wave;
+        if (nq < 4 * wave) return nq;
+        const size_t half = ((nq + 1) / 2 + wave - 1) / wave * wave;
+        return std::min<size_t>(half, ((size_t)1 << 20) / wave * wave);
     }
 
     int knn_host(const void* qv, size_t nq, size_t stride, size_t k, uint64_t* idx, void* distv) override {
@@ -1136,6 +1138,11 @@ struct Engine final : pn_tree {
             ++counters.kernel_launches;
             segment_sort_kernel<<<blocks, wpb * 32, 0, s>>>(r_offsets[b].as<uint64_t>(), r_hits[b].as<uint32_t>(), cq);
             CUB(cudaGetLastError());
+            if (ctotal > SORT_WARP_MAX) {  // some hit list may be longer than a warp should sort: one block per such query
+                segment_sort_large_kernel<<<cq, 256, 0, s>>>(r_offsets[b].as<uint64_t>(), r_hits[b].as<uint32_t>(), cq);
+                CUB(cudaGetLastError());
+                ++counters.kernel_launches;
+            }
             counters.kernel_launches += 2;
             CUB(cudaMemcpyAsync(offs + q0 + 1, r_offsets[b].as<uint64_t>() + 1, (size_t)cq * 8, cudaMemcpyDeviceToHost, s));
             TRYB(copy_out_widen(hit_buf + total, r_hits[b].as<uint32_t>(), ctotal, s));
@@ -1586,17 +1593,20 @@ static int pairwise_host(int device, const A* x, size_t n, size_t d, size_t row_
     if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return fail(PN_CUDA, "no CUDA device available (there is no CPU fallback)"); }
     DeviceGuard g(dev);
     if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+    // the matrix leaves the device in row blocks of at most 256 MiB, so n is bounded by the caller's host buffer, not by HBM
     DevBuf dx, dout;
+    const size_t rows_per_block = std::max<size_t>(32, std::min<size_t>(n, ((size_t)256 << 20) / (n * sizeof(A)) / 32 * 32));
     int rc = dx.ensure(n * d * sizeof(A));
-    if (rc == PN_OK) rc = dout.ensure(n * n * sizeof(A));
+    if (rc == PN_OK) rc = dout.ensure(rows_per_block * n * sizeof(A));
     if (rc == PN_OK) {
         cudaError_t e = cudaMemcpy2D(dx.p, d * sizeof(A), x, row_stride * sizeof(A), d * sizeof(A), n, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) {
-            dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32)), block(32, 32);
-            pairwise_kernel<A><<<grid, block>>>(dx.as<A>(), (uint32_t)n, (uint32_t)d, dout.as<A>());
+        for (size_t r0 = 0; r0 < n && e == cudaSuccess; r0 += rows_per_block) {
+            const size_t rows = std::min(rows_per_block, n - r0);
+            dim3 grid((unsigned)((n + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 32);
+            pairwise_kernel<A><<<grid, block>>>(dx.as<A>(), (uint32_t)n, (uint32_t)d, dout.as<A>(), (uint32_t)r0, (uint32_t)rows);
             e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpy(out + r0 * n, dout.p, rows * n * sizeof(A), cudaMemcpyDeviceToHost);
         }
-        if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, n * n * sizeof(A), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(PN_CUDA, std::string("pairwise: ") + cudaGetErrorString(e));
     }
     dx.release(); dout.release();

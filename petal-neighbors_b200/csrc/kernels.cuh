@@ -743,33 +743,53 @@ __global__ void offsets_scan_kernel(const uint32_t* __restrict__ counts, uint64_
     for (uint32_t i = b; i < e; ++i) { unsigned long long v = counts[i]; offsets[i] = run; run += v; }
 }
 
-// ascending sort of each query's hit list: one warp per segment, bitonic network over the
-// segment padded to a power of two with +inf keys (the reference's order is unspecified DFS
-// order and its tests sort before comparing, src/ball_tree.rs:667, 777)
+// ascending sort of each query's hit list (the reference's order is unspecified DFS order and its tests sort before
+// comparing, src/ball_tree.rs:667, 777): bitonic network over the segment padded to a power of two with virtual +inf
+// keys.  Segments of up to SORT_WARP_MAX entries are sorted by one warp each; longer ones (large radii: whole subtrees
+// included) by one 256-thread block each in a second launch, so that a few huge hit lists do not serialise on 32 lanes.
+constexpr uint32_t SORT_WARP_MAX = 1024;
+// all-ascending form of the network (first step of each phase mirrors, i ^ (size-1)): every compare-exchange moves the
+// smaller key down, so the virtual +inf keys at >= n never move
+__device__ __forceinline__ void sort_cmpx(uint32_t* v, uint32_t n, uint32_t i, uint32_t j) {
+    if (j > i && j < n) {
+        const uint32_t x = v[i], y = v[j];
+        if (x > y) { v[i] = y; v[j] = x; }
+    }
+}
 __global__ void segment_sort_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ vals, uint32_t nq) {
     const int lane = threadIdx.x & 31;
     const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= nq) return;
     const uint64_t lo = offsets[qi];
     const uint32_t n = (uint32_t)(offsets[qi + 1] - lo);
-    if (n < 2) return;
+    if (n < 2 || n > SORT_WARP_MAX) return;
     uint32_t* v = vals + lo;
     uint32_t np2 = 1;
     while (np2 < n) np2 <<= 1;
-    // all-ascending form of the bitonic network (first step of each phase mirrors, i ^ (size-1)):
-    // every compare-exchange moves the smaller key down, so the virtual +inf keys at >= n never move
-    auto cmpx = [&](uint32_t i, uint32_t j) {
-        if (j > i && j < n) {
-            const uint32_t x = v[i], y = v[j];
-            if (x > y) { v[i] = y; v[j] = x; }
-        }
-    };
     for (uint32_t size = 2; size <= np2; size <<= 1) {
-        for (uint32_t i = lane; i < np2; i += 32) cmpx(i, i ^ (size - 1));
+        for (uint32_t i = lane; i < np2; i += 32) sort_cmpx(v, n, i, i ^ (size - 1));
         __syncwarp();
         for (uint32_t stride = size >> 2; stride > 0; stride >>= 1) {
-            for (uint32_t i = lane; i < np2; i += 32) cmpx(i, i ^ stride);
+            for (uint32_t i = lane; i < np2; i += 32) sort_cmpx(v, n, i, i ^ stride);
             __syncwarp();
+        }
+    }
+}
+__global__ void __launch_bounds__(256) segment_sort_large_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ vals, uint32_t nq) {
+    const uint32_t qi = blockIdx.x;
+    const uint64_t lo = offsets[qi];
+    const uint64_t n64 = offsets[qi + 1] - lo;
+    if (n64 <= SORT_WARP_MAX) return;          // block-uniform
+    const uint32_t n = (uint32_t)n64;
+    uint32_t* v = vals + lo;
+    uint64_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (uint64_t size = 2; size <= np2; size <<= 1) {
+        for (uint64_t i = threadIdx.x; i < np2; i += blockDim.x) sort_cmpx(v, n, (uint32_t)i, (uint32_t)(i ^ (size - 1)));
+        __syncthreads();
+        for (uint64_t stride = size >> 2; stride > 0; stride >>= 1) {
+            for (uint64_t i = threadIdx.x; i < np2; i += blockDim.x) sort_cmpx(v, n, (uint32_t)i, (uint32_t)(i ^ stride));
+            __syncthreads();
         }
     }
 }
@@ -779,10 +799,11 @@ __global__ void segment_sort_kernel(const uint64_t* __restrict__ offsets, uint32
 // fold distances.  A 32 x 32 output tile per block; the two 32-row panels are staged in shared
 // memory in chunks of 32 dimensions, every thread keeps its sequential sum across chunks, so the
 // result is bit-identical to the reference's per-pair fold (and symmetric: (a-b)^2 == (b-a)^2). --
+// `out` holds rows [row0, row0 + rows) of the matrix: the host walks the matrix in row blocks that fit a bounded buffer.
 template <typename A>
-__global__ void pairwise_kernel(const A* __restrict__ x, uint32_t n, uint32_t d, A* __restrict__ out) {
+__global__ void pairwise_kernel(const A* __restrict__ x, uint32_t n, uint32_t d, A* __restrict__ out, uint32_t row0, uint32_t rows) {
     __shared__ A pi[32][33], pj[32][33];
-    const uint32_t i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const uint32_t i0 = row0 + blockIdx.y * 32, j0 = blockIdx.x * 32;
     const uint32_t ti = threadIdx.y, tj = threadIdx.x;
     A acc = A(0);
     for (uint32_t c0 = 0; c0 < d; c0 += 32) {
@@ -797,7 +818,7 @@ __global__ void pairwise_kernel(const A* __restrict__ x, uint32_t n, uint32_t d,
         }
         __syncthreads();
     }
-    if (i0 + ti < n && j0 + tj < n) out[(size_t)(i0 + ti) * n + (j0 + tj)] = xsqrt(acc);
+    if (i0 + ti < row0 + rows && i0 + ti < n && j0 + tj < n) out[(size_t)(i0 + ti - row0) * n + (j0 + tj)] = xsqrt(acc);
 }
 
 }  // namespace petal

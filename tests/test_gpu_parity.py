@@ -303,6 +303,14 @@ def test_pairwise(pn, oracle, dtype, n, d):
     assert np.array_equal(got, got.T) and np.all(np.diag(got) == 0)
 
 
+def test_pairwise_row_blocks(pn, oracle):
+    """n x n above the 256 MiB device buffer: the matrix is produced in row blocks (n = 9000: three of them)."""
+    x = np.random.default_rng(77).random((9000, 5)).astype(np.float32)
+    got = pn.distance.pairwise(x, pn.distance.Euclidean())
+    want = oracle.pairwise(x)
+    assert np.array_equal(bits(got), bits(want))
+
+
 def test_concurrent_queries_on_one_handle(pn, oracle):
     """Queries on one tree from several host threads are legal (reference: &self queries,
     Euclidean: Sync, src/distance.rs:19); the engine serialises them and every caller gets its answer."""
