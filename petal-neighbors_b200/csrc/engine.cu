@@ -1139,7 +1139,7 @@ struct Engine final : pn_tree {
             segment_sort_kernel<<<blocks, wpb * 32, 0, s>>>(r_offsets[b].as<uint64_t>(), r_hits[b].as<uint32_t>(), cq);
             CUB(cudaGetLastError());
             if (ctotal > SORT_WARP_MAX) {  // some hit list may be longer than a warp should sort: one block per such query
-                segment_sort_large_kernel<<<cq, 256, 0, s>>>(r_offsets[b].as<uint64_t>(), r_hits[b].as<uint32_t>(), cq);
+                segment_sort_large_kernel<<<std::min<uint32_t>(cq, 8u * (uint32_t)n_sms), 256, 0, s>>>(r_offsets[b].as<uint64_t>(), r_hits[b].as<uint32_t>(), cq);
                 CUB(cudaGetLastError());
                 ++counters.kernel_launches;
             }

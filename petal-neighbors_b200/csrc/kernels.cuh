@@ -776,10 +776,10 @@ __global__ void segment_sort_kernel(const uint64_t* __restrict__ offsets, uint32
     }
 }
 __global__ void __launch_bounds__(256) segment_sort_large_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ vals, uint32_t nq) {
-    const uint32_t qi = blockIdx.x;
+  for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {   // a fixed grid walks the queries; long lists are rare
     const uint64_t lo = offsets[qi];
     const uint64_t n64 = offsets[qi + 1] - lo;
-    if (n64 <= SORT_WARP_MAX) return;          // block-uniform
+    if (n64 <= SORT_WARP_MAX) continue;        // block-uniform
     const uint32_t n = (uint32_t)n64;
     uint32_t* v = vals + lo;
     uint64_t np2 = 1;
@@ -792,6 +792,7 @@ __global__ void __launch_bounds__(256) segment_sort_large_kernel(const uint64_t*
             __syncthreads();
         }
     }
+  }
 }
 
 
