@@ -85,7 +85,7 @@ typedef struct pn_build_opts {
      * (src/ball_tree.rs:535-537 split rule).  Returned indices stay global.  0/0 = all. */
     uint32_t shard_depth;
     uint32_t shard_index;
-    uint32_t builder;     /* pn_builder: where the partition is computed (ball trees; VP trees are host-built) */
+    uint32_t builder;     /* pn_builder: where the partition is computed */
     uint32_t prune;       /* pn_prune: triangle-inequality pruning in front of the tensor filter */
     uint32_t reserved[6];
 } pn_build_opts;

@@ -193,6 +193,45 @@ struct Engine final : pn_tree {
         o.centers = e->d_centers.template as<A>(); o.radii = e->d_radii.template as<A>();
         return o;
     }
+    static gb::VpOut<A> alloc_vp_arrays(void* ctx, uint64_t n, const gb::VpShape& shape) {
+        Engine* e = static_cast<Engine*>(ctx);
+        FlatTree<A>& t = e->ft;
+        t.kind = 1; t.n = n; t.n_total = n;
+        t.dpad = (uint32_t)((t.d + VT<A>::N - 1) / VT<A>::N * VT<A>::N);
+        t.L = shape.L; t.n_internal = (1u << t.L) - 1; t.n_buckets = 1u << t.L; t.n_nodes = t.n_internal;
+        t.bucket_lo = shape.lo[t.L]; t.bucket_hi = shape.hi[t.L];
+        t.bucket_max = 0;
+        for (uint32_t b = 0; b < t.n_buckets; ++b) t.bucket_max = std::max(t.bucket_max, t.bucket_hi[b] - t.bucket_lo[b]);
+        gb::VpOut<A> o{nullptr, nullptr, nullptr, nullptr, nullptr};
+        const size_t nn = std::max<uint32_t>(t.n_nodes, 1);
+        if (e->d_pts.ensure((size_t)n * t.dpad * sizeof(A)) != PN_OK || e->d_ids.ensure((size_t)n * 4) != PN_OK ||
+            e->d_centers.ensure(nn * t.dpad * sizeof(A)) != PN_OK || e->d_radii.ensure(nn * sizeof(A)) != PN_OK || e->d_vpids.ensure(nn * 4) != PN_OK)
+            return o;
+        o.pts = e->d_pts.template as<A>(); o.ids = e->d_ids.template as<uint32_t>();
+        o.centers = e->d_centers.template as<A>(); o.radii = e->d_radii.template as<A>(); o.vp_ids = e->d_vpids.template as<uint32_t>();
+        return o;
+    }
+    // vantage-point tree on the device (gb::build_vp_tree): the same arrays the host VpBuilder + upload() produce
+    int build_vp_on_device(const A* raw_dev, size_t n, size_t d, size_t stride, uint32_t bucket) {
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "no usable CUDA device (there is no CPU fallback)");
+        TRY(open_device());
+        ft.d = (uint32_t)d;
+        gb::VpShape shape;
+        std::string err;
+        const int rc = gb::build_vp_tree<A>(raw_dev, n, (uint32_t)d, stride, bucket, shape, &Engine::alloc_vp_arrays, this, stream, err);
+        if (rc) return fail(rc == (int)cudaErrorMemoryAllocation ? PN_OOM : PN_CUDA, "device tree build: " + err);
+        gpu_built = true;
+        TRY(d_blo.ensure(ft.bucket_lo.size() * 4));
+        TRY(d_bhi.ensure(ft.bucket_hi.size() * 4));
+        CU(cudaMemcpy(d_blo.p, ft.bucket_lo.data(), ft.bucket_lo.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_bhi.p, ft.bucket_hi.data(), ft.bucket_hi.size() * 4, cudaMemcpyHostToDevice));
+        info.device_bytes = d_pts.cap + d_ids.cap + d_blo.cap + d_bhi.cap + d_centers.cap + d_radii.cap + d_vpids.cap;
+        fill_dev_tree();
+        TRY(prepare_tensor());
+        return PN_OK;
+    }
+
     int build_on_device(const A* raw_dev, size_t n_all, size_t d, size_t stride, uint32_t bucket, uint32_t shard_depth, uint32_t shard_index) {
         DeviceGuard g(device);
         if (!g.ok) return fail(PN_CUDA, "no usable CUDA device (there is no CPU fallback)");
@@ -1451,8 +1490,8 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
     if (o.shard_depth && (kind != PN_KIND_BALL || o.shard_depth > 16 || o.shard_index >= (1u << o.shard_depth)))
         return fail(PN_BAD_ARG, kind != PN_KIND_BALL ? "subtree sharding is a ball-tree option" : "bad shard_depth / shard_index");
     // ball trees with a device are built there from 32768 points up (bit-identical layout, tests/test_gpu_build.py)
-    const bool on_device = kind == PN_KIND_BALL && !host_only && (o.builder == PN_BUILDER_DEVICE || (o.builder == PN_BUILDER_AUTO && n >= 32768));
-    if (o.builder == PN_BUILDER_DEVICE && !on_device) return fail(PN_BAD_ARG, "the device builder needs a ball tree with a device");
+    const bool on_device = !host_only && (o.builder == PN_BUILDER_DEVICE || (o.builder == PN_BUILDER_AUTO && n >= 32768));
+    if (o.builder == PN_BUILDER_DEVICE && !on_device) return fail(PN_BAD_ARG, "the device builder needs a device");
     int dev = o.device;
     if (!host_only && dev < 0) {
         if (cudaGetDevice(&dev) != cudaSuccess) {
@@ -1473,8 +1512,9 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
             DevBuf raw;
             TRY(raw.ensure(n * d * sizeof(A)));
             cudaError_t ce = cudaMemcpy2D(raw.p, d * sizeof(A), points, std::max(row_stride, d) * sizeof(A), d * sizeof(A), n, cudaMemcpyHostToDevice);
-            int rc = ce == cudaSuccess ? e->build_on_device(raw.as<A>(), n, d, d, bucket, o.shard_depth, o.shard_index)
-                                       : fail(PN_CUDA, std::string("uploading the points: ") + cudaGetErrorString(ce));
+            int rc = ce != cudaSuccess ? fail(PN_CUDA, std::string("uploading the points: ") + cudaGetErrorString(ce))
+                     : kind == PN_KIND_BALL ? e->build_on_device(raw.as<A>(), n, d, d, bucket, o.shard_depth, o.shard_index)
+                                            : e->build_vp_on_device(raw.as<A>(), n, d, d, bucket);
             raw.release();
             TRY(rc);
         } else if (kind == PN_KIND_BALL) {

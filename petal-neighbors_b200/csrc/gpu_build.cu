@@ -44,11 +44,13 @@ __device__ __forceinline__ double ord_val(unsigned long long k) {
 
 // block b of a level -> (segment, first position, count): cps blocks per segment, ROWS positions each
 struct Span { uint32_t seg, lo, cnt, seg_lo, seg_hi; };
-__device__ __forceinline__ Span block_span(const uint32_t* __restrict__ seg_l, uint32_t cps) {
+// (ball trees: seg_hi = seg_lo + 1, the boundaries of a level are contiguous; vantage-point trees keep separate arrays --
+// the vantage point of a node sits between its children's ranges)
+__device__ __forceinline__ Span block_span(const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, uint32_t cps) {
     Span s;
     s.seg = blockIdx.x / cps;
     const uint32_t chunk = blockIdx.x % cps;
-    s.seg_lo = seg_l[s.seg]; s.seg_hi = seg_l[s.seg + 1];
+    s.seg_lo = seg_lo[s.seg]; s.seg_hi = seg_hi[s.seg];
     const uint64_t lo = (uint64_t)s.seg_lo + (uint64_t)chunk * ROWS;
     s.lo = (uint32_t)min(lo, (uint64_t)s.seg_hi);
     s.cnt = min((uint32_t)ROWS, s.seg_hi - s.lo);
@@ -58,11 +60,11 @@ __device__ __forceinline__ Span block_span(const uint32_t* __restrict__ seg_l, u
 // ---- 1. per-segment, per-column min / max (max_spread_column, src/ball_tree.rs:577-603) -----------------------------
 template <typename A>
 __global__ void __launch_bounds__(BT) minmax_kernel(const A* __restrict__ raw, uint64_t stride, uint32_t d, const uint32_t* __restrict__ idx,
-                                                    const uint32_t* __restrict__ seg_l, uint32_t cps,
+                                                    const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t cps,
                                                     typename KeyT<A>::U* __restrict__ mn, typename KeyT<A>::U* __restrict__ mx) {
     using U = typename KeyT<A>::U;
     __shared__ U s_mn[BT], s_mx[BT];
-    const Span sp = block_span(seg_l, cps);
+    const Span sp = block_span(seg_l, seg_h, cps);
     if (sp.cnt == 0) return;
     uint32_t dp = 1;
     while (dp < d && dp < BT) dp <<= 1;            // threads per row (power of two <= 256)
@@ -91,11 +93,11 @@ __global__ void __launch_bounds__(BT) minmax_kernel(const A* __restrict__ raw, u
 // first column with the strictly greatest spread (src/ball_tree.rs:604-612)
 template <typename A>
 __global__ void choose_kernel(const typename KeyT<A>::U* __restrict__ mn, const typename KeyT<A>::U* __restrict__ mx, uint32_t d,
-                              uint32_t n_seg, const uint32_t* __restrict__ seg_l, uint32_t* __restrict__ col) {
+                              uint32_t n_seg, const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t* __restrict__ col) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     uint32_t best_c = 0;
-    if (seg_l[s + 1] - seg_l[s] >= 2) {
+    if (seg_h[s] - seg_l[s] >= 2) {
         A best = ord_val(mx[(uint64_t)s * d]) - ord_val(mn[(uint64_t)s * d]);
         for (uint32_t j = 1; j < d; ++j) {
             const A sp = ord_val(mx[(uint64_t)s * d + j]) - ord_val(mn[(uint64_t)s * d + j]);
@@ -108,20 +110,28 @@ __global__ void choose_kernel(const typename KeyT<A>::U* __restrict__ mn, const 
 // ---- 2. median of each segment on the (value of the split column, original index) key: MSB-first radix select -------
 template <typename A>
 __global__ void __launch_bounds__(BT) keys_kernel(const A* __restrict__ raw, uint64_t stride, const uint32_t* __restrict__ idx,
-                                                  const uint32_t* __restrict__ seg_l, uint32_t cps, const uint32_t* __restrict__ col,
+                                                  const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t cps, const uint32_t* __restrict__ col,
                                                   typename KeyT<A>::U* __restrict__ kv) {
-    const Span sp = block_span(seg_l, cps);
+    const Span sp = block_span(seg_l, seg_h, cps);
     const uint32_t c = col[sp.seg];
     for (uint32_t r = threadIdx.x; r < sp.cnt; r += BT) kv[sp.lo + r] = ord_key(raw[(uint64_t)idx[sp.lo + r] * stride + c]);
 }
 
 template <typename U> struct SelState { U pv; uint32_t pi; uint32_t m; };
 
+// rank of the element a select is after, by `mode`: 0 = len / 2 (ball: mid - start, src/ball_tree.rs:535-537),
+// 1 = len - 1 (the maximum: a vantage point is the LAST element of its sorted slice, src/vantage_point_tree.rs:169-170),
+// 2 = (len - 1) / 2 (far[0] of the slice without its vantage point, :180-182)
+__device__ __forceinline__ uint32_t select_rank(uint32_t len, int mode) {
+    return mode == 0 ? len / 2 : (mode == 1 ? len - 1 : (len - 1) / 2);
+}
 template <typename U>
-__global__ void init_state_kernel(const uint32_t* __restrict__ seg_l, uint32_t n_seg, SelState<U>* __restrict__ st) {
+__global__ void init_state_kernel(const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t n_seg, int mode,
+                                  SelState<U>* __restrict__ st) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
-    st[s].pv = 0; st[s].pi = 0; st[s].m = (seg_l[s + 1] - seg_l[s]) / 2;  // rank of the pivot: mid - start, :535-537
+    const uint32_t len = seg_h[s] - seg_l[s];
+    st[s].pv = 0; st[s].pi = 0; st[s].m = len ? select_rank(len, mode) : 0;
 }
 
 template <typename U, int VB>
@@ -144,11 +154,11 @@ __device__ __forceinline__ void sel_extend(SelState<U>& s, uint32_t dg, uint32_t
 // large segments: one pass = histogram over many blocks + a pick kernel
 template <typename A>
 __global__ void __launch_bounds__(BT) hist_kernel(const typename KeyT<A>::U* __restrict__ kv, const uint32_t* __restrict__ idx,
-                                                  const uint32_t* __restrict__ seg_l, uint32_t cps,
+                                                  const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t cps,
                                                   const SelState<typename KeyT<A>::U>* __restrict__ st, int pass, uint32_t* __restrict__ hist) {
     using U = typename KeyT<A>::U;
     __shared__ uint32_t sh[256];
-    const Span sp = block_span(seg_l, cps);
+    const Span sp = block_span(seg_l, seg_h, cps);
     if (sp.cnt == 0) return;
     sh[threadIdx.x] = 0;
     __syncthreads();
@@ -162,11 +172,12 @@ __global__ void __launch_bounds__(BT) hist_kernel(const typename KeyT<A>::U* __r
     if (sh[threadIdx.x]) atomicAdd(&hist[(uint64_t)sp.seg * 256 + threadIdx.x], sh[threadIdx.x]);
 }
 template <typename U, int VB>
-__global__ void pick_kernel(uint32_t* __restrict__ hist, SelState<U>* __restrict__ st, const uint32_t* __restrict__ seg_l, uint32_t n_seg, int pass) {
+__global__ void pick_kernel(uint32_t* __restrict__ hist, SelState<U>* __restrict__ st, const uint32_t* __restrict__ seg_l,
+                            const uint32_t* __restrict__ seg_h, uint32_t n_seg, int pass) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     uint32_t* h = hist + (uint64_t)s * 256;
-    if (seg_l[s + 1] > seg_l[s]) {
+    if (seg_h[s] > seg_l[s]) {
         SelState<U> x = st[s];
         uint32_t run = 0, dg = 0;
         for (; dg < 256; ++dg) {
@@ -183,14 +194,15 @@ __global__ void pick_kernel(uint32_t* __restrict__ hist, SelState<U>* __restrict
 constexpr uint32_t SMALL_MAX = 4096;
 template <typename A>
 __global__ void __launch_bounds__(BT) select_small_kernel(const typename KeyT<A>::U* __restrict__ kv, const uint32_t* __restrict__ idx,
-                                                          const uint32_t* __restrict__ seg_l, SelState<typename KeyT<A>::U>* __restrict__ st) {
+                                                          const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, int mode,
+                                                          SelState<typename KeyT<A>::U>* __restrict__ st) {
     using U = typename KeyT<A>::U;
     constexpr int VB = KeyT<A>::VB;
     __shared__ uint32_t sh[256];
     __shared__ SelState<U> s;
-    const uint32_t seg = blockIdx.x, lo = seg_l[seg], cnt = seg_l[seg + 1] - lo;
+    const uint32_t seg = blockIdx.x, lo = seg_l[seg], cnt = seg_h[seg] - lo;
     if (cnt == 0) return;
-    if (threadIdx.x == 0) { s.pv = 0; s.pi = 0; s.m = cnt / 2; }
+    if (threadIdx.x == 0) { s.pv = 0; s.pi = 0; s.m = select_rank(cnt, mode); }
     for (int pass = 0; pass < VB + 4; ++pass) {
         sh[threadIdx.x] = 0;
         __syncthreads();
@@ -227,11 +239,11 @@ __device__ __forceinline__ bool goes_left(U k, uint32_t id, const SelState<U>& s
 
 template <typename A>
 __global__ void __launch_bounds__(BT) count_left_kernel(const typename KeyT<A>::U* __restrict__ kv, const uint32_t* __restrict__ idx,
-                                                        const uint32_t* __restrict__ seg_l, uint32_t cps,
+                                                        const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t cps,
                                                         const SelState<typename KeyT<A>::U>* __restrict__ st, uint32_t* __restrict__ csum) {
     using U = typename KeyT<A>::U;
     __shared__ uint32_t wsum[BT / 32];
-    const Span sp = block_span(seg_l, cps);
+    const Span sp = block_span(seg_l, seg_h, cps);
     uint32_t c = 0;
     if (sp.cnt) {
         const SelState<U> s = st[sp.seg];
@@ -259,12 +271,12 @@ __global__ void scan_blocks_kernel(const uint32_t* __restrict__ in, uint32_t* __
 }
 template <typename A>
 __global__ void __launch_bounds__(BT) scatter_kernel(const typename KeyT<A>::U* __restrict__ kv, const uint32_t* __restrict__ idx,
-                                                     const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_next, uint32_t cps,
+                                                     const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, const uint32_t* __restrict__ seg_next, uint32_t cps,
                                                      const SelState<typename KeyT<A>::U>* __restrict__ st, const uint32_t* __restrict__ cex,
                                                      uint32_t* __restrict__ idx_out) {
     using U = typename KeyT<A>::U;
     __shared__ uint32_t wsum[BT / 32];
-    const Span sp = block_span(seg_l, cps);
+    const Span sp = block_span(seg_l, seg_h, cps);
     if (sp.cnt == 0) return;
     const SelState<U> s = st[sp.seg];
     const uint32_t mid = seg_next[2 * sp.seg + 1];
@@ -436,24 +448,25 @@ static int partition_levels(const A* raw, uint64_t stride, uint32_t d, const Tre
     for (uint32_t l = 0; l < levels; ++l) {
         const uint32_t n_seg = 1u << l, cps = blocks_per_seg(l), nb = n_seg * cps;
         const uint32_t* seg_l = seg_dev[l];
+        const uint32_t* seg_h = seg_dev[l] + 1;   // contiguous boundaries: the end of segment s is the start of s + 1
         const uint32_t* seg_n = seg_dev[l + 1];
         GB_CU(cudaMemsetAsync(mn, 0xff, (size_t)n_seg * d * sizeof(U), st));
         GB_CU(cudaMemsetAsync(mx, 0x00, (size_t)n_seg * d * sizeof(U), st));
-        minmax_kernel<A><<<nb, BT, 0, st>>>(raw, stride, d, cur, seg_l, cps, mn, mx);
-        choose_kernel<A><<<(n_seg + 127) / 128, 128, 0, st>>>(mn, mx, d, n_seg, seg_l, col);
-        keys_kernel<A><<<nb, BT, 0, st>>>(raw, stride, cur, seg_l, cps, col, kv);
+        minmax_kernel<A><<<nb, BT, 0, st>>>(raw, stride, d, cur, seg_l, seg_h, cps, mn, mx);
+        choose_kernel<A><<<(n_seg + 127) / 128, 128, 0, st>>>(mn, mx, d, n_seg, seg_l, seg_h, col);
+        keys_kernel<A><<<nb, BT, 0, st>>>(raw, stride, cur, seg_l, seg_h, cps, col, kv);
         if (((n + ((uint64_t(1) << l) - 1)) >> l) > SMALL_MAX) {
-            init_state_kernel<U><<<(n_seg + 127) / 128, 128, 0, st>>>(seg_l, n_seg, state);
+            init_state_kernel<U><<<(n_seg + 127) / 128, 128, 0, st>>>(seg_l, seg_h, n_seg, 0, state);
             for (int pass = 0; pass < VB + 4; ++pass) {
-                hist_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, cps, state, pass, hist);
-                pick_kernel<U, VB><<<(n_seg + 127) / 128, 128, 0, st>>>(hist, state, seg_l, n_seg, pass);
+                hist_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, seg_h, cps, state, pass, hist);
+                pick_kernel<U, VB><<<(n_seg + 127) / 128, 128, 0, st>>>(hist, state, seg_l, seg_h, n_seg, pass);
             }
         } else {
-            select_small_kernel<A><<<n_seg, BT, 0, st>>>(kv, cur, seg_l, state);
+            select_small_kernel<A><<<n_seg, BT, 0, st>>>(kv, cur, seg_l, seg_h, 0, state);
         }
-        count_left_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, cps, state, csum);
+        count_left_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, seg_h, cps, state, csum);
         scan_blocks_kernel<<<1, 1024, 0, st>>>(csum, cex, nb);
-        scatter_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, seg_n, cps, state, cex, nxt);
+        scatter_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, seg_h, seg_n, cps, state, cex, nxt);
         GB_CU(cudaGetLastError());
         std::swap(cur, nxt);
     }
@@ -541,6 +554,214 @@ template int build_ball_tree<float>(const float*, uint64_t, uint32_t, uint64_t, 
                                     BallOut<float> (*)(void*, uint64_t, const TreeShape&), void*, cudaStream_t, std::string&);
 template int build_ball_tree<double>(const double*, uint64_t, uint32_t, uint64_t, uint32_t, uint32_t, uint32_t, TreeShape&, uint64_t*,
                                      BallOut<double> (*)(void*, uint64_t, const TreeShape&), void*, cudaStream_t, std::string&);
+
+// ======================================================================================================================
+// Vantage-point tree (create_node, src/vantage_point_tree.rs:146-197) level by level on the device.  The host builder sorts
+// each slice by (distance to the vantage point, id), takes the LAST element of the sorted slice as the next vantage point,
+// the first half as `near`, the rest as `far`, mu = far[0].distance.  None of that needs the sort itself:
+//   vantage point of a slice = its maximum on the (distance to the parent's vantage point, id) key  -> select, rank len-1
+//   near / far                = split at rank (len-1)/2 of the (distance to the vantage point, id) key -> select + partition
+// Only the stored order of a bucket is the sorted order, so the buckets are sorted once at the end.  The partition places
+// [near | far | vantage point] exactly as the reference's slices lie, and the keys travel with the indices so that the next
+// level can pick its vantage points.
+template <typename A>
+__global__ void __launch_bounds__(BT) vp_keys_kernel(const A* __restrict__ raw, uint64_t stride, uint32_t d, const uint32_t* __restrict__ idx,
+                                                     const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t cps,
+                                                     const SelState<typename KeyT<A>::U>* __restrict__ st, typename KeyT<A>::U* __restrict__ kv,
+                                                     uint32_t* __restrict__ vp_pos) {
+    using U = typename KeyT<A>::U;
+    const Span sp = block_span(seg_l, seg_h, cps);
+    if (sp.cnt == 0) return;
+    const uint32_t vp = st[sp.seg].pi;  // the id selected as this slice's vantage point
+    const A* vrow = raw + (uint64_t)vp * stride;
+    for (uint32_t r = threadIdx.x; r < sp.cnt; r += BT) {
+        const uint32_t id = idx[sp.lo + r];
+        if (id == vp) { kv[sp.lo + r] = ~(U)0; vp_pos[sp.seg] = sp.lo + r; continue; }   // sorts after every real distance
+        const A* row = raw + (uint64_t)id * stride;
+        A acc = A(0);
+        for (uint32_t j = 0; j < d; ++j) {
+            const A diff = row[j] - vrow[j];
+            acc = acc + diff * diff;
+        }
+        kv[sp.lo + r] = ord_key(xsqrt_rn(acc));
+    }
+}
+template <typename A>
+__global__ void __launch_bounds__(BT) vp_scatter_kernel(const typename KeyT<A>::U* __restrict__ kv, const uint32_t* __restrict__ idx,
+                                                        const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t cps,
+                                                        const SelState<typename KeyT<A>::U>* __restrict__ st, const uint32_t* __restrict__ cex,
+                                                        const uint32_t* __restrict__ vp_pos, uint32_t* __restrict__ idx_out,
+                                                        typename KeyT<A>::U* __restrict__ kv_out) {
+    using U = typename KeyT<A>::U;
+    __shared__ uint32_t wsum[BT / 32];
+    const Span sp = block_span(seg_l, seg_h, cps);
+    if (sp.cnt == 0) return;
+    const SelState<U> s = st[sp.seg];
+    const uint32_t len = sp.seg_hi - sp.seg_lo;
+    const uint32_t mid = sp.seg_lo + (len - 1) / 2;   // first position of `far`
+    const uint32_t vpp = vp_pos[sp.seg];
+    const uint32_t left_before = cex[blockIdx.x] - cex[sp.seg * cps];
+    constexpr int PER = ROWS / BT;
+    uint32_t ids[PER]; U ks[PER]; bool lf[PER];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const uint32_t r = threadIdx.x * PER + i;
+        lf[i] = false; ids[i] = 0; ks[i] = 0;
+        if (r < sp.cnt) { ids[i] = idx[sp.lo + r]; ks[i] = kv[sp.lo + r]; lf[i] = goes_left<U>(ks[i], ids[i], s); mine += lf[i] ? 1u : 0u; }
+    }
+    uint32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)(threadIdx.x & 31) >= o) incl += v; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) wbase += wsum[w];
+    uint32_t lrun = left_before + wbase + incl - mine;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const uint32_t r = threadIdx.x * PER + i;
+        if (r >= sp.cnt) break;
+        const uint32_t pos = sp.lo + r;
+        uint32_t dst;
+        if (pos == vpp) dst = sp.seg_hi - 1;                                              // the vantage point closes the slice
+        else if (lf[i]) dst = sp.seg_lo + lrun;                                           // near, order kept
+        else dst = mid + (pos - sp.seg_lo - lrun) - (pos > vpp ? 1u : 0u);               // far, order kept, the vantage point taken out
+        idx_out[dst] = ids[i];
+        kv_out[dst] = ks[i];
+        lrun += lf[i] ? 1u : 0u;
+    }
+}
+// node arrays: vantage point row, mu = distance key of the pivot (far[0].distance), id
+template <typename A>
+__global__ void vp_nodes_kernel(const A* __restrict__ raw, uint64_t stride, uint32_t d, uint32_t dpad, const SelState<typename KeyT<A>::U>* __restrict__ vsel,
+                                const SelState<typename KeyT<A>::U>* __restrict__ msel, uint32_t first, uint32_t count, A* __restrict__ centers,
+                                A* __restrict__ radii, uint32_t* __restrict__ vp_ids) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (uint64_t)count * dpad) return;
+    const uint32_t s = (uint32_t)(e / dpad), j = (uint32_t)(e % dpad);
+    const uint32_t vp = vsel[s].pi;
+    centers[(uint64_t)(first + s) * dpad + j] = j < d ? raw[(uint64_t)vp * stride + j] : A(0);
+    if (j == 0) { radii[first + s] = ord_val(msel[s].pv); vp_ids[first + s] = vp; }
+}
+// buckets in the reference's stored order: ascending (distance to the parent's vantage point, id); one block per bucket,
+// bitonic network on the (key, id) pairs in global memory (virtual +inf pairs beyond the end never move)
+template <typename A>
+__global__ void __launch_bounds__(BT) vp_bucket_sort_kernel(typename KeyT<A>::U* __restrict__ kv, uint32_t* __restrict__ idx,
+                                                            const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h) {
+    using U = typename KeyT<A>::U;
+    const uint32_t lo = seg_l[blockIdx.x], n = seg_h[blockIdx.x] - lo;
+    if (n < 2) return;
+    U* k = kv + lo;
+    uint32_t* v = idx + lo;
+    uint32_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    auto cmpx = [&](uint32_t i, uint32_t j) {
+        if (j > i && j < n) {
+            const U ki = k[i], kj = k[j];
+            const uint32_t vi = v[i], vj = v[j];
+            if (ki > kj || (ki == kj && vi > vj)) { k[i] = kj; k[j] = ki; v[i] = vj; v[j] = vi; }
+        }
+    };
+    for (uint32_t size = 2; size <= np2; size <<= 1) {
+        for (uint32_t i = threadIdx.x; i < np2; i += BT) cmpx(i, i ^ (size - 1));
+        __syncthreads();
+        for (uint32_t stride = size >> 2; stride > 0; stride >>= 1) {
+            for (uint32_t i = threadIdx.x; i < np2; i += BT) cmpx(i, i ^ stride);
+            __syncthreads();
+        }
+    }
+}
+
+void VpShape::init(uint64_t n_, uint32_t L_) {
+    n = n_; L = L_;
+    lo.assign(L + 1, {}); hi.assign(L + 1, {});
+    lo[0] = {0u}; hi[0] = {(uint32_t)n};
+    for (uint32_t l = 0; l < L; ++l) {
+        const size_t ns = size_t(1) << l;
+        lo[l + 1].resize(2 * ns); hi[l + 1].resize(2 * ns);
+        for (size_t s = 0; s < ns; ++s) {
+            const uint32_t a = lo[l][s], b = hi[l][s], len = b - a;
+            const uint32_t half = len ? (len - 1) / 2 : 0;
+            lo[l + 1][2 * s] = a;            hi[l + 1][2 * s] = a + half;            // near
+            lo[l + 1][2 * s + 1] = a + half; hi[l + 1][2 * s + 1] = len ? b - 1 : a; // far; the vantage point sits at b - 1
+        }
+    }
+}
+
+template <typename A>
+int build_vp_tree(const A* raw, uint64_t n, uint32_t d, uint64_t stride, uint32_t bucket_size, VpShape& shape,
+                  VpOut<A> (*alloc_out)(void* ctx, uint64_t n, const VpShape& shape), void* ctx, cudaStream_t st, std::string& err) {
+    using U = typename KeyT<A>::U;
+    constexpr int VB = KeyT<A>::VB;
+    Scratch sc;
+    shape.init(n, choose_levels(n, bucket_size));
+    const uint32_t L = shape.L, n_internal = (1u << L) - 1;
+    const uint32_t vecn = 16 / sizeof(A), dpad = (d + vecn - 1) / vecn * vecn;
+    VpOut<A> out = alloc_out(ctx, n, shape);
+    if (!out.pts || !out.ids || !out.centers || !out.radii || !out.vp_ids) { err = "allocation of the tree arrays failed"; return (int)cudaErrorMemoryAllocation; }
+    uint32_t *idx_a = nullptr, *idx_b = nullptr, *vpp = nullptr, *hist = nullptr, *csum = nullptr, *cex = nullptr;
+    U *kv_a = nullptr, *kv_b = nullptr;
+    SelState<U>*vsel = nullptr, *msel = nullptr;
+    const uint32_t max_seg = 1u << L;
+    auto blocks_per_seg = [&](uint32_t l) {
+        const uint64_t maxlen = (n + ((uint64_t(1) << l) - 1)) >> l;
+        return (uint32_t)std::max<uint64_t>(1, (maxlen + ROWS - 1) / ROWS);
+    };
+    size_t max_blocks = 1, max_big_seg = 1;
+    for (uint32_t l = 0; l <= L; ++l) {
+        max_blocks = std::max<size_t>(max_blocks, (size_t)blocks_per_seg(l) << l);
+        if (((n + ((uint64_t(1) << l) - 1)) >> l) > SMALL_MAX) max_big_seg = size_t(1) << l;
+    }
+    GB_CU(sc.get(&idx_a, n)); GB_CU(sc.get(&idx_b, n)); GB_CU(sc.get(&kv_a, n)); GB_CU(sc.get(&kv_b, n));
+    GB_CU(sc.get(&vpp, max_seg)); GB_CU(sc.get(&vsel, max_seg)); GB_CU(sc.get(&msel, max_seg));
+    GB_CU(sc.get(&hist, max_big_seg * 256)); GB_CU(sc.get(&csum, max_blocks)); GB_CU(sc.get(&cex, max_blocks));
+    GB_CU(cudaMemsetAsync(hist, 0, max_big_seg * 256 * 4, st));
+    GB_CU(cudaMemsetAsync(kv_a, 0, n * sizeof(U), st));   // create_root: every distance equal, so the last id is the first vantage point
+    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx_a, n);
+    std::vector<uint32_t*> lo_dev(L + 1), hi_dev(L + 1);
+    for (uint32_t l = 0; l <= L; ++l) {
+        GB_CU(sc.get(&lo_dev[l], shape.lo[l].size())); GB_CU(sc.get(&hi_dev[l], shape.hi[l].size()));
+        GB_CU(cudaMemcpyAsync(lo_dev[l], shape.lo[l].data(), shape.lo[l].size() * 4, cudaMemcpyHostToDevice, st));
+        GB_CU(cudaMemcpyAsync(hi_dev[l], shape.hi[l].data(), shape.hi[l].size() * 4, cudaMemcpyHostToDevice, st));
+    }
+    auto select = [&](const U* kv, const uint32_t* idx, uint32_t l, int mode, SelState<U>* state) {
+        const uint32_t n_seg = 1u << l, cps = blocks_per_seg(l), nb = n_seg * cps;
+        if (((n + ((uint64_t(1) << l) - 1)) >> l) > SMALL_MAX) {
+            init_state_kernel<U><<<(n_seg + 127) / 128, 128, 0, st>>>(lo_dev[l], hi_dev[l], n_seg, mode, state);
+            for (int pass = 0; pass < VB + 4; ++pass) {
+                hist_kernel<A><<<nb, BT, 0, st>>>(kv, idx, lo_dev[l], hi_dev[l], cps, state, pass, hist);
+                pick_kernel<U, VB><<<(n_seg + 127) / 128, 128, 0, st>>>(hist, state, lo_dev[l], hi_dev[l], n_seg, pass);
+            }
+        } else {
+            select_small_kernel<A><<<n_seg, BT, 0, st>>>(kv, idx, lo_dev[l], hi_dev[l], mode, state);
+        }
+    };
+    uint32_t *cur = idx_a, *nxt = idx_b;
+    U *kcur = kv_a, *knxt = kv_b;
+    for (uint32_t l = 0; l < L; ++l) {
+        const uint32_t n_seg = 1u << l, cps = blocks_per_seg(l), nb = n_seg * cps, first = n_seg - 1;
+        select(kcur, cur, l, 1, vsel);                                                    // the slice's last element in sorted order
+        vp_keys_kernel<A><<<nb, BT, 0, st>>>(raw, stride, d, cur, lo_dev[l], hi_dev[l], cps, vsel, kcur, vpp);
+        select(kcur, cur, l, 2, msel);                                                    // far[0]
+        vp_nodes_kernel<A><<<(unsigned)(((uint64_t)n_seg * dpad + 255) / 256), 256, 0, st>>>(raw, stride, d, dpad, vsel, msel, first, n_seg, out.centers,
+                                                                                             out.radii, out.vp_ids);
+        count_left_kernel<A><<<nb, BT, 0, st>>>(kcur, cur, lo_dev[l], hi_dev[l], cps, msel, csum);
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(csum, cex, nb);
+        vp_scatter_kernel<A><<<nb, BT, 0, st>>>(kcur, cur, lo_dev[l], hi_dev[l], cps, msel, cex, vpp, nxt, knxt);
+        GB_CU(cudaGetLastError());
+        std::swap(cur, nxt); std::swap(kcur, knxt);
+    }
+    vp_bucket_sort_kernel<A><<<1u << L, BT, 0, st>>>(kcur, cur, lo_dev[L], hi_dev[L]);
+    gather_rows_kernel<A><<<(unsigned)((n * dpad + 255) / 256), 256, 0, st>>>(raw, stride, d, dpad, cur, n, out.pts, out.ids);
+    GB_CU(cudaGetLastError());
+    GB_CU(cudaStreamSynchronize(st));
+    (void)n_internal;
+    return 0;
+}
+template int build_vp_tree<float>(const float*, uint64_t, uint32_t, uint64_t, uint32_t, VpShape&, VpOut<float> (*)(void*, uint64_t, const VpShape&), void*,
+                                  cudaStream_t, std::string&);
+template int build_vp_tree<double>(const double*, uint64_t, uint32_t, uint64_t, uint32_t, VpShape&, VpOut<double> (*)(void*, uint64_t, const VpShape&),
+                                   void*, cudaStream_t, std::string&);
 
 // ---- centre and range of the stored points for the tensor path --------------------------------------------------------
 constexpr uint32_t CH_ROWS = 4096;

@@ -61,6 +61,26 @@ int build_ball_tree(const A* raw, uint64_t n_all, uint32_t d, uint64_t stride, u
                     BallOut<A> (*alloc_out)(void* ctx, uint64_t n, const TreeShape& shape), void* ctx, cudaStream_t st,
                     std::string& err);
 
+// ---- vantage-point tree (src/vantage_point_tree.rs:146-197): ranges of the level-l slices in the stored order; the
+// vantage point of a slice [lo, hi) sits at hi - 1, near = [lo, lo + (len-1)/2), far = [lo + (len-1)/2, hi - 1)
+struct VpShape {
+    uint64_t n = 0;
+    uint32_t L = 0;
+    std::vector<std::vector<uint32_t>> lo, hi;  // [L + 1][2^l]
+    void init(uint64_t n_, uint32_t L_);
+};
+template <typename A>
+struct VpOut {
+    A* pts;            // n x dpad, stored order [near | far | vantage point] recursively, buckets sorted by (distance to the parent's vantage point, id)
+    uint32_t* ids;     // n
+    A* centers;        // n_internal x dpad: vantage point rows
+    A* radii;          // n_internal: mu
+    uint32_t* vp_ids;  // n_internal
+};
+template <typename A>
+int build_vp_tree(const A* raw, uint64_t n, uint32_t d, uint64_t stride, uint32_t bucket_size, VpShape& shape,
+                  VpOut<A> (*alloc_out)(void* ctx, uint64_t n, const VpShape& shape), void* ctx, cudaStream_t st, std::string& err);
+
 // mean of the stored rows (double accumulation over fixed chunks of 4096 rows combined in chunk order: the same value
 // as the host pass of Engine::prepare_tensor) and the largest centred coordinate max |p_j - c_j|
 int centre_and_range_f32(const float* pts, uint64_t n, uint32_t d, uint32_t dpad, float* center_dev, float* center_host,

@@ -1,5 +1,5 @@
 """Device-side tree construction (csrc/gpu_build.cu; reference build_subtree / Node::init / max_spread_column /
-halve_node_indices, src/ball_tree.rs:445-613) against the host builder, which stays as the checker: the flattened layouts
+halve_node_indices, src/ball_tree.rs:445-613, and create_node, src/vantage_point_tree.rs:146-197) against the host builder, which stays as the checker: the flattened layouts
 must be bit-identical (ids, bucket ranges, centroids, radii, point rows), also on data with masses of equal column values
 (ties broken by original index on both sides), for shards, and for points that never leave the device."""
 import numpy as np
@@ -52,6 +52,48 @@ def test_device_builder_matches_host(pn, dtype, n, d, bucket, kind):
     host = pn.BallTree.euclidean(pts, bucket_size=bucket, builder=pn.PN_BUILDER_HOST)
     dev = pn.BallTree.euclidean(pts, bucket_size=bucket, builder=pn.PN_BUILDER_DEVICE)
     same_layout(host, dev)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,d,bucket,kind", [
+    (1, 3, 0, "u"), (7, 5, 8, "u"), (9, 2, 8, "u"), (300, 1, 8, "u"), (5000, 3, 32, "u"), (20000, 16, 0, "u"), (4097, 17, 64, "u"),
+    (33000, 64, 0, "u"), (9000, 130, 128, "u"), (6000, 3, 16, "lattice"), (40000, 8, 64, "lattice"), (5000, 4, 8, "const"),
+    (70000, 10, 0, "mix"), (300000, 3, 0, "u"), (200000, 32, 0, "u"),
+])
+def test_device_vp_builder_matches_host(pn, dtype, n, d, bucket, kind):
+    """Vantage-point trees: vantage point = last element of the sorted slice = maximum of the (distance, id) key, near / far
+    by a select at rank (len-1)/2, buckets sorted at the end -- the stored order, vantage points and thresholds must equal
+    the host builder's sort-based construction, also where masses of distances tie (lattice, constant data)."""
+    from petal_neighbors_b200 import synth
+    rng = np.random.default_rng(n + d + 1)
+    if kind == "u":
+        pts = synth.uniform(n, d, 200 + n + d, dtype)
+    elif kind == "lattice":
+        pts = rng.integers(0, 5, size=(n, d)).astype(dtype)
+    elif kind == "const":
+        pts = np.full((n, d), 0.25, dtype)
+    else:
+        pts = synth.gaussian_mixture(n, d, 5, n_centers=16, dtype=dtype)
+    host = pn.VantagePointTree.euclidean(pts, bucket_size=bucket, builder=pn.PN_BUILDER_HOST)
+    dev = pn.VantagePointTree.euclidean(pts, bucket_size=bucket, builder=pn.PN_BUILDER_DEVICE)
+    same_layout(host, dev)
+
+
+def test_device_vp_builder_queries(pn, oracle):
+    """the pruned SIMT traversal on a device-built vantage-point tree (the tensor path of a VP handle uses the ball partition)"""
+    from petal_neighbors_b200 import synth
+    pts = synth.gaussian_mixture(50000, 24, 5, n_centers=64, dtype=np.float32)
+    Q = synth.gaussian_mixture(3000, 24, 6, n_centers=64, dtype=np.float32)
+    oi, od = oracle.brute_knn(pts, Q, 1)
+    for algo in (pn.PN_ALGO_SIMT, pn.PN_ALGO_AUTO):
+        vp = pn.VantagePointTree.euclidean(pts, builder=pn.PN_BUILDER_DEVICE, algo=algo)
+        vi, vd = vp.query_nearest_batch(Q)
+        assert np.array_equal(vi, oi[:, 0].astype(np.uint64)) and np.array_equal(bits(vd), bits(od[:, 0]))
+    p64 = pts.astype(np.float64)
+    vp = pn.VantagePointTree.euclidean(p64, builder=pn.PN_BUILDER_DEVICE)
+    oi, od = oracle.brute_knn(p64, Q.astype(np.float64), 1)
+    vi, vd = vp.query_nearest_batch(Q.astype(np.float64))
+    assert np.array_equal(vi, oi[:, 0].astype(np.uint64)) and np.array_equal(bits(vd), bits(od[:, 0]))
 
 
 @pytest.mark.parametrize("n,depth", [(10001, 3), (50000, 2), (5, 3)])
