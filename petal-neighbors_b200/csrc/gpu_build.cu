@@ -643,6 +643,13 @@ __global__ void vp_nodes_kernel(const A* __restrict__ raw, uint64_t stride, uint
     centers[(uint64_t)(first + s) * dpad + j] = j < d ? raw[(uint64_t)vp * stride + j] : A(0);
     if (j == 0) { radii[first + s] = ord_val(msel[s].pv); vp_ids[first + s] = vp; }
 }
+// The index arrays ping-pong between two buffers level by level, and the slot of a vantage point belongs to no slice of
+// the levels below it: the slots are written into the final buffer once more from the node array.
+__global__ void vp_slots_kernel(const uint32_t* __restrict__ seg_h, uint32_t n_seg, uint32_t first, const uint32_t* __restrict__ vp_ids,
+                                uint32_t* __restrict__ idx) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_seg) idx[seg_h[s] - 1] = vp_ids[first + s];
+}
 // buckets in the reference's stored order: ascending (distance to the parent's vantage point, id); one block per bucket,
 // bitonic network on the (key, id) pairs in global memory (virtual +inf pairs beyond the end never move)
 template <typename A>
@@ -751,6 +758,8 @@ int build_vp_tree(const A* raw, uint64_t n, uint32_t d, uint64_t stride, uint32_
         GB_CU(cudaGetLastError());
         std::swap(cur, nxt); std::swap(kcur, knxt);
     }
+    for (uint32_t l = 0; l < L; ++l)
+        vp_slots_kernel<<<((1u << l) + 127) / 128, 128, 0, st>>>(hi_dev[l], 1u << l, (1u << l) - 1, out.vp_ids, cur);
     vp_bucket_sort_kernel<A><<<1u << L, BT, 0, st>>>(kcur, cur, lo_dev[L], hi_dev[L]);
     gather_rows_kernel<A><<<(unsigned)((n * dpad + 255) / 256), 256, 0, st>>>(raw, stride, d, dpad, cur, n, out.pts, out.ids);
     GB_CU(cudaGetLastError());
