@@ -1230,7 +1230,11 @@ struct Engine final : pn_tree {
         A* dist_out = (A*)dist_outv;
         const int W = cm->world, R = cm->rank;
         constexpr bool PACKED = sizeof(A) == 4;
-        const size_t chunk = host_chunk(nq), n_chunks = (nq + chunk - 1) / chunk;
+        // chunks of whole waves, about eight of them: the exchange of chunk i hides under the scan of chunk i+1, so only the
+        // last chunk's exchange is exposed
+        const size_t wave = (size_t)n_sms * 512;
+        const size_t chunk = nq < 2 * wave ? nq : std::min<size_t>(std::max<size_t>(1, (nq / 8 + wave - 1) / wave) * wave, ((size_t)1 << 20) / wave * wave);
+        const size_t n_chunks = (nq + chunk - 1) / chunk;
         auto slice = [&](int r, size_t& lo, size_t& hi) { pn_query_slice(nq, r, W, &lo, &hi); };
         size_t my_lo = 0, my_hi = nq;
         if (exchange == PN_EXCHANGE_SLICE) slice(R, my_lo, my_hi);
