@@ -276,6 +276,11 @@ int32_t pn_multi_balltree_create_f32(const int32_t *devices, int32_t n_dev, uint
                                      size_t n, size_t d, size_t row_stride, const pn_build_opts *opts, pn_multi **out);
 int32_t pn_multi_balltree_query_f32(pn_multi *m, const float *queries, size_t nq, size_t q_row_stride, size_t k,
                                     uint64_t *idx_out, float *dist_out);
+/* How the per-shard lists of a BY_SUBTREE handle meet: PN_EXCHANGE_PEER (the default when every pair of devices has peer
+ * access) runs NO collective -- the k-way merge kernel of each device reads the other devices' packed lists directly from
+ * their memory over NVLink (the exchange fused into the consumer); PN_EXCHANGE_SLICE uses grouped ncclSend/ncclRecv. */
+#define PN_EXCHANGE_PEER 2u
+int32_t pn_multi_set_exchange(pn_multi *m, uint32_t exchange);
 /* per-device statistics of the last query: stats[n_dev] (BY_SUBTREE: the exchange; REPLICATE: zeros but rows_out) */
 int32_t pn_multi_get_stats(const pn_multi *m, pn_shard_stats *stats, int32_t n_stats);
 int32_t pn_multi_destroy(pn_multi *m);

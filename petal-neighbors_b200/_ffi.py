@@ -31,10 +31,10 @@ EXPORTS = [
     "pn_tree_get_info", "pn_tree_get_counters", "pn_tree_get_layout",
     "pn_comm_unique_id", "pn_comm_create", "pn_comm_create_all", "pn_comm_destroy", "pn_query_slice",
     "pn_sharded_query_knn_dev", "pn_tree_replicate",
-    "pn_multi_balltree_create_f32", "pn_multi_balltree_query_f32", "pn_multi_get_stats", "pn_multi_destroy",
+    "pn_multi_balltree_create_f32", "pn_multi_balltree_query_f32", "pn_multi_set_exchange", "pn_multi_get_stats", "pn_multi_destroy",
 ]
 PN_SHARD_REPLICATE, PN_SHARD_BY_SUBTREE = 0, 1
-PN_EXCHANGE_ALLGATHER, PN_EXCHANGE_SLICE = 0, 1
+PN_EXCHANGE_ALLGATHER, PN_EXCHANGE_SLICE, PN_EXCHANGE_PEER = 0, 1, 2
 PN_UNIQUE_ID_BYTES = 128
 
 
@@ -148,6 +148,8 @@ def lib():
     L.pn_multi_balltree_create_f32.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.c_uint32, vp, sz, sz, sz, C.POINTER(BuildOpts), C.POINTER(vp)]
     L.pn_multi_balltree_query_f32.restype = C.c_int32
     L.pn_multi_balltree_query_f32.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+    L.pn_multi_set_exchange.restype = C.c_int32
+    L.pn_multi_set_exchange.argtypes = [vp, C.c_uint32]
     L.pn_multi_get_stats.restype = C.c_int32
     L.pn_multi_get_stats.argtypes = [vp, C.POINTER(ShardStats), C.c_int32]
     L.pn_multi_destroy.restype = C.c_int32

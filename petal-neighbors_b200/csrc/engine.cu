@@ -4,6 +4,7 @@
 #include <sys/mman.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -74,6 +75,28 @@ struct DeviceGuard {
 
 using namespace petal;
 
+// State shared by the rank threads of one pn_multi query in PEER mode: every rank's packed-list buffers and events, and a
+// host barrier the rank threads meet at (an event must have been RECORDED before another rank's stream can wait on it).
+struct PeerShared {
+    int n = 0;
+    std::vector<const unsigned long long*> pack[2];   // [buffer][rank]
+    std::vector<cudaEvent_t> ev_scan[2], ev_merge[2]; // [buffer][rank]
+    std::mutex mu;
+    std::condition_variable cv;
+    int count = 0, gen = 0;
+    bool failed = false;
+    // returns false when some rank has failed (nobody waits for it any more)
+    bool barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        if (failed) return false;
+        const int g = gen;
+        if (++count == n) { count = 0; ++gen; cv.notify_all(); return true; }
+        cv.wait(lk, [&] { return gen != g || failed; });
+        return !failed;
+    }
+    void fail() { std::lock_guard<std::mutex> lk(mu); failed = true; cv.notify_all(); }
+};
+
 // The opaque handle.
 struct pn_tree {
     virtual ~pn_tree() {}
@@ -90,6 +113,8 @@ struct pn_tree {
     virtual int knn_sharded(pn_comm* cm, const void* q, size_t nq, size_t stride, size_t k, uint32_t exchange, uint64_t* idx, void* dist,
                             cudaStream_t st, pn_shard_stats* stats) = 0;
     virtual int replicate_send(pn_comm* cm, int root) = 0;
+    virtual int knn_sharded_peer(PeerShared& ps, int rank, int world, const void* q, size_t nq, size_t stride, size_t k, uint64_t* idx, void* dist,
+                                 pn_shard_stats* stats) = 0;
 };
 
 namespace petal {
@@ -1365,6 +1390,110 @@ struct Engine final : pn_tree {
         return fetch_counters(st, nq);
     }
 
+    // ---- point sharding by subtree WITHOUT a collective (one process, several GPUs): the merge kernel of every rank reads
+    // the other ranks' packed lists straight from their memory over NVLink.  Same chunking and double buffering as
+    // knn_sharded; the merge of chunk c-1 is queued behind the scan of chunk c, so waiting for the slowest rank's lists
+    // costs nothing while there is still a chunk to scan.
+    int knn_sharded_peer(PeerShared& ps, int R, int W, const void* qv, size_t nq, size_t stride, size_t k, uint64_t* idx_out, void* dist_outv,
+                         pn_shard_stats* stats) override {
+        if constexpr (sizeof(A) != 4) {
+            (void)ps; (void)R; (void)W; (void)qv; (void)nq; (void)stride; (void)k; (void)idx_out; (void)dist_outv; (void)stats;
+            return fail(PN_BAD_ARG, "the peer exchange serves f32 trees");
+        } else {
+            struct Guard { PeerShared& p; bool ok = false; ~Guard() { if (!ok) p.fail(); } } guard{ps};
+            TRY(check_query_args(qv, nq, stride));
+            if (k == 0 || k > 255 || W > 64) return fail(PN_BAD_ARG, "peer exchange: 1 <= k <= 255, at most 64 ranks");
+            std::lock_guard<std::mutex> lk(mu);
+            DeviceGuard g(device);
+            if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+            cudaStream_t st = stream;
+            TRY(use_stream(st));
+            counters = pn_counters{};
+            if (stats) *stats = pn_shard_stats{};
+            const A* q = (const A*)qv;
+            const size_t wave = (size_t)n_sms * 512;
+            const size_t chunk = nq < 2 * wave ? nq : std::min<size_t>(std::max<size_t>(1, (nq / 8 + wave - 1) / wave) * wave, ((size_t)1 << 20) / wave * wave);
+            const size_t n_chunks = (nq + chunk - 1) / chunk;
+            size_t my_lo, my_hi;
+            pn_query_slice(nq, R, W, &my_lo, &my_hi);
+            DevBuf& ptrs = sh_gat[0];  // [2][W] list pointers of every rank, per buffer
+            TRY(ptrs.ensure((size_t)2 * W * sizeof(void*)));
+            for (int b = 0; b < 2; ++b) {
+                TRY(sh_li[b].ensure(chunk * k * 8));
+                TRY(sh_ld[b].ensure(chunk * k * 4));
+                TRY(sh_pack[b].ensure(chunk * k * 8));
+                ps.pack[b][R] = sh_pack[b].as<unsigned long long>();
+            }
+            while (sh_ev.size() < 4 * n_chunks) { cudaEvent_t e; CU(cudaEventCreate(&e)); sh_ev.push_back(e); }
+            auto EV = [&](size_t c, int i) { return sh_ev[4 * c + i]; };  // 0,1 scan; 2,3 merge
+            if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");     // every rank's buffers exist
+            std::vector<const unsigned long long*> hp(2 * (size_t)W);
+            for (int b = 0; b < 2; ++b) for (int p = 0; p < W; ++p) hp[(size_t)b * W + p] = ps.pack[b][p];
+            CU(cudaMemcpyAsync(ptrs.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+            TRY(begin_call(st));
+            CU(cudaEventRecord(ev[0], st));
+            unsigned long long rows_out = 0, peer_bytes = 0;
+            auto merge_chunk = [&](size_t c) -> int {
+                const int b = (int)(c & 1);
+                const size_t c0 = c * chunk, c1 = std::min(nq, c0 + chunk);
+                const size_t lo = std::max(c0, my_lo), hi = std::min(c1, my_hi);
+                for (int p = 0; p < W; ++p) CU(cudaStreamWaitEvent(st, ps.ev_scan[b][p], 0));   // every rank's lists of chunk c are packed
+                CU(cudaEventRecord(EV(c, 2), st));
+                if (hi > lo) {
+                    const size_t cnt = hi - lo;
+                    merge_packed_peer_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(
+                        reinterpret_cast<const unsigned long long* const*>(ptrs.p) + (size_t)b * W, (uint32_t)W, lo - c0, (uint32_t)cnt, (uint32_t)k,
+                        idx_out + (lo - my_lo) * k, (float*)dist_outv + (lo - my_lo) * k);
+                    CU(cudaGetLastError());
+                    ++counters.kernel_launches;
+                    rows_out += cnt;
+                    peer_bytes += (unsigned long long)(W - 1) * cnt * k * 8;
+                }
+                CU(cudaEventRecord(EV(c, 3), st));
+                CU(cudaEventRecord(ps.ev_merge[b][R], st));
+                return PN_OK;
+            };
+            for (size_t c = 0; c < n_chunks; ++c) {
+                const int b = (int)(c & 1);
+                const size_t c0 = c * chunk, c1 = std::min(nq, c0 + chunk);
+                const uint32_t cq = (uint32_t)(c1 - c0);
+                if (c >= 2) {  // my packed buffer b was read by every rank's merge of chunk c-2
+                    if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");
+                    for (int p = 0; p < W; ++p) CU(cudaStreamWaitEvent(st, ps.ev_merge[b][p], 0));
+                }
+                CU(cudaEventRecord(EV(c, 0), st));
+                TRY(knn_device(q + c0 * stride, cq, stride, (uint32_t)k, sh_li[b].as<uint64_t>(), sh_ld[b].as<A>(), st));
+                const size_t cnt = (size_t)cq * k;
+                pack_lists_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(sh_li[b].as<uint64_t>(), (const float*)sh_ld[b].p, cnt,
+                                                                                 sh_pack[b].as<unsigned long long>());
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+                CU(cudaEventRecord(EV(c, 1), st));
+                CU(cudaEventRecord(ps.ev_scan[b][R], st));
+                if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");   // all ranks have recorded their scan event of chunk c
+                if (c >= 1) TRY(merge_chunk(c - 1));
+            }
+            TRY(merge_chunk(n_chunks - 1));
+            CU(cudaEventRecord(ev[1], st));
+            CU(cudaStreamSynchronize(st));
+            // nobody may free or reuse a packed buffer while a peer still reads it
+            if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");
+            guard.ok = true;
+            if (stats) {
+                float ms = 0.f;
+                for (size_t c = 0; c < n_chunks; ++c) {
+                    if (cudaEventElapsedTime(&ms, EV(c, 0), EV(c, 1)) == cudaSuccess) stats->scan_ms += ms;
+                    if (cudaEventElapsedTime(&ms, EV(c, 2), EV(c, 3)) == cudaSuccess) stats->merge_ms += ms;   // includes the peer loads
+                }
+                if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stats->total_ms = ms;
+                (void)cudaGetLastError();
+                stats->nccl_bytes_sent = 0; stats->nccl_calls = 0; stats->rows_out = rows_out; stats->n_chunks = (uint32_t)n_chunks;
+                stats->reserved = (uint32_t)std::min<unsigned long long>(peer_bytes >> 20, 0xffffffffull);   // MiB read from peers
+            }
+            return fetch_counters(st, nq);
+        }
+    }
+
     // ---- replication of the flattened tree over NCCL (query sharding: build once, broadcast) ------------------------------
     struct ReplicaHeader {
         uint64_t n, n_total;
@@ -1906,6 +2035,9 @@ struct pn_multi {
     std::vector<pn_tree*> trees;
     std::vector<pn_shard_stats> stats;
     std::vector<DevBuf> q_dev, idx_dev, dist_dev;  // BY_SUBTREE: all queries / this device's result slice
+    PeerShared peer;                                // PEER exchange: shared by the rank threads of a query
+    bool peer_ok = false;                           // every pair of devices has peer access
+    uint32_t exchange = PN_EXCHANGE_SLICE;
     ~pn_multi() {
         for (size_t i = 0; i < trees.size(); ++i) {
             if (!trees[i]) continue;
@@ -1919,6 +2051,11 @@ struct pn_multi {
                 if (r < (int)q_dev.size()) { q_dev[r].release(); idx_dev[r].release(); dist_dev[r].release(); }
             }
         }
+        for (int b = 0; b < 2; ++b)
+            for (size_t r = 0; r < peer.ev_scan[b].size(); ++r) {
+                if (peer.ev_scan[b][r]) cudaEventDestroy(peer.ev_scan[b][r]);
+                if (peer.ev_merge[b][r]) cudaEventDestroy(peer.ev_merge[b][r]);
+            }
         for (pn_comm* c : comms) pn_comm_destroy(c);
     }
 };
@@ -1972,6 +2109,30 @@ int32_t pn_multi_balltree_create_f32(const int32_t* devices, int32_t n_dev, uint
             orr.device = devices[r]; orr.shard_depth = depth; orr.shard_index = (uint32_t)r;
             return (int)pn_balltree_create_f32(points, n, d, rs, 1, &orr, &m->trees[r]);
         }));
+        // peer access between every pair of devices: the merge kernels then read the other shards' lists in place
+        m->peer_ok = true;
+        for (int i = 0; i < n_dev; ++i)
+            for (int j = 0; j < n_dev; ++j) {
+                if (devices[i] == devices[j]) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) { m->peer_ok = false; continue; }
+                DeviceGuard g(devices[i]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) m->peer_ok = false;
+                (void)cudaGetLastError();
+            }
+        m->peer.n = n_dev;
+        for (int b = 0; b < 2; ++b) {
+            m->peer.pack[b].assign(n_dev, nullptr);
+            m->peer.ev_scan[b].assign(n_dev, nullptr);
+            m->peer.ev_merge[b].assign(n_dev, nullptr);
+            for (int r = 0; r < n_dev; ++r) {
+                DeviceGuard g(devices[r]);
+                CU(cudaEventCreateWithFlags(&m->peer.ev_scan[b][r], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&m->peer.ev_merge[b][r], cudaEventDisableTiming));
+            }
+        }
+        if (m->peer_ok) m->exchange = PN_EXCHANGE_PEER;
     }
     *out = m.release();
     return PN_OK;
@@ -1984,6 +2145,7 @@ int32_t pn_multi_balltree_query_f32(pn_multi* m, const float* q, size_t nq, size
     if (!q || !idx_out || !dist_out) return fail(PN_BAD_ARG, "null pointer");
     if (nq > 1 && qs < m->d) return fail(PN_BAD_ARG, "q_row_stride < dimension");
     const int W = m->n_dev;
+    { std::lock_guard<std::mutex> lk(m->peer.mu); m->peer.failed = false; m->peer.count = 0; }
     return on_every_rank(W, [&](int r) -> int {
         size_t lo, hi;
         pn_query_slice(nq, r, W, &lo, &hi);
@@ -2001,8 +2163,12 @@ int32_t pn_multi_balltree_query_f32(pn_multi* m, const float* q, size_t nq, size
         TRY(m->idx_dev[r].ensure(std::max<size_t>(rows, 1) * k * 8));
         TRY(m->dist_dev[r].ensure(std::max<size_t>(rows, 1) * k * 4));
         CU(cudaMemcpy2D(m->q_dev[r].p, d * 4, q, std::max(qs, d) * 4, d * 4, nq, cudaMemcpyHostToDevice));
-        TRY(pn_sharded_query_knn_dev(m->trees[r], m->comms[r], m->q_dev[r].p, nq, d, k, PN_EXCHANGE_SLICE, m->idx_dev[r].as<uint64_t>(),
-                                     m->dist_dev[r].p, nullptr, &m->stats[r]));
+        if (m->exchange == PN_EXCHANGE_PEER) {
+            TRY(m->trees[r]->knn_sharded_peer(m->peer, r, W, m->q_dev[r].p, nq, d, k, m->idx_dev[r].as<uint64_t>(), m->dist_dev[r].p, &m->stats[r]));
+        } else {
+            TRY(pn_sharded_query_knn_dev(m->trees[r], m->comms[r], m->q_dev[r].p, nq, d, k, PN_EXCHANGE_SLICE, m->idx_dev[r].as<uint64_t>(),
+                                         m->dist_dev[r].p, nullptr, &m->stats[r]));
+        }
         if (rows) {
             CU(cudaMemcpy(idx_out + lo * k, m->idx_dev[r].p, rows * k * 8, cudaMemcpyDeviceToHost));
             CU(cudaMemcpy(dist_out + lo * k, m->dist_dev[r].p, rows * k * 4, cudaMemcpyDeviceToHost));
@@ -2010,6 +2176,13 @@ int32_t pn_multi_balltree_query_f32(pn_multi* m, const float* q, size_t nq, size
         return PN_OK;
     });
     GUARD_END
+}
+int32_t pn_multi_set_exchange(pn_multi* m, uint32_t exchange) {
+    if (!m) return fail(PN_BAD_ARG, "handle is null");
+    if (exchange != PN_EXCHANGE_SLICE && exchange != PN_EXCHANGE_PEER) return fail(PN_BAD_ARG, "the exchange of a multi-GPU handle is SLICE or PEER");
+    if (exchange == PN_EXCHANGE_PEER && !m->peer_ok) return fail(PN_BAD_ARG, "peer access is not available between every pair of devices");
+    m->exchange = exchange;
+    return PN_OK;
 }
 int32_t pn_multi_get_stats(const pn_multi* m, pn_shard_stats* stats, int32_t n_stats) {
     if (!m || !stats) return fail(PN_BAD_ARG, "null pointer");

@@ -563,6 +563,30 @@ __global__ void merge_packed_kernel(const unsigned long long* __restrict__ lists
     }
 }
 
+// The same merge with the lists read where they were produced: lists[l] is the packed list buffer of rank l -- for l != this
+// rank a PEER pointer, so the loads cross NVLink inside the merge kernel and no collective runs at all (one process driving
+// several GPUs, pn_multi_*).  Rows [row_off, row_off + nq) of every rank's chunk buffer are merged.
+__global__ void merge_packed_peer_kernel(const unsigned long long* const* __restrict__ lists, uint32_t n_lists, size_t row_off, uint32_t nq,
+                                         uint32_t k, uint64_t* __restrict__ out_i, float* __restrict__ out_d) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint8_t head[64];
+    for (uint32_t l = 0; l < n_lists; ++l) head[l] = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        unsigned long long best = ~0ull;
+        int bl = -1;
+        for (uint32_t l = 0; l < n_lists; ++l) {
+            if (head[l] >= k) continue;
+            const unsigned long long key = lists[l][(row_off + q) * k + head[l]];
+            if (bl < 0 || key < best) { best = key; bl = (int)l; }
+        }
+        if (bl >= 0) ++head[bl];
+        const uint32_t id = (uint32_t)best;
+        out_d[(size_t)q * k + i] = __uint_as_float((uint32_t)(best >> 32));
+        out_i[(size_t)q * k + i] = (bl < 0 || id == NO_ID) ? ~0ull : (uint64_t)id;
+    }
+}
+
 // ---- query staging ----------------------------------------------------------------------------
 template <typename A>
 __global__ void pad_queries_kernel(const A* __restrict__ q, size_t q_stride, uint32_t nq, uint32_t d, uint32_t dpad,

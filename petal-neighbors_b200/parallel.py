@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import BallTree, _Tree, _check, _ffi, merge_topk_dev  # noqa: F401
-from ._ffi import PN_EXCHANGE_ALLGATHER, PN_EXCHANGE_SLICE, PN_SHARD_BY_SUBTREE, PN_SHARD_REPLICATE
+from ._ffi import PN_EXCHANGE_ALLGATHER, PN_EXCHANGE_PEER, PN_EXCHANGE_SLICE, PN_SHARD_BY_SUBTREE, PN_SHARD_REPLICATE
 
 
 def query_slice(n_queries: int, rank: int, world: int):
@@ -184,6 +184,11 @@ class MultiGpuBallTree:
         dist = np.empty((nq, k), np.float32)
         _check(_ffi.lib().pn_multi_balltree_query_f32(self._h, Q.ctypes.data, nq, self.dim, k, idx.ctypes.data, dist.ctypes.data))
         return idx, dist
+
+    def set_exchange(self, exchange: int):
+        """BY_SUBTREE handles: PN_EXCHANGE_PEER (merge kernels read the other devices' lists over NVLink, no collective; the
+        default when every pair of devices has peer access) or PN_EXCHANGE_SLICE (grouped ncclSend / ncclRecv)."""
+        _check(_ffi.lib().pn_multi_set_exchange(self._h, exchange))
 
     def stats(self):
         arr = (_ffi.ShardStats * len(self.devices))()

@@ -120,12 +120,19 @@ def test_multi_gpu_handle(pn, oracle, mode):
     pts = synth.fast_gaussian_mixture(n, d, 9, n_centers=128, sigma=0.05)
     Q = synth.fast_gaussian_mixture(nq, d, 10, n_centers=128, sigma=0.05)
     m = parallel.MultiGpuBallTree(pts, list(range(world)), mode=mode)
-    idx, dist = m.query_batch(Q, k)
     sample = np.arange(0, nq, nq // 300)[:300]
     oi, od = oracle.brute_knn(pts, Q[sample], k)
-    assert np.array_equal(idx[sample], oi.astype(np.uint64)) and np.array_equal(bits(dist[sample]), bits(od))
-    st = m.stats()
-    assert sum(s["rows_out"] for s in st) == nq
-    if mode == 1 and world > 1:
-        assert all(s["nccl_bytes_sent"] > 0 for s in st)
+    # BY_SUBTREE: first the default exchange (merge kernels read the peers' lists over NVLink, no collective), then NCCL
+    for exchange in ((None, parallel.PN_EXCHANGE_SLICE) if mode == 1 else (None,)):
+        if exchange is not None:
+            m.set_exchange(exchange)
+        idx, dist = m.query_batch(Q, k)
+        assert np.array_equal(idx[sample], oi.astype(np.uint64)) and np.array_equal(bits(dist[sample]), bits(od))
+        st = m.stats()
+        assert sum(s["rows_out"] for s in st) == nq
+        if mode == 1 and world > 1:
+            if exchange is None:
+                assert all(s["nccl_calls"] == 0 and s["reserved"] > 0 for s in st)      # MiB read from peer memory
+            else:
+                assert all(s["nccl_bytes_sent"] > 0 for s in st)
     m.close()
