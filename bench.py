@@ -433,6 +433,22 @@ def extra_multi_gpu(pn, torch, dist, synth, comm, rank, world, local, steps):
     out["sharded_t128"] = {"workload": "BallTree 10M x 128 f32 sharded by the depth-log2(N) subtrees, every rank scans ALL 1M queries, k=10; "
                                        "per-shard lists exchanged over NCCL and merged (the structure of BASELINE config 5)",
                            "n_gpus": world, "points_per_rank": st.tree.info()["n_points"], "shard_build_seconds": shard_build_s, **arms}
+    # ---- the same sharding from ONE process (pn_multi_*): merge kernels read the other devices' lists over NVLink, no
+    # collective.  Runs as a child process of rank 0 with a time limit while every rank's GPU is idle (the ranks wait at a
+    # CPU-side barrier, never inside an NCCL kernel), so that a failure there cannot take the bench line down.
+    del st, q_all
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    cpu_group = dist.new_group(backend="gloo")
+    dist.barrier(group=cpu_group)
+    if rank == 0:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "multi_arm.py"), str(world)], capture_output=True, text=True, timeout=420)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            out["multi_one_process"] = json.loads(line[-1]) if line else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as e:  # noqa
+            out["multi_one_process"] = {"error": repr(e)}
+    dist.barrier(group=cpu_group)
     return out
 
 
@@ -456,8 +472,8 @@ def main():
         run_reference_arm(args)
         return
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout; stdout carries the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "NONE"   # NCCL prints its version banner on stdout; stdout carries the one JSON line
     import torch
     import torch.distributed as dist
     import petal_neighbors_b200 as pn

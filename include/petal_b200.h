@@ -242,7 +242,8 @@ typedef struct pn_shard_stats {
     uint64_t nccl_bytes_sent; /* payload bytes this rank sent to OTHER ranks */
     uint64_t nccl_calls;
     uint64_t rows_out;   /* result rows written on this rank */
-    uint32_t n_chunks, reserved;
+    uint32_t n_chunks;
+    uint32_t peer_mib;   /* PEER exchange: MiB this rank's merge kernels read from other devices' memory */
 } pn_shard_stats;
 
 /* contiguous slice [*lo, *hi) of a batch of nq queries owned by `rank` (sizes differ by at most one) */

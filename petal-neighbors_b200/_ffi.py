@@ -41,7 +41,7 @@ PN_UNIQUE_ID_BYTES = 128
 class ShardStats(C.Structure):
     _fields_ = [("scan_ms", C.c_double), ("exchange_ms", C.c_double), ("merge_ms", C.c_double), ("total_ms", C.c_double),
                 ("nccl_bytes_sent", C.c_uint64), ("nccl_calls", C.c_uint64), ("rows_out", C.c_uint64),
-                ("n_chunks", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_chunks", C.c_uint32), ("peer_mib", C.c_uint32)]
 
 
 class BuildOpts(C.Structure):

@@ -1488,7 +1488,7 @@ struct Engine final : pn_tree {
                 if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stats->total_ms = ms;
                 (void)cudaGetLastError();
                 stats->nccl_bytes_sent = 0; stats->nccl_calls = 0; stats->rows_out = rows_out; stats->n_chunks = (uint32_t)n_chunks;
-                stats->reserved = (uint32_t)std::min<unsigned long long>(peer_bytes >> 20, 0xffffffffull);   // MiB read from peers
+                stats->peer_mib = (uint32_t)std::min<unsigned long long>((peer_bytes + (1u << 20) - 1) >> 20, 0xffffffffull);
             }
             return fetch_counters(st, nq);
         }

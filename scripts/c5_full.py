@@ -16,8 +16,8 @@ import os
 import sys
 import time
 
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (the JSON line)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"   # keep NCCL's version banner off stdout (the JSON line)
 import numpy as np
 import torch
 import torch.distributed as dist

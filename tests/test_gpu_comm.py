@@ -132,7 +132,7 @@ def test_multi_gpu_handle(pn, oracle, mode):
         assert sum(s["rows_out"] for s in st) == nq
         if mode == 1 and world > 1:
             if exchange is None:
-                assert all(s["nccl_calls"] == 0 and s["reserved"] > 0 for s in st)      # MiB read from peer memory
+                assert all(s["nccl_calls"] == 0 and s["peer_mib"] > 0 for s in st)     # read from peer memory, no collective
             else:
                 assert all(s["nccl_bytes_sent"] > 0 for s in st)
     m.close()
