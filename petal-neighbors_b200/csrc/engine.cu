@@ -1,6 +1,7 @@
-// engine.cu -- host side of libpetal_b200.so: tree handles, workspaces, kernel launches and the
-// C ABI declared in include/petal_b200.h.  No CPU fallback: every query entry point launches the
-// sm_100a kernels of kernels.cuh or fails with PN_CUDA.
+// engine.cu -- host side of libpetal_b200.so: tree handles, workspaces, launch plans, the pipelined host-buffer calls,
+// the NCCL / peer-memory multi-GPU paths and the C ABI declared in include/petal_b200.h.  No CPU fallback: every query
+// entry point launches the sm_100a kernels of kernels.cuh / tc_filter.cuh / tc_prune.cuh or fails with PN_CUDA; trees
+// are built by flat_tree.hpp (host) or gpu_build.cu (device).
 #include <sys/mman.h>
 
 #include <chrono>

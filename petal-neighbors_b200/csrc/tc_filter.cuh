@@ -4,9 +4,10 @@
 // prune nothing, pairs/(N*Q) ~ 1), the distance matrix is evaluated on the 5th-gen tensor cores as
 //     D~^2(q,p) = |q'|^2 + |p'|^2 - 2 q'.p'      (q' = s (q - c), p' = s (p - c); c = data mean,
 //                                                  s = power of two with max |p'_j| <= 1)
-// by ONE augmented FP16 contraction (fp32 accumulate): A row = [q'_0 .. q'_{d-1}, 0.., n1, n2, n3,
-// 1, 1, 1] with |q'|^2 = n1+n2+n3 split into fp16 pieces, B row = [-2p'_0 .., 0.., 1, 1, 1, m1, m2,
-// m3], so the TMEM accumulator holds D~^2 itself and the epilogue is a bare threshold test.  FP16
+// by ONE augmented FP16 contraction (fp32 accumulate): A row = [q'_0 .. q'_{d-1}, n1, n2, n3, 1, 1, 1,
+// 0..] with |q'|^2 = n1+n2+n3 split into fp16 pieces, B row = [-2p'_0 .., 1, 1, 1, m1, m2, m3, 0..], so
+// the TMEM accumulator holds D~^2 itself and the epilogue is a bare threshold test (the K steps of 16 that
+// hold nothing but the zero padding are never issued).  FP16
 // has the significand of TF32 at half the bytes (L2->SM operand traffic and shared-memory operand
 // reads both halve).
 // The filter is only a filter: every element with D~^2 <= Theta_q is re-evaluated with the exact
@@ -22,7 +23,8 @@
 // Queries whose scaled norm leaves the fp16 range get E_q = +inf: every point is reranked exactly.
 //
 // Structure (one CTA = MT x 128 queries, persistent over its share of the point tiles; 1 CTA / SM;
-// MT x NUM_ACC x 128 = the 512 TMEM columns: 2 subtiles x 2 stages for wide rows, 4 x 1 for narrow ones):
+// MT x NUM_ACC x SW = the 512 TMEM columns: 2 subtiles x 2 stages x 128 for wide rows, 4 x 1 x 128 for two or three
+// K chunks, 4 x 2 x 64 -- half-tile stages -- for one K chunk):
 //   warps 4MT, 5MT+1 : two producers on alternate ring groups: 1-D bulk copies (cp.async.bulk) of the
 //                pre-tiled, pre-swizzled B image ([128 rows x 32 fp16] chunks, 64B swizzle)
 //   warps 4MT+1.. : MT tcgen05.mma issuers, one per 128-query subtile: the whole warp runs the loop on
@@ -33,6 +35,8 @@
 //                    + sorted insertion into the owning thread's top-k (shared memory)
 // grid.y splits the point stream (small batches, the last partial wave of large ones); the splits of a
 // query share their k-th bounds through global memory and merge_lists_kernel merges their lists.
+// Seeds and pruning (tc_prune.cuh): a query may start from a seed threshold instead of +inf (FilterArgs::seed_t2), and
+// the PRUNE instantiation scans only the tiles of the CTA's bitmap, every role walking the bitmap on its own.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
