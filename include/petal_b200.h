@@ -237,7 +237,7 @@ typedef enum pn_exchange {
 typedef struct pn_shard_stats {
     double scan_ms;      /* sum over chunks: local tensor/SIMT scan + packing, CUDA events on the compute stream */
     double exchange_ms;  /* sum over chunks: the NCCL calls, CUDA events on the exchange stream (overlaps the next scan) */
-    double merge_ms;     /* sum over chunks: k-way merge kernels */
+    double merge_ms;     /* sum over chunks: k-way merge kernels (PEER exchange: end of this rank's last scan to the end of its last merge) */
     double total_ms;     /* first enqueue to last merge */
     uint64_t nccl_bytes_sent; /* payload bytes this rank sent to OTHER ranks */
     uint64_t nccl_calls;

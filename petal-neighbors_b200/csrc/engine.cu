@@ -80,8 +80,9 @@ using namespace petal;
 // host barrier the rank threads meet at (an event must have been RECORDED before another rank's stream can wait on it).
 struct PeerShared {
     int n = 0;
-    std::vector<const unsigned long long*> pack[2];   // [buffer][rank]
-    std::vector<cudaEvent_t> ev_scan[2], ev_merge[2]; // [buffer][rank]
+    size_t chunk = 0, n_chunks = 0;                           // the chunking of this query (the same on every rank)
+    std::vector<const unsigned long long*> pack;              // [rank] packed lists of ALL queries of this call
+    std::vector<std::vector<cudaEvent_t>> ev_scan;            // [rank][chunk]: lists of that chunk are packed
     std::mutex mu;
     std::condition_variable cv;
     int count = 0, gen = 0;
@@ -114,6 +115,7 @@ struct pn_tree {
     virtual int knn_sharded(pn_comm* cm, const void* q, size_t nq, size_t stride, size_t k, uint32_t exchange, uint64_t* idx, void* dist,
                             cudaStream_t st, pn_shard_stats* stats) = 0;
     virtual int replicate_send(pn_comm* cm, int root) = 0;
+    virtual size_t shard_chunk(size_t nq) const = 0;
     virtual int knn_sharded_peer(PeerShared& ps, int rank, int world, const void* q, size_t nq, size_t stride, size_t k, uint64_t* idx, void* dist,
                                  pn_shard_stats* stats) = 0;
 };
@@ -1258,9 +1260,7 @@ struct Engine final : pn_tree {
         constexpr bool PACKED = sizeof(A) == 4;
         // chunks of whole waves, about eight of them: the exchange of chunk i hides under the scan of chunk i+1, so only the
         // last chunk's exchange is exposed
-        const size_t wave = (size_t)n_sms * 512;
-        const size_t chunk = nq < 2 * wave ? nq : std::min<size_t>(std::max<size_t>(1, (nq / 8 + wave - 1) / wave) * wave, ((size_t)1 << 20) / wave * wave);
-        const size_t n_chunks = (nq + chunk - 1) / chunk;
+        const size_t chunk = shard_chunk(nq), n_chunks = (nq + chunk - 1) / chunk;
         auto slice = [&](int r, size_t& lo, size_t& hi) { pn_query_slice(nq, r, W, &lo, &hi); };
         size_t my_lo = 0, my_hi = nq;
         if (exchange == PN_EXCHANGE_SLICE) slice(R, my_lo, my_hi);
@@ -1391,10 +1391,17 @@ struct Engine final : pn_tree {
         return fetch_counters(st, nq);
     }
 
+    // whole waves per chunk, about eight chunks (see knn_sharded)
+    size_t shard_chunk(size_t nq) const override {
+        const size_t wave = (size_t)n_sms * 512;
+        return nq < 2 * wave ? nq : std::min<size_t>(std::max<size_t>(1, (nq / 8 + wave - 1) / wave) * wave, ((size_t)1 << 20) / wave * wave);
+    }
     // ---- point sharding by subtree WITHOUT a collective (one process, several GPUs): the merge kernel of every rank reads
-    // the other ranks' packed lists straight from their memory over NVLink.  Same chunking and double buffering as
-    // knn_sharded; the merge of chunk c-1 is queued behind the scan of chunk c, so waiting for the slowest rank's lists
-    // costs nothing while there is still a chunk to scan.
+    // the other ranks' packed lists straight from their memory over NVLink.  Every rank scans chunk after chunk on its own
+    // stream into ONE packed buffer covering all queries (8 k bytes per query), recording an event per chunk; after the
+    // rank threads have met once (an event must be recorded before another device's stream can wait on it), the merges of
+    // all chunks are queued on a second stream, each waiting for that chunk's events of every rank.  No rank's scan ever
+    // waits for another rank.
     int knn_sharded_peer(PeerShared& ps, int R, int W, const void* qv, size_t nq, size_t stride, size_t k, uint64_t* idx_out, void* dist_outv,
                          pn_shard_stats* stats) override {
         if constexpr (sizeof(A) != 4) {
@@ -1409,84 +1416,74 @@ struct Engine final : pn_tree {
             if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
             cudaStream_t st = stream;
             TRY(use_stream(st));
+            TRY(ensure_io());
+            cudaStream_t ms = s_out;   // the merge stream
             counters = pn_counters{};
             if (stats) *stats = pn_shard_stats{};
             const A* q = (const A*)qv;
-            const size_t wave = (size_t)n_sms * 512;
-            const size_t chunk = nq < 2 * wave ? nq : std::min<size_t>(std::max<size_t>(1, (nq / 8 + wave - 1) / wave) * wave, ((size_t)1 << 20) / wave * wave);
-            const size_t n_chunks = (nq + chunk - 1) / chunk;
+            const size_t chunk = ps.chunk, n_chunks = ps.n_chunks;
             size_t my_lo, my_hi;
             pn_query_slice(nq, R, W, &my_lo, &my_hi);
-            DevBuf& ptrs = sh_gat[0];  // [2][W] list pointers of every rank, per buffer
-            TRY(ptrs.ensure((size_t)2 * W * sizeof(void*)));
+            DevBuf& ptrs = sh_gat[0];    // [W] list pointers of every rank
+            DevBuf& packall = sh_gat[1]; // this rank's packed lists of all queries
+            TRY(ptrs.ensure((size_t)W * sizeof(void*)));
+            TRY(packall.ensure(nq * k * 8));
             for (int b = 0; b < 2; ++b) {
                 TRY(sh_li[b].ensure(chunk * k * 8));
                 TRY(sh_ld[b].ensure(chunk * k * 4));
-                TRY(sh_pack[b].ensure(chunk * k * 8));
-                ps.pack[b][R] = sh_pack[b].as<unsigned long long>();
             }
-            while (sh_ev.size() < 4 * n_chunks) { cudaEvent_t e; CU(cudaEventCreate(&e)); sh_ev.push_back(e); }
-            auto EV = [&](size_t c, int i) { return sh_ev[4 * c + i]; };  // 0,1 scan; 2,3 merge
-            if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");     // every rank's buffers exist
-            std::vector<const unsigned long long*> hp(2 * (size_t)W);
-            for (int b = 0; b < 2; ++b) for (int p = 0; p < W; ++p) hp[(size_t)b * W + p] = ps.pack[b][p];
-            CU(cudaMemcpyAsync(ptrs.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+            ps.pack[R] = packall.as<unsigned long long>();
+            while (sh_ev.size() < 2 * n_chunks + 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); sh_ev.push_back(e); }
+            auto EV = [&](size_t c, int i) { return sh_ev[2 * c + i]; };  // scan start / end of chunk c; the last two: merge start / end
             TRY(begin_call(st));
             CU(cudaEventRecord(ev[0], st));
-            unsigned long long rows_out = 0, peer_bytes = 0;
-            auto merge_chunk = [&](size_t c) -> int {
-                const int b = (int)(c & 1);
-                const size_t c0 = c * chunk, c1 = std::min(nq, c0 + chunk);
-                const size_t lo = std::max(c0, my_lo), hi = std::min(c1, my_hi);
-                for (int p = 0; p < W; ++p) CU(cudaStreamWaitEvent(st, ps.ev_scan[b][p], 0));   // every rank's lists of chunk c are packed
-                CU(cudaEventRecord(EV(c, 2), st));
-                if (hi > lo) {
-                    const size_t cnt = hi - lo;
-                    merge_packed_peer_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(
-                        reinterpret_cast<const unsigned long long* const*>(ptrs.p) + (size_t)b * W, (uint32_t)W, lo - c0, (uint32_t)cnt, (uint32_t)k,
-                        idx_out + (lo - my_lo) * k, (float*)dist_outv + (lo - my_lo) * k);
-                    CU(cudaGetLastError());
-                    ++counters.kernel_launches;
-                    rows_out += cnt;
-                    peer_bytes += (unsigned long long)(W - 1) * cnt * k * 8;
-                }
-                CU(cudaEventRecord(EV(c, 3), st));
-                CU(cudaEventRecord(ps.ev_merge[b][R], st));
-                return PN_OK;
-            };
             for (size_t c = 0; c < n_chunks; ++c) {
                 const int b = (int)(c & 1);
                 const size_t c0 = c * chunk, c1 = std::min(nq, c0 + chunk);
                 const uint32_t cq = (uint32_t)(c1 - c0);
-                if (c >= 2) {  // my packed buffer b was read by every rank's merge of chunk c-2
-                    if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");
-                    for (int p = 0; p < W; ++p) CU(cudaStreamWaitEvent(st, ps.ev_merge[b][p], 0));
-                }
                 CU(cudaEventRecord(EV(c, 0), st));
                 TRY(knn_device(q + c0 * stride, cq, stride, (uint32_t)k, sh_li[b].as<uint64_t>(), sh_ld[b].as<A>(), st));
                 const size_t cnt = (size_t)cq * k;
                 pack_lists_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(sh_li[b].as<uint64_t>(), (const float*)sh_ld[b].p, cnt,
-                                                                                 sh_pack[b].as<unsigned long long>());
+                                                                                 packall.as<unsigned long long>() + c0 * k);
                 CU(cudaGetLastError());
                 ++counters.kernel_launches;
                 CU(cudaEventRecord(EV(c, 1), st));
-                CU(cudaEventRecord(ps.ev_scan[b][R], st));
-                if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");   // all ranks have recorded their scan event of chunk c
-                if (c >= 1) TRY(merge_chunk(c - 1));
+                CU(cudaEventRecord(ps.ev_scan[R][c], st));
             }
-            TRY(merge_chunk(n_chunks - 1));
+            if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");   // every rank's buffers exist and all scan events are recorded
+            std::vector<const unsigned long long*> hp(ps.pack.begin(), ps.pack.end());
+            CU(cudaMemcpyAsync(ptrs.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, ms));
+            unsigned long long rows_out = 0, peer_bytes = 0;
+            CU(cudaEventRecord(EV(n_chunks, 0), ms));
+            for (size_t c = 0; c < n_chunks; ++c) {
+                const size_t c0 = c * chunk, c1 = std::min(nq, c0 + chunk);
+                const size_t lo = std::max(c0, my_lo), hi = std::min(c1, my_hi);
+                if (hi <= lo) continue;
+                for (int p = 0; p < W; ++p) CU(cudaStreamWaitEvent(ms, ps.ev_scan[p][c], 0));   // every rank's lists of chunk c are packed
+                const size_t cnt = hi - lo;
+                merge_packed_peer_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, ms>>>(
+                    reinterpret_cast<const unsigned long long* const*>(ptrs.p), (uint32_t)W, lo, (uint32_t)cnt, (uint32_t)k,
+                    idx_out + (lo - my_lo) * k, (float*)dist_outv + (lo - my_lo) * k);
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+                rows_out += cnt;
+                peer_bytes += (unsigned long long)(W - 1) * cnt * k * 8;
+            }
+            CU(cudaEventRecord(EV(n_chunks, 1), ms));
+            CU(cudaStreamWaitEvent(st, EV(n_chunks, 1), 0));
             CU(cudaEventRecord(ev[1], st));
             CU(cudaStreamSynchronize(st));
             // nobody may free or reuse a packed buffer while a peer still reads it
             if (!ps.barrier()) return fail(PN_CUDA, "another rank failed");
             guard.ok = true;
             if (stats) {
-                float ms = 0.f;
-                for (size_t c = 0; c < n_chunks; ++c) {
-                    if (cudaEventElapsedTime(&ms, EV(c, 0), EV(c, 1)) == cudaSuccess) stats->scan_ms += ms;
-                    if (cudaEventElapsedTime(&ms, EV(c, 2), EV(c, 3)) == cudaSuccess) stats->merge_ms += ms;   // includes the peer loads
-                }
-                if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stats->total_ms = ms;
+                float ms_ = 0.f;
+                for (size_t c = 0; c < n_chunks; ++c)
+                    if (cudaEventElapsedTime(&ms_, EV(c, 0), EV(c, 1)) == cudaSuccess) stats->scan_ms += ms_;
+                // exposed tail: end of this rank's last scan to the end of its last merge (waits for the slowest rank included)
+                if (cudaEventElapsedTime(&ms_, EV(n_chunks - 1, 1), EV(n_chunks, 1)) == cudaSuccess) stats->merge_ms = ms_;
+                if (cudaEventElapsedTime(&ms_, ev[0], ev[1]) == cudaSuccess) stats->total_ms = ms_;
                 (void)cudaGetLastError();
                 stats->nccl_bytes_sent = 0; stats->nccl_calls = 0; stats->rows_out = rows_out; stats->n_chunks = (uint32_t)n_chunks;
                 stats->peer_mib = (uint32_t)std::min<unsigned long long>((peer_bytes + (1u << 20) - 1) >> 20, 0xffffffffull);
@@ -2052,11 +2049,8 @@ struct pn_multi {
                 if (r < (int)q_dev.size()) { q_dev[r].release(); idx_dev[r].release(); dist_dev[r].release(); }
             }
         }
-        for (int b = 0; b < 2; ++b)
-            for (size_t r = 0; r < peer.ev_scan[b].size(); ++r) {
-                if (peer.ev_scan[b][r]) cudaEventDestroy(peer.ev_scan[b][r]);
-                if (peer.ev_merge[b][r]) cudaEventDestroy(peer.ev_merge[b][r]);
-            }
+        for (auto& v : peer.ev_scan)
+            for (cudaEvent_t e : v) if (e) cudaEventDestroy(e);
         for (pn_comm* c : comms) pn_comm_destroy(c);
     }
 };
@@ -2123,16 +2117,8 @@ int32_t pn_multi_balltree_create_f32(const int32_t* devices, int32_t n_dev, uint
                 (void)cudaGetLastError();
             }
         m->peer.n = n_dev;
-        for (int b = 0; b < 2; ++b) {
-            m->peer.pack[b].assign(n_dev, nullptr);
-            m->peer.ev_scan[b].assign(n_dev, nullptr);
-            m->peer.ev_merge[b].assign(n_dev, nullptr);
-            for (int r = 0; r < n_dev; ++r) {
-                DeviceGuard g(devices[r]);
-                CU(cudaEventCreateWithFlags(&m->peer.ev_scan[b][r], cudaEventDisableTiming));
-                CU(cudaEventCreateWithFlags(&m->peer.ev_merge[b][r], cudaEventDisableTiming));
-            }
-        }
+        m->peer.pack.assign(n_dev, nullptr);
+        m->peer.ev_scan.assign(n_dev, {});
         if (m->peer_ok) m->exchange = PN_EXCHANGE_PEER;
     }
     *out = m.release();
@@ -2147,6 +2133,19 @@ int32_t pn_multi_balltree_query_f32(pn_multi* m, const float* q, size_t nq, size
     if (nq > 1 && qs < m->d) return fail(PN_BAD_ARG, "q_row_stride < dimension");
     const int W = m->n_dev;
     { std::lock_guard<std::mutex> lk(m->peer.mu); m->peer.failed = false; m->peer.count = 0; }
+    if (m->mode == PN_SHARD_BY_SUBTREE && m->exchange == PN_EXCHANGE_PEER) {
+        // the chunking of this call and one scan event per (rank, chunk), created on the rank's device
+        m->peer.chunk = m->trees[0]->shard_chunk(nq);
+        m->peer.n_chunks = (nq + m->peer.chunk - 1) / m->peer.chunk;
+        for (int r = 0; r < W; ++r) {
+            DeviceGuard g(m->devices[r]);
+            while (m->peer.ev_scan[r].size() < m->peer.n_chunks) {
+                cudaEvent_t e;
+                CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                m->peer.ev_scan[r].push_back(e);
+            }
+        }
+    }
     return on_every_rank(W, [&](int r) -> int {
         size_t lo, hi;
         pn_query_slice(nq, r, W, &lo, &hi);

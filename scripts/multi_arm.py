@@ -32,7 +32,7 @@ ref = None
 for name, ex in (("peer", None), ("nccl_slice", parallel.PN_EXCHANGE_SLICE)):
     if ex is not None:
         m.set_exchange(ex)
-    m.query_batch(Q[: min(nq, 100_000)], k)   # warm-up (buffers, NCCL channels)
+    m.query_batch(Q, k)   # warm-up at full size (buffers of every rank at their final size, NCCL channels)
     t0 = time.perf_counter()
     idx, dist = m.query_batch(Q, k)
     wall = time.perf_counter() - t0
