@@ -551,10 +551,18 @@ struct Engine final : pn_tree {
             if (dt.dv == 4) return launch_filter_t<4, K, 2, 2>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 2, 2>(map_a, fa, st);
 #ifdef PN_TC_PROFILE
-            // experiment (PN_TC_TS=1, diagnostic builds): two subtiles x ONE stage with the A operand in tensor memory.
-            // Bit-exact, and the MMA drops from 85 to 70 cycles, but the single accumulator stage serialises MMA and
-            // read-out of a subtile: 10M-shaped d = 128 scan 70.4 -> 74.0 ms (scripts/ts_test.sh).  Not used.
-            if (getenv("PN_TC_TS") && atoi(getenv("PN_TC_TS")) != 0) return launch_filter_t<0, K, 2, 1>(map_a, fa, st);
+            // Experiments (diagnostic builds): the A operand in tensor memory (TS-form MMA).  scripts/mma_rate.cu, two
+            // issuers, cycles per 128 accumulator columns: SS N=128 86.5 (= the 64-cycle floor + 22 of operand fetch),
+            // TS N=128 70, TS N=64 78.4.  Two whole-tile stages per subtile AND the operands (2 x 2 x 128 + 2 x 72 columns at
+            // d = 128) do not fit the 512 columns, and both arrangements that fit lose to the SS kernel:
+            //   PN_TC_TS=2: ONE whole-tile stage per subtile: MMA and read-out of a subtile serialise, 10M x 128 scan 70.4 -> 74.0 ms
+            //   PN_TC_TS=1: TWO half-tile stages per subtile (N = 64 MMAs): twice the stage hand-overs, 368 -> 436 ms
+            //               (151 552 queries; profiles/r02_mma_rate.md).  Both bit-exact.
+            {
+                static const int ts = getenv("PN_TC_TS") ? atoi(getenv("PN_TC_TS")) : 0;
+                if (ts == 1 && fa.nkc <= 8) return launch_filter_t<0, K, 2, 2, 64>(map_a, fa, st);
+                if (ts == 2) return launch_filter_t<0, K, 2, 1>(map_a, fa, st);
+            }
 #endif
             return launch_filter_t<0, K, 2, 2>(map_a, fa, st);
         }

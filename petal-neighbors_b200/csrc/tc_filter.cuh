@@ -365,12 +365,14 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
     // Wide rows with one accumulator stage per subtile keep the A operand in tensor memory (TS-form MMA): the pipe then
     // reads only B from shared memory (measured 70 instead of 85 cycles per 128x128x16 MMA, scripts/mma_rate.cu).
     // Columns: MT accumulators of 128, then MT A operands of Kp/2 (two fp16 per column), 512 allocated.
-    constexpr bool TS = MT == 2 && NUM_ACC == 1;
+    // With half-tile stages (SW = 64) the two subtiles keep TWO accumulator stages each next to their A operands:
+    // 2 x 2 x 64 accumulator columns + 2 x nkc x 16 operand columns <= 512 up to nkc = 8.
+    constexpr bool TS = MT == 2 && (NUM_ACC == 1 || SW == 64);
     constexpr int TMEM_COLS = TS ? 512 : NUM_ACC * MT * SW;  // power of two
     // accumulator units per B tile: a stage holds SW columns, i.e. the distances of 128 queries to SW of the tile's 128
     // points; with SW = 64 the four-subtile configuration gets TWO stages per subtile out of the same 512 columns
     constexpr int U = BN / SW;
-    static_assert(SW == BN || (SW == 64 && !TS), "stage width is a whole tile or half a tile");
+    static_assert(SW == BN || SW == 64, "stage width is a whole tile or half a tile");
 
     if (warp == EPI_WARPS && lane == 0) {
         for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MT); }
@@ -459,7 +461,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             mbar_wait(a_bar, 0);
             // TS: this subtile's A operand goes to tensor memory once, K step by K step (copies and MMAs issued by one
             // thread execute in order)
-            const uint32_t a_tmem = tmem_base + MT * BN + mt * (a.nkc * 16);
+            const uint32_t a_tmem = tmem_base + NUM_ACC * MT * SW + mt * (a.nkc * 16);
             if (TS) {
                 tc_fence_after();
                 if (elect_one()) {
@@ -716,7 +718,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
         // The whole 128-column accumulator stage is pulled into registers at once and released
         // BEFORE it is tested: with only two stages in TMEM the MMA -> read-out -> release loop of a
         // stage is the critical path, so nothing but the TMEM loads may sit inside it.
-        if constexpr (MT <= 2) {
+        if constexpr (MT <= 2 && SW == BN) {
             constexpr int G = BN / 32;
             uint32_t r[G][32];
             const uint32_t lane_off = (uint32_t)(quad * 32) << 16;

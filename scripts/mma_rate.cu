@@ -176,6 +176,12 @@ int main() {
         {1, 4, 128, 2, 0, 4000, 1, 1, 2},
         {1, 4, 128, 1, 2, 4000, 1, 1, 2},
         {0, 4, 128, 1, 0, 4000, 0, 1, 2},   // f16 accumulate
+        {1, 4, 64, 1, 0, 4000, 1, 1, 2},    // TS N=64
+        {1, 4, 64, 2, 0, 4000, 1, 1, 2},    // TS N=64, two issuers
+        {0, 4, 64, 2, 0, 4000, 1, 1, 2},    // SS N=64, two issuers
+        {0, 4, 256, 2, 0, 4000, 1, 1, 2},   // SS N=256, two issuers
+        {1, 4, 256, 1, 0, 4000, 1, 1, 2},   // TS N=256
+        {1, 4, 192, 2, 0, 4000, 1, 1, 2},   // TS N=192, two issuers
     };
     for (int grid : {1}) {
         for (const Cfg& c : cfgs) {
