@@ -518,7 +518,20 @@ struct Engine final : pn_tree {
 #endif
         // measured (scripts/mt_sweep.sh, 1M points, k = 10): d = 16: 208 -> 165 ms; d = 64: 58.0 -> 51.0 ms; d = 96 (Kp = 128,
         // the resident A operand of four subtiles would take 128 KB): 68.1 -> 65.5 ms, not worth the shallow ring
+#ifdef PN_TC_PROFILE
+        // experiment (PN_TC_MT3=1): two or three chunks with at most five K steps of data (27 <= d <= 74): THREE subtiles
+        // with their A operands in tensor memory (TS-form MMA, 70 instead of 86.5 cycles).  Bit-exact, and slower: the
+        // one-stage subtiles are bound by the MMA -> read-out -> release chain, not by the pipe (1M x 64, 227 328
+        // queries, k = 1: 32.7 -> 36.6 ms; profiles/r02_mma_rate.md)
+        static const int mt3 = getenv("PN_TC_MT3") ? atoi(getenv("PN_TC_MT3")) : 0;
+        if (mt3 && nkc >= 2 && nkc <= 3 && ft.d + tc::NSLOT <= 80) return 3;
+#endif
         return nkc <= 3 ? 4 : (nkc <= 6 ? 2 : 1);
+    }
+    // queries per CTA of the scan this handle (or the ball tree behind a vantage-point handle) runs
+    size_t query_tile() const {
+        const Engine* e = aux ? aux.get() : this;
+        return e->tensor_ready ? (size_t)128 * e->filter_subtiles(e->kp / tc::KC) : 512;
     }
     template <int K>
     int launch_filter_k(const CUtensorMap& map_a, tc::FilterArgs& fa, cudaStream_t st) {
@@ -547,6 +560,9 @@ struct Engine final : pn_tree {
             if (dt.dv == 8) return launch_filter_t<8, K, 4, 1>(map_a, fa, st);
             return launch_filter_t<0, K, 4, 1>(map_a, fa, st);
         }
+#ifdef PN_TC_PROFILE
+        if (mt == 3) return launch_filter_t<0, K, 3, 1>(map_a, fa, st);
+#endif
         if (mt == 2) {
             if (dt.dv == 4) return launch_filter_t<4, K, 2, 2>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 2, 2>(map_a, fa, st);
@@ -943,7 +959,7 @@ struct Engine final : pn_tree {
     // enough to hide the copies (H2D of the second and D2H of the first run under the other's kernels) and keep the per-chunk
     // set-up (query staging, sort, seeds, a partial last wave) small; chunks are capped at 2^20 queries (workspace size).
     size_t host_chunk(size_t nq) const {
-        const size_t wave = (size_t)n_sms * 512;
+        const size_t wave = (size_t)n_sms * query_tile();
         if (nq < 4 * wave) return nq;
         const size_t half = ((nq + 1) / 2 + wave - 1) / wave * wave;
         return std::min<size_t>(half, ((size_t)1 << 20) / wave * wave);
@@ -1401,7 +1417,7 @@ struct Engine final : pn_tree {
 
     // whole waves per chunk, about eight chunks (see knn_sharded)
     size_t shard_chunk(size_t nq) const override {
-        const size_t wave = (size_t)n_sms * 512;
+        const size_t wave = (size_t)n_sms * query_tile();
         return nq < 2 * wave ? nq : std::min<size_t>(std::max<size_t>(1, (nq / 8 + wave - 1) / wave) * wave, ((size_t)1 << 20) / wave * wave);
     }
     // ---- point sharding by subtree WITHOUT a collective (one process, several GPUs): the merge kernel of every rank reads

@@ -367,7 +367,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
     // Columns: MT accumulators of 128, then MT A operands of Kp/2 (two fp16 per column), 512 allocated.
     // With half-tile stages (SW = 64) the two subtiles keep TWO accumulator stages each next to their A operands:
     // 2 x 2 x 64 accumulator columns + 2 x nkc x 16 operand columns <= 512 up to nkc = 8.
-    constexpr bool TS = MT == 2 && (NUM_ACC == 1 || SW == 64);
+    // THREE subtiles x one whole-tile stage (384 columns) leave 128 columns: three operands of up to five K steps
+    // (8 columns each), i.e. rows of up to 74 dimensions.
+    constexpr bool TS = (MT == 2 && (NUM_ACC == 1 || SW == 64)) || MT == 3;
     constexpr int TMEM_COLS = TS ? 512 : NUM_ACC * MT * SW;  // power of two
     // accumulator units per B tile: a stage holds SW columns, i.e. the distances of 128 queries to SW of the tile's 128
     // points; with SW = 64 the four-subtile configuration gets TWO stages per subtile out of the same 512 columns
@@ -461,14 +463,15 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_a, const unsigned char
             mbar_wait(a_bar, 0);
             // TS: this subtile's A operand goes to tensor memory once, K step by K step (copies and MMAs issued by one
             // thread execute in order)
-            const uint32_t a_tmem = tmem_base + NUM_ACC * MT * SW + mt * (a.nkc * 16);
+            const uint32_t a_ksteps = 2 * a.nkc - (a.last_steps > 1 ? 0u : 1u);   // K steps of 16 that carry data
+            const uint32_t a_tmem = tmem_base + NUM_ACC * MT * SW + mt * (a_ksteps * 8);
             if (TS) {
                 tc_fence_after();
                 if (elect_one()) {
                     for (uint32_t c = 0; c < a.nkc; ++c) {
                         const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
                         tc_cp_128x256b(a_tmem + c * 16, ad);
-                        tc_cp_128x256b(a_tmem + c * 16 + 8, ad + 2);
+                        if (c + 1 < a.nkc || a.last_steps > 1) tc_cp_128x256b(a_tmem + c * 16 + 8, ad + 2);
                     }
                 }
                 __syncwarp();
