@@ -141,7 +141,7 @@ struct Engine final : pn_tree {
     DevBuf w_qraw2[2], w_oi2[2], w_od2[2];
     DevBuf sh_li[2], sh_ld[2], sh_pack[2], sh_gat[2], sh_gat_d[2];   // sharded k-NN: local lists, packed keys, gathered lists
     std::vector<cudaEvent_t> sh_ev;                                    // timing events of the sharded pipeline (reused)
-    DevBuf r_qraw[2], r_q[2], r_counts[2], r_offsets[2], r_hits[2], r_slab[2], r_qlist[2], r_nlist[2];  // radius pipeline workspaces
+    DevBuf r_qraw[2], r_q[2], r_counts[2], r_offsets[2], r_hits[2], r_slab[2], r_qlist[2], r_nlist[2], r_sums[2];  // radius pipeline workspaces
     unsigned long long* pin_tot = nullptr;                            // pinned: chunk totals of the radius count pass
     void* pin_stage[2] = {nullptr, nullptr};  // pinned D2H staging for the variable-length radius output
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
@@ -181,7 +181,7 @@ struct Engine final : pn_tree {
                 if (pin_stage[i]) cudaFreeHost(pin_stage[i]);
                 if (pin_ev[i]) cudaEventDestroy(pin_ev[i]);
                 w_qraw2[i].release(); w_oi2[i].release(); w_od2[i].release();
-                r_qraw[i].release(); r_q[i].release(); r_counts[i].release(); r_offsets[i].release(); r_hits[i].release();
+                r_qraw[i].release(); r_q[i].release(); r_counts[i].release(); r_offsets[i].release(); r_hits[i].release(); r_sums[i].release();
                 r_slab[i].release(); r_qlist[i].release(); r_nlist[i].release();
                 sh_li[i].release(); sh_ld[i].release(); sh_pack[i].release(); sh_gat[i].release(); sh_gat_d[i].release();
                 for (cudaEvent_t e : {e_in[i], e_cmp[i], e_out[i]}) if (e) cudaEventDestroy(e);
@@ -518,13 +518,13 @@ struct Engine final : pn_tree {
 #endif
         // measured (scripts/mt_sweep.sh, 1M points, k = 10): d = 16: 208 -> 165 ms; d = 64: 58.0 -> 51.0 ms; d = 96 (Kp = 128,
         // the resident A operand of four subtiles would take 128 KB): 68.1 -> 65.5 ms, not worth the shallow ring
-#ifdef PN_TC_PROFILE
+#if defined(PN_TC_PROFILE) || defined(PN_TC_EXPERIMENTS)
         // experiment (PN_TC_MT3=1): two or three chunks with at most five K steps of data (27 <= d <= 74): THREE subtiles
         // with their A operands in tensor memory (TS-form MMA, 70 instead of 86.5 cycles).  Bit-exact, and slower: the
         // one-stage subtiles are bound by the MMA -> read-out -> release chain, not by the pipe (1M x 64, 227 328
         // queries, k = 1: 32.7 -> 36.6 ms; profiles/r02_mma_rate.md)
         static const int mt3 = getenv("PN_TC_MT3") ? atoi(getenv("PN_TC_MT3")) : 0;
-        if (mt3 && nkc >= 2 && nkc <= 3 && ft.d + tc::NSLOT <= 80) return 3;
+        if (mt3 && nkc <= 3 && ft.d + tc::NSLOT <= 80) return 3;
 #endif
         return nkc <= 3 ? 4 : (nkc <= 6 ? 2 : 1);
     }
@@ -560,13 +560,17 @@ struct Engine final : pn_tree {
             if (dt.dv == 8) return launch_filter_t<8, K, 4, 1>(map_a, fa, st);
             return launch_filter_t<0, K, 4, 1>(map_a, fa, st);
         }
-#ifdef PN_TC_PROFILE
-        if (mt == 3) return launch_filter_t<0, K, 3, 1>(map_a, fa, st);
+#if defined(PN_TC_PROFILE) || defined(PN_TC_EXPERIMENTS)
+        if (mt == 3) {
+            // one chunk: two half-tile stages per subtile (3 x 2 x 64 accumulator columns + 3 x 16 operand columns)
+            if (fa.nkc == 1) return dt.dv == 4 ? launch_filter_t<4, K, 3, 2, 64>(map_a, fa, st) : launch_filter_t<0, K, 3, 2, 64>(map_a, fa, st);
+            return launch_filter_t<0, K, 3, 1>(map_a, fa, st);
+        }
 #endif
         if (mt == 2) {
             if (dt.dv == 4) return launch_filter_t<4, K, 2, 2>(map_a, fa, st);
             if (dt.dv == 8) return launch_filter_t<8, K, 2, 2>(map_a, fa, st);
-#ifdef PN_TC_PROFILE
+#if defined(PN_TC_PROFILE) || defined(PN_TC_EXPERIMENTS)
             // Experiments (diagnostic builds): the A operand in tensor memory (TS-form MMA).  scripts/mma_rate.cu, two
             // issuers, cycles per 128 accumulator columns: SS N=128 86.5 (= the 64-cycle floor + 22 of operand fetch),
             // TS N=128 70, TS N=64 78.4.  Two whole-tile stages per subtile AND the operands (2 x 2 x 128 + 2 x 72 columns at
@@ -1170,6 +1174,7 @@ struct Engine final : pn_tree {
             TRYB(r_q[b].ensure(chunk * ft.dpad * sizeof(A)));
             TRYB(r_counts[b].ensure(chunk * 4));
             TRYB(r_offsets[b].ensure((chunk + 1) * 8));
+            TRYB(r_sums[b].ensure((chunk / SCAN_BLOCK + 1) * 8));
             TRYB(r_slab[b].ensure(chunk * RADIUS_CAP * 4));
             TRYB(r_qlist[b].ensure(chunk * 4));
             TRYB(r_nlist[b].ensure(16));
@@ -1192,8 +1197,11 @@ struct Engine final : pn_tree {
             radius_kernel<A, 0><<<blocks, wpb * 32, 0, s>>>(dt, r_q[b].as<V>(), cq, r, r_counts[b].as<uint32_t>(), nullptr, r_slab[b].as<uint32_t>(),
                                                            w_counters.as<unsigned long long>());
             CU(cudaGetLastError());
-            offsets_scan_kernel<<<1, 1024, 0, s>>>(r_counts[b].as<uint32_t>(), r_offsets[b].as<uint64_t>(), cq);
+            const unsigned sblocks = std::max(1u, (cq + SCAN_BLOCK - 1) / SCAN_BLOCK);
+            scan_sums_kernel<<<sblocks, 1024, 0, s>>>(r_counts[b].as<uint32_t>(), cq, r_sums[b].as<unsigned long long>());
+            offsets_scan_kernel<<<sblocks, 1024, 0, s>>>(r_counts[b].as<uint32_t>(), r_sums[b].as<unsigned long long>(), r_offsets[b].as<uint64_t>(), cq);
             CU(cudaGetLastError());
+            ++counters.kernel_launches;
             CU(cudaMemcpyAsync(&pin_tot[b], r_offsets[b].as<uint64_t>() + cq, 8, cudaMemcpyDeviceToHost, s));
             CU(cudaEventRecord(e_in[b], s));
             counters.kernel_launches += 3;

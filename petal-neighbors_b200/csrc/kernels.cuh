@@ -747,24 +747,75 @@ __global__ void compact_hits_kernel(const uint32_t* __restrict__ slab, const uin
     for (uint32_t i = lane; i < c; i += 32) hits[o + i] = slab[(uint64_t)qi * RADIUS_CAP + i];
 }
 
-// u32 counts -> u64 exclusive offsets (single block)
-__global__ void offsets_scan_kernel(const uint32_t* __restrict__ counts, uint64_t* __restrict__ offsets, uint32_t n) {
-    __shared__ unsigned long long sums[1024];
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    const uint32_t chunk = (n + nt - 1) / nt;
-    const uint32_t b = min(n, tid * chunk), e = min(n, b + chunk);
+// u32 counts -> u64 exclusive offsets, offsets[n] = total.  Two launches over blocks of SCAN_BLOCK counts: the sums of the
+// blocks, then every block adds the sums of the blocks before it (at most a few hundred values) to its own scan.
+constexpr uint32_t SCAN_BLOCK = 4096;   // 1024 threads x 4 counts
+__global__ void scan_sums_kernel(const uint32_t* __restrict__ counts, uint32_t n, unsigned long long* __restrict__ sums) {
+    __shared__ unsigned long long ws[32];
+    const uint32_t i0 = blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
     unsigned long long s = 0;
-    for (uint32_t i = b; i < e; ++i) s += counts[i];
-    sums[tid] = s;
+    if (i0 + 3 < n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(counts + i0);
+        s = (unsigned long long)v.x + v.y + v.z + v.w;
+    } else {
+        for (uint32_t i = i0; i < n && i < i0 + 4; ++i) s += counts[i];
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long run = 0;
-        for (uint32_t i = 0; i < nt; ++i) { unsigned long long v = sums[i]; sums[i] = run; run += v; }
-        offsets[n] = run;
+    if (threadIdx.x < 32) {
+        s = ws[threadIdx.x];
+        for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) sums[blockIdx.x] = s;
+    }
+}
+__global__ void offsets_scan_kernel(const uint32_t* __restrict__ counts, const unsigned long long* __restrict__ sums,
+                                    uint64_t* __restrict__ offsets, uint32_t n) {
+    __shared__ unsigned long long ws[33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // sum of the blocks before this one
+    unsigned long long base = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += blockDim.x) base += sums[b];
+    for (int o = 16; o; o >>= 1) base += __shfl_down_sync(0xffffffffu, base, o);
+    if (lane == 0) ws[w] = base;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        base = ws[threadIdx.x];
+        for (int o = 16; o; o >>= 1) base += __shfl_down_sync(0xffffffffu, base, o);
+        if (threadIdx.x == 0) ws[32] = base;
     }
     __syncthreads();
-    unsigned long long run = sums[tid];
-    for (uint32_t i = b; i < e; ++i) { unsigned long long v = counts[i]; offsets[i] = run; run += v; }
+    base = ws[32];
+    __syncthreads();
+    const uint32_t i0 = blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+    uint32_t v[4] = {0, 0, 0, 0};
+    if (i0 + 3 < n) {
+        const uint4 t = *reinterpret_cast<const uint4*>(counts + i0);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        for (uint32_t i = 0; i < 4 && i0 + i < n; ++i) v[i] = counts[i0 + i];
+    }
+    const unsigned long long mine = (unsigned long long)v[0] + v[1] + v[2] + v[3];
+    unsigned long long inc = mine;   // inclusive scan over the warp
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long x = ws[threadIdx.x], xi = x;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, xi, o);
+            if (lane >= o) xi += t;
+        }
+        ws[threadIdx.x] = xi - x;   // exclusive over the warps
+    }
+    __syncthreads();
+    unsigned long long run = base + ws[w] + inc - mine;
+    for (uint32_t i = 0; i < 4 && i0 + i < n; ++i) { offsets[i0 + i] = run; run += v[i]; }
+    if (i0 < n && i0 + 4 >= n) offsets[n] = run;   // the thread holding the last count
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) offsets[0] = 0;
 }
 
 // ascending sort of each query's hit list (the reference's order is unspecified DFS order and its tests sort before
