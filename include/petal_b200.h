@@ -181,6 +181,23 @@ int32_t pn_vptree_query_nearest_f32(pn_tree *tree, const float *queries, size_t 
 int32_t pn_vptree_query_nearest_f64(pn_tree *tree, const double *queries, size_t nq,
                                     size_t q_row_stride, uint64_t *idx_out, double *dist_out);
 
+/* --- k-NN and radius search on a vantage-point handle.  EXTENSIONS: the reference's
+ * VantagePointTree has query_nearest only (src/vantage_point_tree.rs:88-98).  The results are those BallTree::query /
+ * BallTree::query_radius return for the same points (same (distance, index) order, same strict `< r`, same output
+ * shapes as pn_balltree_query_* above): exact answers do not depend on the partition.  k-NN runs on the vantage-point
+ * arrays (or, for tensor-eligible trees, on the ball partition the handle keeps next to them); radius search on a ball
+ * partition of the stored points, built on the device at the first such call. */
+int32_t pn_vptree_query_f32(pn_tree *tree, const float *queries, size_t nq, size_t q_row_stride,
+                            size_t k, uint64_t *idx_out, float *dist_out);
+int32_t pn_vptree_query_f64(pn_tree *tree, const double *queries, size_t nq, size_t q_row_stride,
+                            size_t k, uint64_t *idx_out, double *dist_out);
+int32_t pn_vptree_query_radius_f32(pn_tree *tree, const float *queries, size_t nq,
+                                   size_t q_row_stride, float radius, uint64_t **offsets_out,
+                                   uint64_t **indices_out);
+int32_t pn_vptree_query_radius_f64(pn_tree *tree, const double *queries, size_t nq,
+                                   size_t q_row_stride, double radius, uint64_t **offsets_out,
+                                   uint64_t **indices_out);
+
 /* --- all-points self-query: every stored point is a query (the reference bench's loop,
  * benches/ball_tree.rs:53-59, and the k-NN-graph shape of downstream clustering).  Row i of the
  * n x k outputs is the answer for points[i]; the point itself is its own first neighbour

@@ -7,6 +7,7 @@
 //                                                   (reference src/ball_tree.rs:38-142, 351-373)
 //   petal_neighbors::VantagePointTree<A>::euclidean / query_nearest
 //                                                   (reference src/vantage_point_tree.rs:31-98)
+//     + query / query_radius on the vantage-point tree: extensions, the reference has none
 //   petal_neighbors::ArrayError {Empty, NotContiguous}          (reference src/lib.rs:9-16)
 //   petal_neighbors::distance::{Metric, Euclidean}              (reference src/distance.rs:9-55)
 //
@@ -82,6 +83,8 @@ template <> struct Abi<float> {
     static constexpr auto nearest = pn_balltree_query_nearest_f32;
     static constexpr auto radius = pn_balltree_query_radius_f32;
     static constexpr auto vp_nearest = pn_vptree_query_nearest_f32;
+    static constexpr auto vp_query = pn_vptree_query_f32;
+    static constexpr auto vp_radius = pn_vptree_query_radius_f32;
     static constexpr auto self = pn_balltree_query_self_f32;
 };
 template <> struct Abi<double> {
@@ -91,6 +94,8 @@ template <> struct Abi<double> {
     static constexpr auto nearest = pn_balltree_query_nearest_f64;
     static constexpr auto radius = pn_balltree_query_radius_f64;
     static constexpr auto vp_nearest = pn_vptree_query_nearest_f64;
+    static constexpr auto vp_query = pn_vptree_query_f64;
+    static constexpr auto vp_radius = pn_vptree_query_radius_f64;
     static constexpr auto self = pn_balltree_query_self_f64;
 };
 }  // namespace detail
@@ -179,6 +184,24 @@ template <typename A> class VantagePointTree {
         if ((q.cols > 1 && q.col_stride != 1) || (q.rows > 1 && q.row_stride < q.cols))
             throw std::invalid_argument("petal_neighbors: query rows must be contiguous with row stride >= dimension");
         detail::check(detail::Abi<A>::vp_nearest(h_, q.data, q.rows, q.row_stride, idx_out, dist_out));
+    }
+    // Extensions (not in the reference): what BallTree::query / query_radius return for the same points.
+    std::pair<std::vector<size_t>, std::vector<A>> query(const std::vector<A>& point, size_t k) const {
+        detail::check_dim(point.size(), d_, "point");
+        if (k == 0) return {};
+        std::vector<uint64_t> idx(k); std::vector<A> dist(k);
+        detail::check(detail::Abi<A>::vp_query(h_, point.data(), 1, d_, k, idx.data(), dist.data()));
+        size_t m = 0;
+        while (m < k && idx[m] != ~uint64_t(0)) ++m;   // rows are padded when k > n
+        return {std::vector<size_t>(idx.begin(), idx.begin() + m), std::vector<A>(dist.begin(), dist.begin() + m)};
+    }
+    std::vector<size_t> query_radius(const std::vector<A>& point, A distance) const {
+        detail::check_dim(point.size(), d_, "point");
+        uint64_t *po = nullptr, *pi = nullptr;
+        detail::check(detail::Abi<A>::vp_radius(h_, point.data(), 1, d_, distance, &po, &pi));
+        std::vector<size_t> ind(pi, pi + po[1]);
+        pn_free(po); pn_free(pi);
+        return ind;
     }
 
   private:

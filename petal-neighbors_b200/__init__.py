@@ -197,6 +197,27 @@ class _Tree:
                 _check(fn(self._h, Q.ctypes.data, nq, qs, idx.ctypes.data, dist.ctypes.data))
         return idx, dist
 
+    def _radius(self, Q, radius):
+        Q, qs = self._queries(Q)
+        nq = Q.shape[0]
+        L = _ffi.lib()
+        offs_p = C.POINTER(C.c_uint64)()
+        idx_p = C.POINTER(C.c_uint64)()
+        fn = getattr(L, f"pn_{self._kind}_query_radius_{self._sfx}")
+        _check(fn(self._h, Q.ctypes.data if nq else None, nq, qs, self.dtype.type(radius), C.byref(offs_p), C.byref(idx_p)))
+        # zero-copy: the engine-allocated buffers back the arrays and are released with pn_free when
+        # the arrays are garbage-collected (the Rust shim's Vec::from_raw_parts equivalent)
+        offsets = np.ctypeslib.as_array(offs_p, shape=(nq + 1,))
+        weakref.finalize(offsets, L.pn_free, C.cast(offs_p, C.c_void_p))
+        total = int(offsets[-1])
+        if total:
+            indices = np.ctypeslib.as_array(idx_p, shape=(total,))
+            weakref.finalize(indices, L.pn_free, C.cast(idx_p, C.c_void_p))
+        else:
+            indices = np.empty(0, np.uint64)
+            L.pn_free(idx_p)
+        return offsets, indices
+
     def query_knn_dev(self, q_ptr: int, nq: int, q_row_stride: int, k: int, idx_ptr: int, dist_ptr: int,
                       stream: int = 0, sync: bool = True):
         """Device-pointer k-NN (pn_tree_query_knn_dev): queries/outputs already in HBM."""
@@ -241,25 +262,7 @@ class BallTree(_Tree):
     def query_radius_batch(self, Q, radius):
         """Batched BallTree::query_radius: CSR (offsets[nq+1], indices), each query's indices
         ascending; strict `distance < radius` (src/ball_tree.rs:277)."""
-        Q, qs = self._queries(Q)
-        nq = Q.shape[0]
-        L = _ffi.lib()
-        offs_p = C.POINTER(C.c_uint64)()
-        idx_p = C.POINTER(C.c_uint64)()
-        fn = getattr(L, f"pn_balltree_query_radius_{self._sfx}")
-        _check(fn(self._h, Q.ctypes.data if nq else None, nq, qs, self.dtype.type(radius), C.byref(offs_p), C.byref(idx_p)))
-        # zero-copy: the engine-allocated buffers back the arrays and are released with pn_free when
-        # the arrays are garbage-collected (the Rust shim's Vec::from_raw_parts equivalent)
-        offsets = np.ctypeslib.as_array(offs_p, shape=(nq + 1,))
-        weakref.finalize(offsets, L.pn_free, C.cast(offs_p, C.c_void_p))
-        total = int(offsets[-1])
-        if total:
-            indices = np.ctypeslib.as_array(idx_p, shape=(total,))
-            weakref.finalize(indices, L.pn_free, C.cast(idx_p, C.c_void_p))
-        else:
-            indices = np.empty(0, np.uint64)
-            L.pn_free(idx_p)
-        return offsets, indices
+        return self._radius(Q, radius)
 
     def query_radius(self, point, radius):
         """BallTree::query_radius src/ball_tree.rs:137-142 (indices ascending)."""
@@ -279,6 +282,24 @@ class VantagePointTree(_Tree):
         """VantagePointTree::query_nearest src/vantage_point_tree.rs:88-98: (index, distance)."""
         idx, dist = self.query_nearest_batch(np.asarray(needle, dtype=self.dtype)[None, :])
         return int(idx[0]), dist[0]
+
+    # Extensions (the reference VP tree has query_nearest only): the answers BallTree gives for the same points.
+    def query_batch(self, Q, k: int):
+        """k-NN on the vantage-point handle: (indices[nq, k] u64, distances[nq, k]), (distance, index) ascending."""
+        return self._knn("pn_vptree_query", Q, int(k))
+
+    def query(self, point, k: int):
+        idx, dist = self.query_batch(np.asarray(point, dtype=self.dtype)[None, :], k)
+        m = min(int(k), self.num_points())
+        return idx[0, :m].astype(np.uintp), dist[0, :m]
+
+    def query_radius_batch(self, Q, radius):
+        """Radius search on the vantage-point handle: CSR (offsets[nq+1], indices), strict `distance < radius`."""
+        return self._radius(Q, radius)
+
+    def query_radius(self, point, radius):
+        _, indices = self.query_radius_batch(np.asarray(point, dtype=self.dtype)[None, :], radius)
+        return indices.astype(np.uintp)
 
 
 def merge_topk_dev(dtype, device: int, idx_lists_ptr: int, dist_lists_ptr: int, n_lists: int, nq: int, k: int,

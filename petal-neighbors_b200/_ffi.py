@@ -25,6 +25,7 @@ EXPORTS = [
     "pn_balltree_query_nearest_f32", "pn_balltree_query_nearest_f64",
     "pn_balltree_query_radius_f32", "pn_balltree_query_radius_f64",
     "pn_vptree_query_nearest_f32", "pn_vptree_query_nearest_f64",
+    "pn_vptree_query_f32", "pn_vptree_query_f64", "pn_vptree_query_radius_f32", "pn_vptree_query_radius_f64",
     "pn_balltree_query_self_f32", "pn_balltree_query_self_f64", "pn_tree_query_self_dev",
     "pn_pairwise_f32", "pn_pairwise_f64",
     "pn_free", "pn_tree_query_knn_dev", "pn_merge_topk_dev",
@@ -98,9 +99,13 @@ def lib():
         f = getattr(L, f"pn_balltree_create_dev_{sfx}")
         f.restype = C.c_int32
         f.argtypes = [vp, sz, sz, sz, C.POINTER(BuildOpts), C.POINTER(vp)]
-        f = getattr(L, f"pn_balltree_query_{sfx}")
-        f.restype = C.c_int32
-        f.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+        for kind in ("balltree", "vptree"):
+            f = getattr(L, f"pn_{kind}_query_{sfx}")
+            f.restype = C.c_int32
+            f.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+            f = getattr(L, f"pn_{kind}_query_radius_{sfx}")
+            f.restype = C.c_int32
+            f.argtypes = [vp, vp, sz, sz, real, C.POINTER(u64p), C.POINTER(u64p)]
         for name in (f"pn_balltree_query_nearest_{sfx}", f"pn_vptree_query_nearest_{sfx}"):
             f = getattr(L, name)
             f.restype = C.c_int32
@@ -111,9 +116,6 @@ def lib():
         f = getattr(L, f"pn_balltree_query_self_{sfx}")
         f.restype = C.c_int32
         f.argtypes = [vp, sz, vp, vp]
-        f = getattr(L, f"pn_balltree_query_radius_{sfx}")
-        f.restype = C.c_int32
-        f.argtypes = [vp, vp, sz, sz, real, C.POINTER(u64p), C.POINTER(u64p)]
     L.pn_tree_destroy.argtypes = [vp]
     L.pn_tree_destroy.restype = C.c_int32
     L.pn_free.argtypes = [vp]

@@ -27,12 +27,12 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
-#define CU(x)                                                                                          \
+#define CU(...)                                                                                        \
     do {                                                                                               \
-        cudaError_t e_ = (x);                                                                          \
+        cudaError_t e_ = (__VA_ARGS__);                                                                \
         if (e_ != cudaSuccess)                                                                         \
             return fail(e_ == cudaErrorMemoryAllocation ? PN_OOM : PN_CUDA,                            \
-                        std::string(#x) + ": " + cudaGetErrorString(e_));                              \
+                        std::string(#__VA_ARGS__) + ": " + cudaGetErrorString(e_));                    \
     } while (0)
 #define TRY(x)                  \
     do {                        \
@@ -405,8 +405,8 @@ struct Engine final : pn_tree {
                         for (uint32_t j = 0; j < ft.d; ++j) m[j] += (double)ft.pts[i * ft.dpad + j];
                 });
                 std::vector<double> mean(ft.dpad, 0.0);
-                for (size_t c = 0; c < n_ch; ++c)
-                    for (uint32_t j = 0; j < ft.d; ++j) mean[j] += part[c * ft.dpad + j];
+                for (size_t ch = 0; ch < n_ch; ++ch)
+                    for (uint32_t j = 0; j < ft.d; ++j) mean[j] += part[ch * ft.dpad + j];
                 for (uint32_t j = 0; j < ft.d; ++j) c[j] = (float)(mean[j] / (double)ft.n);
                 std::vector<float> pmaxabs(n_ch, 0.f);
                 chunks([&](size_t ch) {
@@ -670,8 +670,8 @@ struct Engine final : pn_tree {
             fa.tile_bits = w_bits.as<uint32_t>(); fa.tile_cnt = w_tcnt.as<uint32_t>(); fa.tile_words = words; fa.seed_t2 = w_seed.as<float>();
             TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
             // results of sorted slot i belong to query order[i] (self query: to the original row of stored point i)
-            merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, nq, k, idx_out, dist_out, kstride,
-                                                                            0, nullptr, nullptr, self_query ? d_ids.as<uint32_t>() : order);
+            CU(merge_lists<A, uint32_t>(st, w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, nq, k, idx_out, dist_out, kstride,
+                                                                            0, nullptr, nullptr, self_query ? d_ids.as<uint32_t>() : order));
             CU(cudaGetLastError());
             counters.kernel_launches += 2;
             counters.filter_pairs += (uint64_t)ft.n * nq;  // replaced by the device-side count of scanned pairs in fetch_counters
@@ -763,8 +763,7 @@ struct Engine final : pn_tree {
                 if (q_main) {
                     fa.row0 = 0; fa.nq = q_main; fa.tiles_per_split = n_tiles; fa.g_bound = nullptr;
                     TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
-                    merge_lists_kernel<A, uint32_t><<<(q_main + 127) / 128, 128, 0, st>>>(
-                        w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, q_main, kk, idx_out, dist_out, kstride, p * KP, fl_d, fl_i, rmap);
+                    CU(merge_lists<A, uint32_t>(st, w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, q_main, kk, idx_out, dist_out, kstride, p * KP, fl_d, fl_i, rmap));
                     CU(cudaGetLastError());
                     counters.kernel_launches += 2;
                 }
@@ -778,10 +777,9 @@ struct Engine final : pn_tree {
                     fa.part_d = w_part_d.as<float>() + (size_t)q_main * kk; fa.part_i = w_part_i.as<uint32_t>() + (size_t)q_main * kk;
                     TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
                     // with a row map (self query) the merge addresses output rows absolutely; otherwise the outputs are offset
-                    merge_lists_kernel<A, uint32_t><<<(q_tail + 127) / 128, 128, 0, st>>>(
-                        reinterpret_cast<const A*>(fa.part_d), fa.part_i, S, q_tail, kk, rmap ? idx_out : idx_out + (size_t)q_main * kstride,
+                    CU(merge_lists<A, uint32_t>(st, reinterpret_cast<const A*>(fa.part_d), fa.part_i, S, q_tail, kk, rmap ? idx_out : idx_out + (size_t)q_main * kstride,
                         rmap ? dist_out : dist_out + (size_t)q_main * kstride, kstride, p * KP, fl_d ? fl_d + q_main : nullptr,
-                        fl_i ? fl_i + q_main : nullptr, rmap ? rmap + q_main : nullptr);
+                        fl_i ? fl_i + q_main : nullptr, rmap ? rmap + q_main : nullptr));
                     CU(cudaGetLastError());
                     counters.kernel_launches += 2;
                 }
@@ -870,14 +868,33 @@ struct Engine final : pn_tree {
             a.floor_d = p ? w_floor_d.as<A>() : nullptr; a.floor_i = p ? w_floor_i.as<uint32_t>() : nullptr;
             a.counters = w_counters.as<unsigned long long>();
             TRY(launch_knn(a, dim3(tiles, n_splits), st, k1));
-            merge_lists_kernel<A, uint32_t><<<(nq + 127) / 128, 128, 0, st>>>(
-                w_part_d.as<A>(), w_part_i.as<uint32_t>(), n_splits, nq, kk, idx_out, dist_out, kstride, p * KP,
+            CU(merge_lists<A, uint32_t>(st, w_part_d.as<A>(), w_part_i.as<uint32_t>(), n_splits, nq, kk, idx_out, dist_out, kstride, p * KP,
                 n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr,
-                self_query ? d_ids.as<uint32_t>() : nullptr);
+                self_query ? d_ids.as<uint32_t>() : nullptr));
             CU(cudaGetLastError());
             counters.kernel_launches += 2;
         }
         CU(cudaEventRecord(ev[3], st));
+        return PN_OK;
+    }
+
+    // A vantage-point handle's ball partition of the same points (Engine::aux).  Tensor-eligible trees get it when they are
+    // created; the others on the first query the VP arrays do not serve (radius search): built on the device from the
+    // stored rows, then its ids (positions in this tree's stored order) are translated to the original point indices.
+    int ensure_companion() {
+        if (aux) return PN_OK;
+        if (host_only) return fail(PN_CUDA, "this handle was built without a device (there is no CPU fallback)");
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        std::unique_ptr<Engine<A>> ax(new Engine<A>());
+        ax->device = device; ax->algo = algo; ax->prune_opt = prune_opt;
+        CU(cudaStreamSynchronize(stream));
+        TRY(ax->build_on_device(d_pts.as<A>(), ft.n, ft.d, ft.dpad, 256, 0, 0));
+        translate_ids_kernel<<<(unsigned)((ft.n + 255) / 256), 256, 0, ax->stream>>>(ax->d_ids.template as<uint32_t>(), d_ids.as<uint32_t>(), (uint32_t)ft.n);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ax->stream));
+        info.device_bytes += ax->info.device_bytes;
+        aux = std::move(ax);
         return PN_OK;
     }
 
@@ -1142,9 +1159,16 @@ struct Engine final : pn_tree {
     // host-side widening of this one.
     int radius_host(const void* qv, size_t nq, size_t stride, double rr, uint64_t** offs_out, uint64_t** idx_out) override {
         TRY(check_query_args(qv, nq, stride));
-        if (ft.kind != 0) return fail(PN_BAD_ARG, "query_radius is a BallTree method (the reference VP tree has none)");
         if (!offs_out || !idx_out) return fail(PN_BAD_ARG, "output pointer is null");
         std::lock_guard<std::mutex> lk(mu);
+        if (ft.kind != 0) {
+            // an extension (the reference VP tree has no radius query): answered from the ball partition of the same points
+            TRY(ensure_companion());
+            const int rc = aux->radius_host(qv, nq, stride, rr, offs_out, idx_out);
+            counters = aux->counters;
+            last_used_tensor = false; last_pruned = false;
+            return rc;
+        }
         DeviceGuard g(device);
         if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
         counters = pn_counters{};
@@ -1330,9 +1354,9 @@ struct Engine final : pn_tree {
                     merge_packed_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(sh_gat[b].as<unsigned long long>(), (uint32_t)W, cnt * k, (uint32_t)cnt,
                                                                                        (uint32_t)k, idx_out + orow * k, (float*)dist_out + orow * k);
                 } else {
-                    merge_lists_kernel<A, uint64_t><<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(sh_gat_d[b].as<A>(), sh_gat[b].as<uint64_t>(), (uint32_t)W,
+                    CU(merge_lists<A, uint64_t>(st, sh_gat_d[b].as<A>(), sh_gat[b].as<uint64_t>(), (uint32_t)W,
                                                                                                   (uint32_t)cnt, (uint32_t)k, idx_out + orow * k,
-                                                                                                  dist_out + orow * k, (uint32_t)k, 0, nullptr, nullptr);
+                                                                                                  dist_out + orow * k, (uint32_t)k, 0, nullptr, nullptr));
                 }
                 CU(cudaGetLastError());
                 ++counters.kernel_launches;
@@ -1780,8 +1804,8 @@ static int merge_topk_dev(int device, const uint64_t* idx_lists, const A* dist_l
     if (nq == 0 || k == 0) return PN_OK;
     DeviceGuard g(device);
     if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
-    merge_lists_kernel<A, uint64_t><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(dist_lists, idx_lists, (uint32_t)n_lists, (uint32_t)nq,
-                                                                          (uint32_t)k, idx_out, dist_out, (uint32_t)k, 0, nullptr, nullptr);
+    CU(merge_lists<A, uint64_t>(st, dist_lists, idx_lists, (uint32_t)n_lists, (uint32_t)nq,
+                                                                          (uint32_t)k, idx_out, dist_out, (uint32_t)k, 0, nullptr, nullptr));
     CU(cudaGetLastError());
     if (sync) CU(cudaStreamSynchronize(st));
     return PN_OK;
@@ -1890,6 +1914,18 @@ int32_t pn_vptree_query_nearest_f32(pn_tree* t, const float* q, size_t nq, size_
 }
 int32_t pn_vptree_query_nearest_f64(pn_tree* t, const double* q, size_t nq, size_t qs, uint64_t* io, double* dd) {
     GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_VP)); return t->knn_host(q, nq, qs, 1, io, dd); GUARD_END
+}
+int32_t pn_vptree_query_f32(pn_tree* t, const float* q, size_t nq, size_t qs, size_t k, uint64_t* io, float* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F32, PN_KIND_VP)); return t->knn_host(q, nq, qs, k, io, dd); GUARD_END
+}
+int32_t pn_vptree_query_f64(pn_tree* t, const double* q, size_t nq, size_t qs, size_t k, uint64_t* io, double* dd) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_VP)); return t->knn_host(q, nq, qs, k, io, dd); GUARD_END
+}
+int32_t pn_vptree_query_radius_f32(pn_tree* t, const float* q, size_t nq, size_t qs, float r, uint64_t** oo, uint64_t** io) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F32, PN_KIND_VP)); return t->radius_host(q, nq, qs, (double)r, oo, io); GUARD_END
+}
+int32_t pn_vptree_query_radius_f64(pn_tree* t, const double* q, size_t nq, size_t qs, double r, uint64_t** oo, uint64_t** io) {
+    GUARD_BEGIN TRY(check_tree(t, PN_F64, PN_KIND_VP)); return t->radius_host(q, nq, qs, r, oo, io); GUARD_END
 }
 int32_t pn_balltree_query_self_f32(pn_tree* t, size_t k, uint64_t* io, float* dd) {
     GUARD_BEGIN TRY(check_tree(t, PN_F32, PN_KIND_BALL)); return t->knn_self(k, io, dd, false, nullptr, true); GUARD_END

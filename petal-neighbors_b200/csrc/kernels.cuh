@@ -474,7 +474,8 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
 }
 
 // ---- k-way merge of sorted (distance, index) lists: split scans of one GPU, or the gathered
-// per-shard lists of several GPUs (K7 in SURVEY.md 2).  One thread per query. ---------------
+// per-shard lists of several GPUs (K7 in SURVEY.md 2): merge_lists() below.  This kernel is its
+// single-list case, one thread per query. ---------------
 constexpr int MAX_LISTS = 256;
 template <typename A, typename I>
 __global__ void merge_lists_kernel(const A* __restrict__ in_d, const I* __restrict__ in_i, uint32_t n_lists,
@@ -487,36 +488,87 @@ __global__ void merge_lists_kernel(const A* __restrict__ in_d, const I* __restri
     const I none = (I)~(I)0;
     A last_d = pos_inf<A>();
     uint64_t last_i = ~0ull;
-    if (n_lists == 1) {
-        for (uint32_t i = 0; i < k; ++i) {
-            const A d = in_d[(size_t)q * k + i];
-            const I id = in_i[(size_t)q * k + i];
-            out_d[orow * out_stride + out_off + i] = d;
-            out_i[orow * out_stride + out_off + i] = id == none ? ~0ull : (uint64_t)id;
-            last_d = d; last_i = id == none ? ~0ull : (uint64_t)id;
-        }
-    } else {
-        uint16_t head[MAX_LISTS];
-        for (uint32_t l = 0; l < n_lists; ++l) head[l] = 0;
-        for (uint32_t i = 0; i < k; ++i) {
-            A bd = pos_inf<A>();
-            uint64_t bi = ~0ull;
-            int bl = -1;
-            for (uint32_t l = 0; l < n_lists; ++l) {
-                if (head[l] >= k) continue;
-                const size_t at = ((size_t)l * nq + q) * k + head[l];
-                const I id = in_i[at];
-                if (id == none) continue;
-                const A d = in_d[at];
-                if (bl < 0 || d < bd || (d == bd && (uint64_t)id < bi)) { bd = d; bi = (uint64_t)id; bl = (int)l; }
-            }
-            if (bl >= 0) ++head[bl];
-            out_d[orow * out_stride + out_off + i] = bd;
-            out_i[orow * out_stride + out_off + i] = bi;
-            last_d = bd; last_i = bi;
-        }
+    (void)n_lists;   // one list per query: copy (and widen the indices) to the output rows
+    for (uint32_t i = 0; i < k; ++i) {
+        const A d = in_d[(size_t)q * k + i];
+        const I id = in_i[(size_t)q * k + i];
+        out_d[orow * out_stride + out_off + i] = d;
+        out_i[orow * out_stride + out_off + i] = id == none ? ~0ull : (uint64_t)id;
+        last_d = d; last_i = id == none ? ~0ull : (uint64_t)id;
     }
     if (floor_d && k > 0) { floor_d[q] = last_d; floor_i[q] = last_i == ~0ull ? NO_ID : (uint32_t)last_i; }
+}
+
+// Several lists: one WARP per query.  Lane l keeps the heads of lists l, l + 32, ... (at most MAX_LISTS / 32) in
+// registers; every output slot is one lane-local minimum, one five-step warp arg-min on (distance, index) and one reload
+// by the winning lane -- no per-thread head array in local memory, O(k (n_lists / 32 + 5)) steps per query.
+template <typename A, typename I>
+__global__ void merge_lists_warp_kernel(const A* __restrict__ in_d, const I* __restrict__ in_i, uint32_t n_lists, uint32_t nq, uint32_t k,
+                                        uint64_t* __restrict__ out_i, A* __restrict__ out_d, uint32_t out_stride, uint32_t out_off,
+                                        A* floor_d, uint32_t* floor_i, const uint32_t* __restrict__ row_map) {
+    constexpr int PER = MAX_LISTS / 32;
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const size_t orow = row_map ? row_map[q] : q;
+    const I none = (I)~(I)0;
+    const unsigned full = 0xffffffffu;
+    uint32_t head[PER];
+    A hd[PER];
+    uint64_t hi[PER];
+    auto load = [&](int s_, uint32_t h, A& d, uint64_t& id) {
+        const uint32_t l = (uint32_t)lane + 32u * (uint32_t)s_;
+        d = pos_inf<A>(); id = ~0ull;   // exhausted (or absent) list: never wins against a real entry
+        if (l < n_lists && h < k) {
+            const size_t at = ((size_t)l * nq + q) * k + h;
+            const I v = in_i[at];
+            if (v != none) { d = in_d[at]; id = (uint64_t)v; }
+        }
+    };
+#pragma unroll
+    for (int s_ = 0; s_ < PER; ++s_) { head[s_] = 0; load(s_, 0, hd[s_], hi[s_]); }
+    A last_d = pos_inf<A>();
+    uint64_t last_i = ~0ull;
+    for (uint32_t i = 0; i < k; ++i) {
+        A bd = hd[0];
+        uint64_t bi = hi[0];
+        int bs = 0;
+#pragma unroll
+        for (int s_ = 1; s_ < PER; ++s_)
+            if (hd[s_] < bd || (hd[s_] == bd && hi[s_] < bi)) { bd = hd[s_]; bi = hi[s_]; bs = s_; }
+        A wd = bd;
+        uint64_t wi = bi;
+        int wl = lane;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const A od = __shfl_xor_sync(full, wd, o);
+            const uint64_t oi = __shfl_xor_sync(full, wi, o);
+            const int ol = __shfl_xor_sync(full, wl, o);
+            if (od < wd || (od == wd && (oi < wi || (oi == wi && ol < wl)))) { wd = od; wi = oi; wl = ol; }
+        }
+        if (lane == wl && wi != ~0ull) {
+#pragma unroll
+            for (int s_ = 0; s_ < PER; ++s_)
+                if (s_ == bs) { ++head[s_]; load(s_, head[s_], hd[s_], hi[s_]); }
+        }
+        if (lane == 0) {
+            out_d[orow * out_stride + out_off + i] = wd;
+            out_i[orow * out_stride + out_off + i] = wi;
+        }
+        last_d = wd; last_i = wi;
+    }
+    if (lane == 0 && floor_d && k > 0) { floor_d[q] = last_d; floor_i[q] = last_i == ~0ull ? NO_ID : (uint32_t)last_i; }
+}
+// one list: the copy / row-map kernel above, a thread per query; several: a warp per query
+template <typename A, typename I>
+inline cudaError_t merge_lists(cudaStream_t st, const A* in_d, const I* in_i, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t* out_i,
+                               A* out_d, uint32_t out_stride, uint32_t out_off, A* floor_d, uint32_t* floor_i, const uint32_t* row_map = nullptr) {
+    if (nq == 0) return cudaSuccess;
+    if (n_lists <= 1)
+        merge_lists_kernel<A, I><<<(nq + 127) / 128, 128, 0, st>>>(in_d, in_i, n_lists, nq, k, out_i, out_d, out_stride, out_off, floor_d, floor_i, row_map);
+    else
+        merge_lists_warp_kernel<A, I><<<(nq + 7) / 8, 256, 0, st>>>(in_d, in_i, n_lists, nq, k, out_i, out_d, out_stride, out_off, floor_d, floor_i, row_map);
+    return cudaGetLastError();
 }
 
 // k > n: columns [k_eff, k) of every output row are (UINT64_MAX, +inf) -- the reference returns only n results
@@ -585,6 +637,12 @@ __global__ void merge_packed_peer_kernel(const unsigned long long* const* __rest
         out_d[(size_t)q * k + i] = __uint_as_float((uint32_t)(best >> 32));
         out_i[(size_t)q * k + i] = (bl < 0 || id == NO_ID) ? ~0ull : (uint64_t)id;
     }
+}
+
+// ids[i] = map[ids[i]]: the companion ball tree of a vantage-point handle is built over that handle's stored rows
+__global__ void translate_ids_kernel(uint32_t* __restrict__ ids, const uint32_t* __restrict__ map, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = map[ids[i]];
 }
 
 // ---- query staging ----------------------------------------------------------------------------

@@ -54,6 +54,14 @@ extern "C" {
                                        idx: *mut u64, dist: *mut f32) -> i32;
     pub fn pn_vptree_query_nearest_f64(t: *mut pn_tree, q: *const f64, nq: usize, q_row_stride: usize,
                                        idx: *mut u64, dist: *mut f64) -> i32;
+    pub fn pn_vptree_query_f32(t: *mut pn_tree, q: *const f32, nq: usize, q_row_stride: usize, k: usize,
+                               idx: *mut u64, dist: *mut f32) -> i32;
+    pub fn pn_vptree_query_f64(t: *mut pn_tree, q: *const f64, nq: usize, q_row_stride: usize, k: usize,
+                               idx: *mut u64, dist: *mut f64) -> i32;
+    pub fn pn_vptree_query_radius_f32(t: *mut pn_tree, q: *const f32, nq: usize, q_row_stride: usize, r: f32,
+                                      offsets: *mut *mut u64, indices: *mut *mut u64) -> i32;
+    pub fn pn_vptree_query_radius_f64(t: *mut pn_tree, q: *const f64, nq: usize, q_row_stride: usize, r: f64,
+                                      offsets: *mut *mut u64, indices: *mut *mut u64) -> i32;
     pub fn pn_balltree_query_self_f32(t: *mut pn_tree, k: usize, idx: *mut u64, dist: *mut f32) -> i32;
     pub fn pn_balltree_query_self_f64(t: *mut pn_tree, k: usize, idx: *mut u64, dist: *mut f64) -> i32;
     pub fn pn_free(p: *mut std::ffi::c_void);
@@ -81,10 +89,12 @@ pub trait Element: Copy + num_traits::Float + 'static {
     unsafe fn ball_radius(t: *mut pn_tree, q: *const Self, nq: usize, qs: usize, r: Self, o: *mut *mut u64, i: *mut *mut u64) -> i32;
     unsafe fn vp_nearest(t: *mut pn_tree, q: *const Self, nq: usize, qs: usize, idx: *mut u64, dist: *mut Self) -> i32;
     unsafe fn ball_self(t: *mut pn_tree, k: usize, idx: *mut u64, dist: *mut Self) -> i32;
+    unsafe fn vp_query(t: *mut pn_tree, q: *const Self, nq: usize, qs: usize, k: usize, idx: *mut u64, dist: *mut Self) -> i32;
+    unsafe fn vp_radius(t: *mut pn_tree, q: *const Self, nq: usize, qs: usize, r: Self, o: *mut *mut u64, i: *mut *mut u64) -> i32;
 }
 
 macro_rules! impl_element {
-    ($t:ty, $bc:ident, $vc:ident, $bq:ident, $bn:ident, $br:ident, $vn:ident, $bs:ident) => {
+    ($t:ty, $bc:ident, $vc:ident, $bq:ident, $bn:ident, $br:ident, $vn:ident, $bs:ident, $vq:ident, $vr:ident) => {
         impl Element for $t {
             unsafe fn ball_create(p: *const Self, n: usize, d: usize, rs: usize, cs: usize, o: *const pn_build_opts, out: *mut *mut pn_tree) -> i32 { $bc(p, n, d, rs, cs, o, out) }
             unsafe fn vp_create(p: *const Self, n: usize, d: usize, rs: usize, cs: usize, o: *const pn_build_opts, out: *mut *mut pn_tree) -> i32 { $vc(p, n, d, rs, cs, o, out) }
@@ -93,8 +103,10 @@ macro_rules! impl_element {
             unsafe fn ball_radius(t: *mut pn_tree, q: *const Self, nq: usize, qs: usize, r: Self, o: *mut *mut u64, i: *mut *mut u64) -> i32 { $br(t, q, nq, qs, r, o, i) }
             unsafe fn vp_nearest(t: *mut pn_tree, q: *const Self, nq: usize, qs: usize, idx: *mut u64, dist: *mut Self) -> i32 { $vn(t, q, nq, qs, idx, dist) }
             unsafe fn ball_self(t: *mut pn_tree, k: usize, idx: *mut u64, dist: *mut Self) -> i32 { $bs(t, k, idx, dist) }
+            unsafe fn vp_query(t: *mut pn_tree, q: *const Self, nq: usize, qs: usize, k: usize, idx: *mut u64, dist: *mut Self) -> i32 { $vq(t, q, nq, qs, k, idx, dist) }
+            unsafe fn vp_radius(t: *mut pn_tree, q: *const Self, nq: usize, qs: usize, r: Self, o: *mut *mut u64, i: *mut *mut u64) -> i32 { $vr(t, q, nq, qs, r, o, i) }
         }
     };
 }
-impl_element!(f32, pn_balltree_create_f32, pn_vptree_create_f32, pn_balltree_query_f32, pn_balltree_query_nearest_f32, pn_balltree_query_radius_f32, pn_vptree_query_nearest_f32, pn_balltree_query_self_f32);
-impl_element!(f64, pn_balltree_create_f64, pn_vptree_create_f64, pn_balltree_query_f64, pn_balltree_query_nearest_f64, pn_balltree_query_radius_f64, pn_vptree_query_nearest_f64, pn_balltree_query_self_f64);
+impl_element!(f32, pn_balltree_create_f32, pn_vptree_create_f32, pn_balltree_query_f32, pn_balltree_query_nearest_f32, pn_balltree_query_radius_f32, pn_vptree_query_nearest_f32, pn_balltree_query_self_f32, pn_vptree_query_f32, pn_vptree_query_radius_f32);
+impl_element!(f64, pn_balltree_create_f64, pn_vptree_create_f64, pn_balltree_query_f64, pn_balltree_query_nearest_f64, pn_balltree_query_radius_f64, pn_vptree_query_nearest_f64, pn_balltree_query_self_f64, pn_vptree_query_f64, pn_vptree_query_radius_f64);

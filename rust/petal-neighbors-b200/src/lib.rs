@@ -250,6 +250,36 @@ impl<'a, A: Element> VantagePointTree<'a, A, Euclidean> {
         check(unsafe { A::vp_nearest(self.handle.0, q.as_ptr(), nq, self.d, idx.as_mut_ptr(), dist.as_mut_ptr()) });
         (idx.into_iter().map(|i| i as usize).collect(), Array1::from_vec(dist))
     }
+
+    /// Extension (the reference tree has `query_nearest` only): the `k` nearest neighbours, as `BallTree::query`
+    /// returns them for the same points.
+    pub fn query<S: Data<Elem = A>>(&self, point: &ArrayBase<S, Ix1>, k: usize) -> (Vec<usize>, Vec<A>) {
+        check_dim(point.len(), self.d, "point");
+        if k == 0 {
+            return (Vec::new(), Vec::new());
+        }
+        let q = point.to_owned();
+        let mut idx = vec![0u64; k];
+        let mut dist = vec![A::zero(); k];
+        check(unsafe { A::vp_query(self.handle.0, q.as_ptr(), 1, self.d, k, idx.as_mut_ptr(), dist.as_mut_ptr()) });
+        let m = idx.iter().take_while(|&&i| i != u64::MAX).count(); // rows are padded when k > n
+        (idx[..m].iter().map(|&i| i as usize).collect(), dist[..m].to_vec())
+    }
+
+    /// Extension: all points with `distance < radius` (strict), indices ascending, as `BallTree::query_radius`.
+    pub fn query_radius<S: Data<Elem = A>>(&self, point: &ArrayBase<S, Ix1>, distance: A) -> Vec<usize> {
+        check_dim(point.len(), self.d, "point");
+        let q = point.to_owned();
+        let (mut po, mut pi) = (std::ptr::null_mut::<u64>(), std::ptr::null_mut::<u64>());
+        check(unsafe { A::vp_radius(self.handle.0, q.as_ptr(), 1, self.d, distance, &mut po, &mut pi) });
+        let total = unsafe { *po.add(1) } as usize;
+        let out = (0..total).map(|i| unsafe { *pi.add(i) } as usize).collect();
+        unsafe {
+            ffi::pn_free(po as *mut std::ffi::c_void);
+            ffi::pn_free(pi as *mut std::ffi::c_void);
+        }
+        out
+    }
 }
 
 /// How a [`MultiGpuBallTree`] spreads over the devices.

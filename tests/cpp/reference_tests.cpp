@@ -97,6 +97,12 @@ static void vp_euclidian() {  // src/vantage_point_tree.rs:220-233
     const double a[] = {1.0, 2.0, 1.1, 2.2, 0.9, 1.9, 1.0, 2.1, -2.0, 3.0, -2.2, 3.1};
     auto vp = VantagePointTree<double>::euclidean(View2<double>(a, 6, 2));
     CHECK(vp.query_nearest({0.95, 1.96}).first == 0);
+    // extensions (not in the reference): the answers BallTree gives for the same points
+    auto bt = BallTree<double>::euclidean(View2<double>(a, 6, 2));
+    auto kq = vp.query({0.95, 1.96}, 4), kb = bt.query({0.95, 1.96}, 4);
+    CHECK(kq.first == kb.first && kq.second == kb.second);
+    CHECK(vp.query({0.95, 1.96}, 9).first.size() == 6);
+    CHECK(vp.query_radius({0.95, 1.96}, 0.3) == bt.query_radius({0.95, 1.96}, 0.3));
 }
 static void ball_tree_query_property() {  // src/ball_tree.rs:742-765: tree distances == naive distances
     const size_t N = 40, D = 3;

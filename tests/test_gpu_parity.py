@@ -185,6 +185,36 @@ def test_radius_random(pn, oracle, dtype, n, d, nq, bucket, quant):
     assert offs.tolist() == [0, n, 2 * n, 3 * n] and np.array_equal(ind[:n], np.arange(n, dtype=np.uint64))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,d,nq,k,bucket,clustered", [
+    (1, 3, 4, 1, 0, False), (7, 2, 5, 10, 0, False), (5000, 3, 400, 10, 32, False), (20000, 16, 600, 10, 0, False),
+    (3000, 64, 150, 16, 0, True), (4000, 5, 200, 40, 16, False), (900, 24, 64, 3, 8, True),
+])
+def test_vp_knn_and_radius_extensions(pn, oracle, dtype, n, d, nq, k, bucket, clustered):
+    """k-NN and radius search on a vantage-point handle return what BallTree returns for the same
+    points (the reference VP tree has query_nearest only, src/vantage_point_tree.rs:88-98)."""
+    from petal_neighbors_b200 import synth
+    pts = synth.gaussian_mixture(n, d, 61, 16, 0.05, dtype=dtype) if clustered else synth.uniform(n, d, 61 + n, dtype)
+    Q = synth.gaussian_mixture(nq, d, 62, 16, 0.05, dtype=dtype) if clustered else synth.uniform(nq, d, 62 + n, dtype)
+    vp = pn.VantagePointTree.euclidean(pts, bucket_size=bucket)
+    idx, dist = vp.query_batch(Q, k)
+    oi, od = oracle.brute_knn(pts, Q, k)
+    assert_knn_equal(idx, dist, oi, od)
+    i1, d1 = vp.query(Q[0], k)
+    m = min(k, n)
+    assert np.array_equal(i1, oi[0, :m].astype(np.uintp)) and np.array_equal(bits(d1), bits(od[0, :m]))
+    r = dtype(np.quantile(od[:, min(k, n) - 1], 0.5))
+    offs, ind = vp.query_radius_batch(Q, r)
+    boffs, bind = oracle.brute_radius(pts, Q, r)
+    assert np.array_equal(offs, boffs.astype(np.uint64)) and np.array_equal(ind, bind.astype(np.uint64))
+    # strict `<` at a realised distance, and the single-point form
+    r_exact = od[0, m - 1]
+    assert np.array_equal(vp.query_radius(Q[0], r_exact), oracle.brute_radius(pts, Q[:1], r_exact)[1].astype(np.uintp))
+    # the nearest query still answers after the ball partition was attached
+    ni, nd = vp.query_nearest_batch(Q)
+    assert np.array_equal(ni, oi[:, 0].astype(np.uint64)) and np.array_equal(bits(nd), bits(od[:, 0]))
+
+
 def test_empty_query_batches(pn):
     pts = np.random.default_rng(0).random((100, 3)).astype(np.float32)
     bt = pn.BallTree.euclidean(pts)
