@@ -976,14 +976,28 @@ struct Engine final : pn_tree {
             for (cudaEvent_t* e : {&e_in[i], &e_cmp[i], &e_out[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         return PN_OK;
     }
-    // queries per chunk of a host-buffer call: whole waves of the tensor scan (n_sms CTAs x 512 queries).  Two chunks are
-    // enough to hide the copies (H2D of the second and D2H of the first run under the other's kernels) and keep the per-chunk
-    // set-up (query staging, sort, seeds, a partial last wave) small; chunks are capped at 2^20 queries (workspace size).
-    size_t host_chunk(size_t nq) const {
+    // Chunk boundaries of a host-buffer call.  Only the H2D copy of the FIRST chunk and the D2H copy of the LAST one are
+    // not hidden under another chunk's kernels, so those two chunks are one wave of the scan each (n_sms CTAs x the
+    // scan's queries per CTA; the last one also takes the partial wave at the end) and the middle is as few whole-wave
+    // chunks as the 2^20-query workspace cap allows: per-chunk set-up (query staging, sort, seeds) stays small.
+    std::vector<size_t> host_chunks(size_t nq) const {
         const size_t wave = (size_t)n_sms * query_tile();
-        if (nq < 4 * wave) return nq;
-        const size_t half = ((nq + 1) / 2 + wave - 1) / wave * wave;
-        return std::min<size_t>(half, ((size_t)1 << 20) / wave * wave);
+        std::vector<size_t> b{0};
+        if (nq >= 4 * wave) {
+            const size_t cap = std::max<size_t>(wave, ((size_t)1 << 20) / wave * wave);
+            const size_t last = wave + nq % wave;            // start of the last chunk: nq - last
+            b.push_back(wave);
+            size_t mid = nq - last - wave;                    // whole waves
+            const size_t n_mid = (mid + cap - 1) / cap;
+            for (size_t i = 0; i < n_mid; ++i) {
+                const size_t left = nq - last - b.back();
+                const size_t take = std::min(cap, (left / wave + (n_mid - i) - 1) / (n_mid - i) * wave);
+                b.push_back(b.back() + take);
+            }
+            if (b.back() != nq - last) b.back() = nq - last;
+        }
+        b.push_back(nq);
+        return b;
     }
 
     int knn_host(const void* qv, size_t nq, size_t stride, size_t k, uint64_t* idx, void* distv) override {
@@ -1000,7 +1014,10 @@ struct Engine final : pn_tree {
         cudaStream_t st = stream;
         TRY(use_stream(st));
         TRY(ensure_io());
-        const size_t chunk = host_chunk(nq), n_chunks = (nq + chunk - 1) / chunk;
+        const std::vector<size_t> cb = host_chunks(nq);
+        const size_t n_chunks = cb.size() - 1;
+        size_t chunk = 0;   // the largest chunk sizes the buffers
+        for (size_t c = 0; c < n_chunks; ++c) chunk = std::max(chunk, cb[c + 1] - cb[c]);
         const size_t spitch = std::max<size_t>(stride, ft.d) * sizeof(A);  // a single row may come with any stride
         // every allocation happens before the first copy is enqueued (cudaMalloc synchronises the device)
         for (int b = 0; b < (n_chunks > 1 ? 2 : 1); ++b) {
@@ -1015,8 +1032,8 @@ struct Engine final : pn_tree {
         // is done, so it is issued only after the next chunk's kernels are already queued behind it on the device.
         auto d2h = [&](size_t c) -> int {
             const int b = (int)(c & 1);
-            const size_t q0 = c * chunk;
-            const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
+            const size_t q0 = cb[c];
+            const uint32_t cq = (uint32_t)(cb[c + 1] - q0);
             CU(cudaStreamWaitEvent(s_out, e_cmp[b], 0));
             CU(cudaMemcpyAsync(idx + q0 * k, w_oi2[b].p, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, s_out));
             CU(cudaMemcpyAsync(dist + q0 * k, w_od2[b].p, (size_t)cq * k * sizeof(A), cudaMemcpyDeviceToHost, s_out));
@@ -1026,8 +1043,8 @@ struct Engine final : pn_tree {
         };
         for (size_t c = 0; c < n_chunks; ++c) {
             const int b = (int)(c & 1);
-            const size_t q0 = c * chunk;
-            const uint32_t cq = (uint32_t)std::min(chunk, nq - q0);
+            const size_t q0 = cb[c];
+            const uint32_t cq = (uint32_t)(cb[c + 1] - q0);
             // H2D: the raw-query buffer is free once the kernels of chunk c-2 are done
             if (c >= 2) CU(cudaStreamWaitEvent(s_in, e_cmp[b], 0));
             CU(cudaMemcpy2DAsync(w_qraw2[b].p, ft.d * sizeof(A), q + q0 * stride, spitch, ft.d * sizeof(A), cq, cudaMemcpyHostToDevice, s_in));
