@@ -258,11 +258,13 @@ def extra_t128(pn, torch, synth, stream, flush, steps):
     dist_pin = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     from petal_neighbors_b200 import _ffi
     fn = _ffi.lib().pn_balltree_query_f32
-    t0 = time.perf_counter()
-    rc = fn(tree._h, q_pin.data_ptr(), nq, d, k, idx_pin.data_ptr(), dist_pin.data_ptr())
-    e2e_s = time.perf_counter() - t0
-    if rc != 0:
-        raise RuntimeError(_ffi.last_error())
+    e2e_s = None
+    for it in range(2):   # the first host-buffer call of a handle allocates its staging buffers: warm-up at full size
+        t0 = time.perf_counter()
+        rc = fn(tree._h, q_pin.data_ptr(), nq, d, k, idx_pin.data_ptr(), dist_pin.data_ptr())
+        e2e_s = time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError(_ffi.last_error())
     same = bool(torch.equal(idx_pin, idx_dev.cpu()) and torch.equal(dist_pin, dist_dev.cpu()))
     m = float(np.mean(ms))
     kp = (d + 6 + 31) // 32 * 32

@@ -976,25 +976,17 @@ struct Engine final : pn_tree {
             for (cudaEvent_t* e : {&e_in[i], &e_cmp[i], &e_out[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         return PN_OK;
     }
-    // Chunk boundaries of a host-buffer call.  Only the H2D copy of the FIRST chunk and the D2H copy of the LAST one are
-    // not hidden under another chunk's kernels, so those two chunks are one wave of the scan each (n_sms CTAs x the
-    // scan's queries per CTA; the last one also takes the partial wave at the end) and the middle is as few whole-wave
-    // chunks as the 2^20-query workspace cap allows: per-chunk set-up (query staging, sort, seeds) stays small.
+    // Chunk boundaries of a host-buffer call: whole waves of the scan (n_sms CTAs x the scan's queries per CTA).  Two
+    // chunks are enough to hide the copies (H2D of the second and D2H of the first run under the other's kernels) and keep
+    // the per-chunk costs (query staging, sort, seeds, the drain of a launch's last wave, a partial last wave) small;
+    // chunks are capped at 2^20 queries (workspace size).  Measured alternative: one-wave first and last chunks (less
+    // exposed copy) -- the same 107.9 ms on config 2 and 2770 instead of 2724 ms on 10M x 128 (scripts/e2e_chunks.py).
     std::vector<size_t> host_chunks(size_t nq) const {
         const size_t wave = (size_t)n_sms * query_tile();
         std::vector<size_t> b{0};
         if (nq >= 4 * wave) {
-            const size_t cap = std::max<size_t>(wave, ((size_t)1 << 20) / wave * wave);
-            const size_t last = wave + nq % wave;            // start of the last chunk: nq - last
-            b.push_back(wave);
-            size_t mid = nq - last - wave;                    // whole waves
-            const size_t n_mid = (mid + cap - 1) / cap;
-            for (size_t i = 0; i < n_mid; ++i) {
-                const size_t left = nq - last - b.back();
-                const size_t take = std::min(cap, (left / wave + (n_mid - i) - 1) / (n_mid - i) * wave);
-                b.push_back(b.back() + take);
-            }
-            if (b.back() != nq - last) b.back() = nq - last;
+            const size_t half = std::min<size_t>(((nq + 1) / 2 + wave - 1) / wave * wave, ((size_t)1 << 20) / wave * wave);
+            for (size_t x = half; x < nq; x += half) b.push_back(x);
         }
         b.push_back(nq);
         return b;
