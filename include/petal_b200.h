@@ -23,8 +23,9 @@
  *   - there is no CPU fallback: a query on a machine without a usable CUDA device fails with
  *     PN_CUDA.
  * Threading: queries on one tree from several host threads are legal (the reference's
- * `&self` queries, `Euclidean: Sync`, src/distance.rs:19); they serialise on an internal
- * mutex.  create/destroy must not race with queries on the same handle.
+ * `&self` queries, `Euclidean: Sync`, src/distance.rs:19); on one handle they serialise on an
+ * internal mutex, on sessions of it (pn_tree_session) they run concurrently.  create/destroy
+ * must not race with queries on the same handle.
  */
 #ifndef PETAL_B200_H
 #define PETAL_B200_H
@@ -149,6 +150,15 @@ int32_t pn_balltree_create_dev_f32(const float *points_dev, size_t n, size_t d, 
 int32_t pn_balltree_create_dev_f64(const double *points_dev, size_t n, size_t d, size_t row_stride,
                                    const pn_build_opts *opts, pn_tree **out);
 int32_t pn_tree_destroy(pn_tree *tree); /* Rust Drop */
+
+/* --- sessions: concurrent callers.  The reference's queries take `&self` and `Euclidean` is `Sync`
+ * (src/distance.rs:19), so several threads may query one tree at once.  Calls on ONE handle serialise on its mutex
+ * (they share one stream and one set of workspaces).  A session is a second handle onto the same device-resident tree
+ * -- nothing of the tree is copied -- with its own stream, events, workspaces and counters: calls on different
+ * sessions overlap on the device.  One session per calling thread is the intended use.  Sessions and the tree they
+ * came from may be destroyed in any order (the arrays live until the last of them is gone); a session answers every
+ * query entry point of its tree's kind. */
+int32_t pn_tree_session(pn_tree *tree, pn_tree **out);
 
 /* --- BallTree::query (src/ball_tree.rs:102-121), batched: `nq` queries, row stride
  * `q_row_stride` elements; outputs are caller-allocated row-major nq x k.  k == 0 is a no-op

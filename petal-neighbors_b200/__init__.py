@@ -135,6 +135,15 @@ class _Tree:
     def new(cls, points, metric, **opts):
         return cls(points, metric, **opts)
 
+    def session(self):
+        """pn_tree_session: a second handle onto the same device-resident tree with its own stream and workspaces, for
+        a concurrent caller (the reference's `&self` queries from several threads).  Nothing of the tree is copied."""
+        other = object.__new__(type(self))
+        other._h = C.c_void_p()
+        other.metric, other.dtype, other._sfx, other.dim = self.metric, self.dtype, self._sfx, self.dim
+        _check(_ffi.lib().pn_tree_session(self._h, C.byref(other._h)))
+        return other
+
     def close(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

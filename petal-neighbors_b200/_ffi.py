@@ -20,7 +20,7 @@ PN_PRUNE_AUTO, PN_PRUNE_ON, PN_PRUNE_OFF = 0, 1, 2
 EXPORTS = [
     "pn_last_error_message", "pn_abi_version", "pn_device_count",
     "pn_balltree_create_f32", "pn_balltree_create_f64", "pn_vptree_create_f32", "pn_vptree_create_f64",
-    "pn_balltree_create_dev_f32", "pn_balltree_create_dev_f64", "pn_tree_destroy",
+    "pn_balltree_create_dev_f32", "pn_balltree_create_dev_f64", "pn_tree_destroy", "pn_tree_session",
     "pn_balltree_query_f32", "pn_balltree_query_f64",
     "pn_balltree_query_nearest_f32", "pn_balltree_query_nearest_f64",
     "pn_balltree_query_radius_f32", "pn_balltree_query_radius_f64",
@@ -118,6 +118,8 @@ def lib():
         f.argtypes = [vp, sz, vp, vp]
     L.pn_tree_destroy.argtypes = [vp]
     L.pn_tree_destroy.restype = C.c_int32
+    L.pn_tree_session.argtypes = [vp, C.POINTER(vp)]
+    L.pn_tree_session.restype = C.c_int32
     L.pn_free.argtypes = [vp]
     L.pn_free.restype = None
     L.pn_tree_query_knn_dev.restype = C.c_int32

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -43,8 +44,11 @@ static int fail(int code, const std::string& msg) {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;   // an alias of another handle's array (pn_tree_session): never freed or grown here
+    void alias(const DevBuf& o) { release(); p = o.p; cap = o.cap; borrowed = true; }
     int ensure(size_t bytes) {
         if (bytes <= cap) return PN_OK;
+        if (borrowed) return fail(PN_BAD_ARG, "internal: a borrowed array cannot grow");
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
@@ -58,7 +62,7 @@ struct DevBuf {
         cap = want;
         return PN_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -106,6 +110,12 @@ struct pn_tree {
     pn_counters counters{};
     std::mutex mu;
     bool host_only = false;
+    // sessions (pn_tree_session): handles that borrow this handle's device arrays.  The owner is freed when it has been
+    // destroyed AND its last session is gone.
+    pn_tree* owner = nullptr;
+    std::atomic<int> n_sessions{0};
+    bool zombie = false;
+    virtual int session(pn_tree** out) = 0;
     virtual int knn_host(const void* q, size_t nq, size_t stride, size_t k, uint64_t* idx, void* dist) = 0;
     virtual int knn_dev(const void* q, size_t nq, size_t stride, size_t k, uint64_t* idx, void* dist,
                         cudaStream_t st, bool sync) = 0;
@@ -846,6 +856,30 @@ struct Engine final : pn_tree {
         // PN_ALGO_SIMT selects it.
         last_used_tensor = tensor_ready;
         if (last_used_tensor) return knn_device_tensor(qraw, nq, stride, k, kstride, idx_out, dist_out, st, self_query);
+        // narrow rows of a ball tree: one warp per query (knn_warp_kernel) -- every query walks its own few buckets
+        if (ft.kind == 0 && ft.d <= 8 && dt.dv <= 4) {
+            const bool wsort = !self_query && ft.n_buckets > 1 && nq >= 16384;   // neighbouring warps then share buckets in L1 / L2
+            if (!self_query) TRY(stage_queries(qraw, nq, stride, st, wsort));
+            const uint32_t WP = 32, w_pass = (k + WP - 1) / WP;
+            if (w_pass > 1) { TRY(w_floor_d.ensure((size_t)nq * sizeof(A))); TRY(w_floor_i.ensure((size_t)nq * 4)); }
+            CU(cudaEventRecord(ev[2], st));
+            for (uint32_t p = 0; p < w_pass; ++p) {
+                WarpKnnArgs<A> a{};
+                a.t = dt; a.q = self_query ? d_pts.as<V>() : w_q.as<V>();
+                a.qorder = wsort ? w_order.as<uint32_t>() : nullptr;
+                a.row_map = self_query ? d_ids.as<uint32_t>() : nullptr;
+                a.nq = nq; a.k = std::min(WP, k - p * WP);
+                a.out_i = idx_out; a.out_d = dist_out; a.out_stride = kstride; a.out_off = p * WP;
+                a.floor_d = w_pass > 1 ? w_floor_d.as<A>() : nullptr; a.floor_i = w_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr;
+                a.pass = p;
+                a.counters = w_counters.as<unsigned long long>();
+                knn_warp_kernel<A><<<(nq + 7) / 8, 256, 0, st>>>(a);
+                CU(cudaGetLastError());
+                ++counters.kernel_launches;
+            }
+            CU(cudaEventRecord(ev[3], st));
+            return PN_OK;
+        }
         const bool sort = !self_query && ft.n_buckets > 1 && nq > (uint32_t)TQ;
         if (!self_query) TRY(stage_queries(qraw, nq, stride, st, sort));
         const uint32_t tiles = (nq + TQ - 1) / TQ;
@@ -867,6 +901,11 @@ struct Engine final : pn_tree {
             a.part_d = w_part_d.as<A>(); a.part_i = w_part_i.as<uint32_t>();
             a.floor_d = p ? w_floor_d.as<A>() : nullptr; a.floor_i = p ? w_floor_i.as<uint32_t>() : nullptr;
             a.counters = w_counters.as<unsigned long long>();
+            if (n_splits > 1) {   // the splits of a query share their k-th bounds (initialised to a huge finite value)
+                TRY(w_gbound.ensure((size_t)nq * sizeof(A)));
+                CU(cudaMemsetAsync(w_gbound.p, 0x7f, (size_t)nq * sizeof(A), st));
+                a.g_bound = w_gbound.as<A>();
+            }
             TRY(launch_knn(a, dim3(tiles, n_splits), st, k1));
             CU(merge_lists<A, uint32_t>(st, w_part_d.as<A>(), w_part_i.as<uint32_t>(), n_splits, nq, kk, idx_out, dist_out, kstride, p * KP,
                 n_pass > 1 ? w_floor_d.as<A>() : nullptr, n_pass > 1 ? w_floor_i.as<uint32_t>() : nullptr,
@@ -1632,6 +1671,49 @@ struct Engine final : pn_tree {
     }
 #undef NC
 
+    // ---- sessions: a second handle onto the same device-resident tree (pn_tree_session).  The tree arrays are borrowed,
+    // everything a call writes (stream, events, workspaces, counters, the mutex) is the session's own, so calls on
+    // different sessions of one tree overlap on the device.
+    int attach(Engine& src) {
+        device = src.device;
+        DeviceGuard g(device);
+        if (!g.ok) return fail(PN_CUDA, "cudaSetDevice failed");
+        TRY(open_device());
+        ft.n = src.ft.n; ft.n_total = src.ft.n_total; ft.d = src.ft.d; ft.dpad = src.ft.dpad; ft.L = src.ft.L;
+        ft.n_internal = src.ft.n_internal; ft.n_buckets = src.ft.n_buckets; ft.n_nodes = src.ft.n_nodes;
+        ft.bucket_max = src.ft.bucket_max; ft.kind = src.ft.kind;
+        ft.bucket_lo = src.ft.bucket_lo; ft.bucket_hi = src.ft.bucket_hi; ft.vp_ids = src.ft.vp_ids;
+        kp = src.kp; algo = src.algo; tensor_ready = src.tensor_ready; pmax = src.pmax; tscale = src.tscale;
+        prune_on = src.prune_on; tiles_on = src.tiles_on; prune_opt = src.prune_opt;
+        prune_frac = src.prune_frac; seed_candidates = src.seed_candidates; tile_frac = src.tile_frac;
+        gpu_built = true;   // no host copies: layout() reads the device arrays
+        auto mine = replica_arrays();
+        auto theirs = src.replica_arrays();
+        for (size_t i = 0; i < mine.size(); ++i) mine[i].first->alias(*theirs[i].first);
+        fill_dev_tree();
+        TRY(w_counters.ensure(256));
+        info = src.info;
+        info.device_bytes = 0;   // nothing of the tree is owned here
+        if (src.aux) {
+            aux.reset(new Engine<A>());
+            TRY(aux->attach(*src.aux));
+        }
+        return PN_OK;
+    }
+    int session(pn_tree** out) override {
+        if (host_only) return fail(PN_BAD_ARG, "a host-only tree has no device arrays to share");
+        pn_tree* root = owner ? owner : this;   // a session of a session borrows from the same owner
+        std::unique_ptr<Engine<A>> e(new Engine<A>());
+        {
+            std::lock_guard<std::mutex> lk(mu);   // no call of this handle is attaching a companion meanwhile
+            TRY(e->attach(*this));
+        }
+        e->owner = root;
+        root->n_sessions.fetch_add(1);
+        *out = e.release();
+        return PN_OK;
+    }
+
     int layout(uint32_t* ids, uint32_t* blo, uint32_t* bhi, void* rad, void* cen, void* pts) override {
         if (gpu_built) {
             DeviceGuard g(device);
@@ -1897,7 +1979,21 @@ int32_t pn_balltree_create_dev_f64(const double* p, size_t n, size_t d, size_t r
     GUARD_BEGIN return create_tree_dev<double>(p, n, d, rs, o, out); GUARD_END
 }
 int32_t pn_tree_destroy(pn_tree* t) {
-    GUARD_BEGIN delete t; return PN_OK; GUARD_END
+    GUARD_BEGIN
+    if (!t) return PN_OK;
+    if (t->n_sessions.load() > 0) { t->zombie = true; return PN_OK; }   // its sessions still read its arrays: freed with the last one
+    pn_tree* owner = t->owner;
+    delete t;
+    if (owner && owner->n_sessions.fetch_sub(1) == 1 && owner->zombie) delete owner;
+    return PN_OK;
+    GUARD_END
+}
+int32_t pn_tree_session(pn_tree* t, pn_tree** out) {
+    GUARD_BEGIN
+    if (!t || !out) return fail(PN_BAD_ARG, "null argument");
+    *out = nullptr;
+    return t->session(out);
+    GUARD_END
 }
 
 int32_t pn_balltree_query_f32(pn_tree* t, const float* q, size_t nq, size_t qs, size_t k, uint64_t* io, float* dd) {

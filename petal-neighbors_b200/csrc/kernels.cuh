@@ -242,7 +242,13 @@ struct KnnArgs {
     const A* floor_d;            // optional [nq] floor keys (multi-pass k > K)
     const uint32_t* floor_i;
     unsigned long long* counters;  // [0] pairs, [1] node visits
+    // split scans only (may be null): per query, the smallest k-th distance any split's list has reached so far.  It is
+    // an upper bound of the final k-th distance, so every split may prune with it (strictly: lb > bound); without it a
+    // split far from the query starts from +inf and walks its whole subtree's near side before its own list is full.
+    A* g_bound;                  // [nq] by query id, initialised to a huge finite value
 };
+__device__ __forceinline__ void publish_bound(float* p, float v) { atomicMin(reinterpret_cast<int*>(p), __float_as_int(v)); }
+__device__ __forceinline__ void publish_bound(double* p, double v) { atomicMin(reinterpret_cast<long long*>(p), __double_as_longlong(v)); }
 
 // ---- the tile scan: one CTA = 128 queries (one per thread), DFS over the flattened tree with
 // block-uniform control flow, buckets staged through shared memory with 16-byte loads, every
@@ -287,6 +293,17 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
     typename TileTopK<A, K, DVR>::type topk;
     topk.init(active, k);
     if (a.floor_d && active) topk.set_floor(a.floor_d[qid], a.floor_i[qid]);
+    // pruning bound: this split's own k-th distance, or a smaller one another split of the same query has published
+    A* const gb = a.g_bound && active ? a.g_bound + qid : nullptr;
+    auto bound = [&]() -> A {
+        const A own = topk.kth();
+        if (!gb) return own;
+        const A g = __ldcg(gb);
+        return own < g ? own : g;
+    };
+    auto publish = [&]() {
+        if (gb) { const A own = topk.kth(); if (own < __ldcg(gb)) publish_bound(gb, own); }
+    };
 
     unsigned long long my_pairs = 0, my_visits = 0;
     int parity = 0;
@@ -395,17 +412,19 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
                 if (R < A(0)) continue;  // empty
                 const A cd = dist_to(t.centers + (size_t)node * DV);
                 const A lb = xsub(xsub(cd, R), xmul(t.slack, xadd(cd, R)));
-                const bool need = active && !(lb > topk.kth());
+                const bool need = active && !(lb > bound());
                 if (!__syncthreads_or(need)) continue;
                 scan_bucket(node - t.n_internal, need);
+                publish();
             } else {
                 const uint32_t c1 = 2 * node + 1, c2 = c1 + 1;
                 const A R1 = t.radii[c1], R2 = t.radii[c2];
                 A lb1 = pos_inf<A>(), lb2 = pos_inf<A>();
                 if (!(R1 < A(0))) { const A cd = dist_to(t.centers + (size_t)c1 * DV); lb1 = xsub(xsub(cd, R1), xmul(t.slack, xadd(cd, R1))); }
                 if (!(R2 < A(0))) { const A cd = dist_to(t.centers + (size_t)c2 * DV); lb2 = xsub(xsub(cd, R2), xmul(t.slack, xadd(cd, R2))); }
-                const bool need1 = active && !(R1 < A(0)) && !(lb1 > topk.kth());
-                const bool need2 = active && !(R2 < A(0)) && !(lb2 > topk.kth());
+                const A bnd = bound();
+                const bool need1 = active && !(R1 < A(0)) && !(lb1 > bnd);
+                const bool need2 = active && !(R2 < A(0)) && !(lb2 > bnd);
                 int n1, n2, npref, nany;
                 block_counts(votes, parity, need1, need2, (need1 || need2) && (lb1 < lb2), need1 || need2, n1, n2, npref, nany);
                 // nearer child first (:232-236), decided by the tile's majority
@@ -433,10 +452,12 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
             const uint32_t node = stack[sp];
             const A lb = lbs[sp];
             ++my_visits;
-            const bool need = active && !(lb > topk.kth());
+            const A bnd = bound();
+            const bool need = active && !(lb > bnd);
             if (node >= t.n_internal) {
                 if (!__syncthreads_or(need)) continue;
                 scan_bucket(node - t.n_internal, need);
+                publish();
             } else {
                 const A mu = t.radii[node];
                 const A dq = dist_to(t.centers + (size_t)node * DV);
@@ -444,8 +465,10 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
                 const A s = xmul(t.slack, xadd(dq, mu));
                 const A lbn = fmax(lb, xsub(xsub(dq, mu), s));   // near side: d(p,vp) <= mu
                 const A lbf = fmax(lb, xsub(xsub(mu, dq), s));   // far side:  d(p,vp) >= mu
-                const bool needn = active && !(lbn > topk.kth());
-                const bool needf = active && !(lbf > topk.kth());
+                const A own = topk.kth();   // the vantage point may just have tightened this split's list
+                const A bnd2 = own < bnd ? own : bnd;
+                const bool needn = active && !(lbn > bnd2);
+                const bool needf = active && !(lbf > bnd2);
                 int nn, nf, npref, nany;
                 block_counts(votes, parity, needn, needf, (needn || needf) && (dq < mu), needn || needf, nn, nf, npref, nany);
                 const bool near_first = 2 * npref >= nany;  // :111 `distance < radius` -> near first
@@ -471,6 +494,135 @@ __global__ void __launch_bounds__(TQ) knn_tile_kernel(const KnnArgs<A> a) {
         __syncthreads();
         if (tid == 0) { atomicAdd(&a.counters[0], s_pairs); atomicAdd(&a.counters[1], s_visits); }
     }
+}
+
+// ---- the warp scan: ONE WARP PER QUERY, for narrow rows (dv <= 4: f32 d <= 16, f64 d <= 8) where the ball bounds prune
+// almost everything and a query needs a handful of buckets.  The tile scan above walks the UNION of what its 128 queries
+// need, one node after the other: fine when a batch is dense in the tree (a tile's queries share their buckets), a
+// long serial chain when it is not (4096 queries on a 10M x 3 tree: 21.7 ms, against 11 ms for 262 144).  Here every
+// query walks its own path (BallTree::nearest_k_neighbors_in_subtree, src/ball_tree.rs:203-243): nearer child first,
+// a node is skipped iff its conservative lower bound exceeds the current k-th distance (strict, :212); the lanes fold
+// the points of a bucket 32 at a time and the sorted top-k list lives across the lanes (lane i = i-th best, up to 32 per
+// pass), keyed on (sqrt'd distance, index) like every other list of the engine.  Results go straight to the output
+// rows: no splits, no merge.
+template <typename A>
+struct WarpKnnArgs {
+    DevTree<A> t;
+    const typename VT<A>::V* q;    // nq x dpad, zero padded
+    const uint32_t* qorder;        // sorted slot -> query id (cache locality between neighbouring warps), may be null
+    const uint32_t* row_map;       // query id -> output row (self query: the stored point's original index), may be null
+    uint32_t nq, k;                // k <= 32 per pass
+    uint64_t* out_i;
+    A* out_d;
+    uint32_t out_stride, out_off;
+    A* floor_d;                    // [nq] (multi-pass k > 32): in = the last key of the previous pass (pass > 0), out = this pass's
+    uint32_t* floor_i;
+    uint32_t pass;
+    unsigned long long* counters;  // [0] pairs, [1] node visits
+};
+template <typename A>
+__global__ void __launch_bounds__(256) knn_warp_kernel(const WarpKnnArgs<A> a) {
+    using V = typename VT<A>::V;
+    const DevTree<A>& t = a.t;
+    const int lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= a.nq) return;
+    const uint32_t qid = a.qorder ? a.qorder[slot] : slot;
+    const unsigned full = 0xffffffffu;
+    const int DV = (int)t.dv;   // <= 4
+    V qreg[4];
+#pragma unroll
+    for (int jc = 0; jc < 4; ++jc) qreg[jc] = jc < DV ? __ldg(a.q + (size_t)qid * DV + jc) : vzero(A(0));
+    auto dist2_to = [&](const V* row) -> A {
+        A acc = A(0);
+#pragma unroll
+        for (int jc = 0; jc < 4; ++jc)
+            if (jc < DV) acc = fold(acc, qreg[jc], __ldg(row + jc));
+        return acc;
+    };
+    // the list: lane i holds the i-th best (distance, index); +inf / NO_ID = empty
+    A kd = pos_inf<A>();
+    uint32_t ki = NO_ID;
+    A kth_d = pos_inf<A>();      // key of entry k-1 (warp-uniform): the pruning bound and the admission threshold
+    uint32_t kth_i = NO_ID;
+    A t2 = pos_inf<A>();         // squared-domain filter for kth_d
+    const uint32_t k = a.k;
+    const bool has_floor = a.pass > 0;
+    const A fl_d = has_floor ? a.floor_d[qid] : A(0);
+    const uint32_t fl_i = has_floor ? a.floor_i[qid] : 0u;
+    auto insert = [&](A cd, uint32_t ci) {   // warp-uniform candidate
+        if (has_floor && !(cd > fl_d || (cd == fl_d && ci > fl_i))) return;   // already reported by an earlier pass
+        const bool less = kd < cd || (kd == cd && ki < ci);
+        const uint32_t pos = __popc(__ballot_sync(full, less));   // held entries smaller than the candidate: a prefix
+        if (pos >= k) return;
+        const A ud = __shfl_up_sync(full, kd, 1);
+        const uint32_t ui = __shfl_up_sync(full, ki, 1);
+        if ((uint32_t)lane > pos) { kd = ud; ki = ui; }
+        else if ((uint32_t)lane == pos) { kd = cd; ki = ci; }
+        kth_d = __shfl_sync(full, kd, (int)k - 1);
+        kth_i = __shfl_sync(full, ki, (int)k - 1);
+        t2 = kth_i == NO_ID ? pos_inf<A>() : thresh2(kth_d);
+    };
+    unsigned long long pairs = 0, visits = 0;
+    uint32_t stack[MAX_STACK];
+    A lbs[MAX_STACK];
+    int sp = 0;
+    stack[0] = 0; lbs[0] = -pos_inf<A>(); sp = 1;
+    while (sp) {
+        --sp;
+        const uint32_t node = stack[sp];
+        if (lbs[sp] > kth_d) continue;   // the bound has tightened since this node was pushed
+        ++visits;
+        if (node >= t.n_internal) {
+            const uint32_t b = node - t.n_internal;
+            const uint32_t lo = __ldg(t.bucket_lo + b), hi = __ldg(t.bucket_hi + b);
+            pairs += hi - lo;
+            for (uint32_t base = lo; base < hi; base += 32) {
+                const uint32_t p = base + lane;
+                A acc = pos_inf<A>();
+                if (p < hi) acc = dist2_to(t.pts + (size_t)p * DV);
+                unsigned mask = __ballot_sync(full, acc <= t2);
+                if (!mask) continue;
+                A dd = A(0);
+                uint32_t id = NO_ID;
+                if ((mask >> lane) & 1u) { dd = xsqrt(acc); id = __ldg(t.ids + p); }
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const A cd = __shfl_sync(full, dd, src);
+                    const uint32_t ci = __shfl_sync(full, id, src);
+                    if (cd < kth_d || (cd == kth_d && ci < kth_i)) insert(cd, ci);
+                }
+            }
+        } else {
+            // lanes 0 and 1 take one child each
+            const uint32_t c = 2 * node + 1 + (uint32_t)(lane & 1);
+            const A R = __ldg(t.radii + c);
+            A lb = pos_inf<A>();
+            if (lane < 2 && !(R < A(0))) {
+                const A cd = xsqrt(dist2_to(t.centers + (size_t)c * DV));
+                lb = xsub(xsub(cd, R), xmul(t.slack, xadd(cd, R)));
+            }
+            const A lb1 = __shfl_sync(full, lb, 0), lb2 = __shfl_sync(full, lb, 1);
+            const uint32_t c1 = 2 * node + 1, c2 = c1 + 1;
+            const bool n1 = !(lb1 > kth_d) && lb1 < pos_inf<A>(), n2 = !(lb2 > kth_d) && lb2 < pos_inf<A>();
+            // nearer child first (:232-236): it is pushed last
+            if (lb1 < lb2) {
+                if (n2) { stack[sp] = c2; lbs[sp] = lb2; ++sp; }
+                if (n1) { stack[sp] = c1; lbs[sp] = lb1; ++sp; }
+            } else {
+                if (n1) { stack[sp] = c1; lbs[sp] = lb1; ++sp; }
+                if (n2) { stack[sp] = c2; lbs[sp] = lb2; ++sp; }
+            }
+        }
+    }
+    const size_t orow = a.row_map ? a.row_map[qid] : qid;
+    if ((uint32_t)lane < k) {
+        a.out_d[orow * a.out_stride + a.out_off + lane] = kd;
+        a.out_i[orow * a.out_stride + a.out_off + lane] = ki == NO_ID ? ~0ull : (uint64_t)ki;
+    }
+    if (a.floor_d && (uint32_t)lane == k - 1) { a.floor_d[qid] = kd; a.floor_i[qid] = ki; }
+    if (a.counters && lane == 0) { atomicAdd(&a.counters[0], pairs); atomicAdd(&a.counters[1], visits); }
 }
 
 // ---- k-way merge of sorted (distance, index) lists: split scans of one GPU, or the gathered

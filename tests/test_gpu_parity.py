@@ -369,6 +369,48 @@ def test_concurrent_queries_on_one_handle(pn, oracle):
             assert np.array_equal(out[i][0], boffs.astype(np.uint64)) and np.array_equal(out[i][1], bind.astype(np.uint64))
 
 
+@pytest.mark.parametrize("kind,d", [("ball", 3), ("ball", 32), ("vp", 24)])
+def test_sessions_concurrent_callers(pn, oracle, kind, d):
+    """pn_tree_session: every thread queries through its own session of one tree (own stream and workspaces, the tree's
+    arrays shared); results equal the oracle's; the tree may be destroyed before its sessions."""
+    import threading
+    from petal_neighbors_b200 import synth
+    n, nq, k = 30000, 4000, 10
+    pts = synth.uniform(n, d, 71, np.float32)
+    tree = (pn.BallTree if kind == "ball" else pn.VantagePointTree).euclidean(pts)
+    Qs = [synth.uniform(nq, d, 80 + t, np.float32) for t in range(4)]
+    sessions = [tree.session() for _ in Qs]
+    assert sessions[0].info()["device_bytes"] == 0 and sessions[0].num_points() == n
+    tree.close()   # the sessions keep the arrays alive
+    out = [None] * len(Qs)
+
+    def work(t):
+        for _ in range(3):
+            if kind == "ball":
+                out[t] = sessions[t].query_batch(Qs[t], k) + sessions[t].query_radius_batch(Qs[t][:200], 0.2 if d == 3 else 1.2)
+            else:
+                ni, nd = sessions[t].query_nearest_batch(Qs[t])
+                out[t] = (ni[:, None], nd[:, None])
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(len(Qs))]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    for t, Q in enumerate(Qs):
+        kk = k if kind == "ball" else 1
+        oi, od = oracle.brute_knn(pts, Q, kk)
+        assert_knn_equal(out[t][0], out[t][1], oi, od)
+        if kind == "ball":
+            boffs, bind = oracle.brute_radius(pts, Q[:200], np.float32(0.2 if d == 3 else 1.2))
+            assert np.array_equal(out[t][2], boffs.astype(np.uint64)) and np.array_equal(out[t][3], bind.astype(np.uint64))
+    s2 = sessions[0].session()   # a session of a session borrows from the same owner
+    for x in sessions:
+        x.close()
+    oi, od = oracle.brute_knn(pts, Qs[0][:64], 1)
+    ni, nd = s2.query_nearest_batch(Qs[0][:64])
+    assert np.array_equal(ni, oi[:, 0].astype(np.uint64))
+    s2.close()
+
+
 def test_randomized_shapes_all_entry_points(pn, oracle):
     """Seeded sweep over random (n, d, nq, k, bucket, dtype, engine): k-NN, 1-NN, radius, VP 1-NN and
     self-query against the oracle; every case bit-exact."""
