@@ -350,7 +350,20 @@ def extra_c4(pn, torch, synth, steps):
     b_alg = n * d * 4 + nq * d * 4 + 8 * (nq + 1) + 8 * hits + ctr["pairs"] * d * 4 / 128.0
     pk = peaks()
     ach = b_alg / (m * 1e-3) / 1e9
-    return {"workload": "BallTree::query_radius 10M x 3 f32 uniform, 1M queries, r = 0.01 (BASELINE config 4)",
+    # k-NN (k = 10) on the same tree: narrow rows take the warp-per-query scan
+    kw, kd, kc = [], [], None
+    for it in range(steps + 1):
+        t0 = time.perf_counter()
+        bt.query_batch(Q, 10)
+        dt = time.perf_counter() - t0
+        kc = bt.counters()
+        if it:
+            kw.append(dt); kd.append(kc["device_ms"])
+    knn = {"workload": "BallTree::query on the same tree, 1M queries, k = 10 (warp-per-query scan)", "ms_per_step": float(np.mean(kd)),
+           "value": nq / (float(np.mean(kd)) * 1e-3), "unit": UNIT, "scan_ms": kc["scan_ms"], "pairs_per_query": kc["pairs"] / nq,
+           "e2e": {"value": nq / float(np.mean(kw)), "unit": UNIT, "h2d_bytes_per_step": int(kc["h2d_bytes"]), "d2h_bytes_per_step": int(kc["d2h_bytes"]),
+                   "note": "wall clock around pn_balltree_query_f32, pageable numpy buffers"}}
+    return {"knn_k10": knn, "workload": "BallTree::query_radius 10M x 3 f32 uniform, 1M queries, r = 0.01 (BASELINE config 4)",
             "ms_per_step": m, "value": nq / (m * 1e-3), "unit": UNIT, "steps": len(dev),
             "timing": "device_ms of the host-buffer call (pipelined chunks: H2D, traversal, D2H of the CSR result)",
             "hits_per_query": hits / nq, "pairs_per_query": ctr["pairs"] / nq, "pairs_over_NQ": ctr["pairs"] / (float(n) * nq),
@@ -359,6 +372,32 @@ def extra_c4(pn, torch, synth, steps):
             "build_seconds": info["build_seconds"], "build": "on the device",
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "algorithmic_bytes": b_alg,
                          "note": "d = 3 prunes to ~1.2e3 pairs per query: bound by traversal latency and host-side result handling, not by HBM"}}
+
+
+def extra_c1(pn, synth, steps):
+    """BASELINE config 1 (the reference's own bench, benches/ball_tree.rs:53-59): BallTree 10k x 3 f64, every point a
+    query, k = 10; host buffers in and out (query_batch) and the no-upload self query."""
+    n, d, k = 10_000, 3, 10
+    pts = synth.uniform(n, d, 1, np.float64)
+    bt = pn.BallTree.euclidean(pts)
+    wall, dev, ctr = [], [], None
+    for it in range(10 * steps + 1):
+        t0 = time.perf_counter()
+        idx, dist = bt.query_batch(pts, k)
+        dt = time.perf_counter() - t0
+        ctr = bt.counters()
+        if it:
+            wall.append(dt); dev.append(ctr["device_ms"])
+    t0 = time.perf_counter()
+    for it in range(10):
+        si, sd = bt.query_self(k)
+    self_s = (time.perf_counter() - t0) / 10
+    return {"workload": "BallTree 10k x 3 f64, every point a query, k = 10 (BASELINE config 1)", "ms_per_step": float(np.mean(dev)),
+            "value": n / (float(np.mean(dev)) * 1e-3), "unit": UNIT, "steps": len(dev), "scan_ms": ctr["scan_ms"], "pairs_over_NQ": ctr["pairs"] / float(n * n),
+            "e2e": {"value": n / float(np.mean(wall)), "unit": UNIT, "h2d_bytes_per_step": int(ctr["h2d_bytes"]), "d2h_bytes_per_step": int(ctr["d2h_bytes"]),
+                    "note": "wall clock around pn_balltree_query_f64, pageable numpy buffers"},
+            "self_query": {"value": n / self_s, "unit": UNIT, "same_rows": bool(np.array_equal(si, idx) and np.array_equal(sd, dist))},
+            "path": "warp-per-query scan (f64, d = 3)"}
 
 
 def extra_multi_gpu(pn, torch, dist, synth, comm, rank, world, local, steps):
@@ -587,7 +626,7 @@ def main():
 
     # ---------------- the other configurations ----------------
     extra = {}
-    want = set(x for x in args.extras.split(",") if x) or {"t128", "c3", "c4", "multi"}
+    want = set(x for x in args.extras.split(",") if x) or {"t128", "c3", "c4", "c1", "multi"}
     if not args.no_extras and not reduced and wl == "c2":
         del q_dev, idx_dev, dist_dev, q_pin, idx_pin, dist_pin
         esteps = max(1, min(args.steps, 3))
@@ -595,7 +634,8 @@ def main():
         if world == 1:
             for name, fnx in (("t128", lambda: extra_t128(pn, torch, synth, stream, flush, esteps)),
                               ("c3", lambda: extra_c3(pn, torch, synth, stream, flush, esteps)),
-                              ("c4", lambda: extra_c4(pn, torch, synth, esteps))):
+                              ("c4", lambda: extra_c4(pn, torch, synth, esteps)),
+                              ("c1", lambda: extra_c1(pn, synth, esteps))):
                 if name not in want:
                     continue
                 try:
