@@ -153,6 +153,12 @@ template <typename A> class BallTree {
     void query_self(size_t k, uint64_t* idx_out, A* dist_out) const { detail::check(detail::Abi<A>::self(h_, k, idx_out, dist_out)); }
     size_t num_points() const { return n_; }
     pn_tree* handle() const { return h_; }
+    // a second handle onto the same device-resident tree (own stream and workspaces) for a concurrent caller
+    BallTree session() const {
+        BallTree s(n_, d_);
+        detail::check(pn_tree_session(h_, &s.h_));
+        return s;
+    }
 
   private:
     void check_view(const View2<A>& q) const {
@@ -163,6 +169,7 @@ template <typename A> class BallTree {
     BallTree(const View2<A>& p, const pn_build_opts* opts) : n_(p.rows), d_(p.cols) {
         detail::check_create(detail::Abi<A>::ball_create(p.data, p.rows, p.cols, p.row_stride, p.col_stride, opts, &h_));
     }
+    BallTree(size_t n, size_t d) : n_(n), d_(d) {}   // session(): the handle is filled in by pn_tree_session
     pn_tree* h_ = nullptr;
     size_t n_, d_;
 };

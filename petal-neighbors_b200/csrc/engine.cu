@@ -1061,13 +1061,20 @@ struct Engine final : pn_tree {
         CU(cudaStreamWaitEvent(s_in, ev[0], 0));
         // Enqueue order: H2D(c), kernels(c), then D2H(c-1).  With pageable host memory a D2H copy blocks the host until it
         // is done, so it is issued only after the next chunk's kernels are already queued behind it on the device.
+        // Large results bound for pageable memory go through the engine's own pinned staging (copy_out_bytes).
+        const bool staged_out = is_pageable(idx) || is_pageable(dist);
         auto d2h = [&](size_t c) -> int {
             const int b = (int)(c & 1);
             const size_t q0 = cb[c];
             const uint32_t cq = (uint32_t)(cb[c + 1] - q0);
             CU(cudaStreamWaitEvent(s_out, e_cmp[b], 0));
-            CU(cudaMemcpyAsync(idx + q0 * k, w_oi2[b].p, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, s_out));
-            CU(cudaMemcpyAsync(dist + q0 * k, w_od2[b].p, (size_t)cq * k * sizeof(A), cudaMemcpyDeviceToHost, s_out));
+            if (staged_out && (size_t)cq * k * 8 >= ((size_t)4 << 20)) {
+                TRY(copy_out_bytes(idx + q0 * k, w_oi2[b].p, (size_t)cq * k * 8, s_out));
+                TRY(copy_out_bytes(dist + q0 * k, w_od2[b].p, (size_t)cq * k * sizeof(A), s_out));
+            } else {
+                CU(cudaMemcpyAsync(idx + q0 * k, w_oi2[b].p, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, s_out));
+                CU(cudaMemcpyAsync(dist + q0 * k, w_od2[b].p, (size_t)cq * k * sizeof(A), cudaMemcpyDeviceToHost, s_out));
+            }
             CU(cudaEventRecord(e_out[b], s_out));
             counters.d2h_bytes += (uint64_t)cq * k * (8 + sizeof(A));
             return PN_OK;
@@ -1153,6 +1160,50 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 
+    // Device -> PAGEABLE host memory: the driver's own staged copy runs at about 4 GB/s into freshly allocated pages (it
+    // faults them in one by one).  Same pipeline as copy_out_widen: D2H in 16 MB pieces through two pinned buffers; while
+    // piece p+1 is in flight, piece p is copied to its destination by a few host threads (page faults in parallel).
+    int copy_out_bytes(void* dstv, const void* src_devv, size_t bytes, cudaStream_t st) {
+        if (bytes == 0) return PN_OK;
+        for (int i = 0; i < 2; ++i) {
+            if (!pin_stage[i]) CU(cudaHostAlloc(&pin_stage[i], PIN_BYTES, cudaHostAllocDefault));
+            if (!pin_ev[i]) CU(cudaEventCreateWithFlags(&pin_ev[i], cudaEventDisableTiming));
+        }
+        unsigned char* dst = (unsigned char*)dstv;
+        const unsigned char* src = (const unsigned char*)src_devv;
+        const size_t per = PIN_BYTES;
+        const size_t pieces = (bytes + per - 1) / per;
+        auto issue = [&](size_t p) -> int {
+            const size_t off = p * per, cnt = std::min(per, bytes - off);
+            CU(cudaMemcpyAsync(pin_stage[p & 1], src + off, cnt, cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(pin_ev[p & 1], st));
+            return PN_OK;
+        };
+        TRY(issue(0));
+        const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+        for (size_t p = 0; p < pieces; ++p) {
+            CU(cudaEventSynchronize(pin_ev[p & 1]));
+            if (p + 1 < pieces) TRY(issue(p + 1));  // the other buffer was consumed in the previous iteration
+            const size_t off = p * per, cnt = std::min(per, bytes - off);
+            const unsigned char* sp = (const unsigned char*)pin_stage[p & 1];
+            unsigned char* dp = dst + off;
+            const size_t chunk = ((cnt + nt - 1) / nt + 4095) & ~(size_t)4095;
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nt; ++t) {
+                const size_t b = t * chunk, e = std::min(cnt, b + chunk);
+                if (b < e) th.emplace_back([=] { memcpy(dp + b, sp + b, e - b); });
+            }
+            memcpy(dp, sp, std::min(cnt, chunk));
+            for (auto& x : th) x.join();
+        }
+        return PN_OK;
+    }
+    static bool is_pageable(const void* p) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+        return at.type == cudaMemoryTypeUnregistered;
+    }
+
     // every stored point is a query (benches/ball_tree.rs:53-59): no H2D at all
     int knn_self(size_t k, uint64_t* idx, void* distv, bool dev, cudaStream_t st, bool sync) override {
         if (host_only) return fail(PN_CUDA, "tree was built with PN_FLAG_HOST_ONLY: no device, and there is no CPU fallback");
@@ -1177,8 +1228,13 @@ struct Engine final : pn_tree {
         CU(cudaEventRecord(ev[0], st));
         TRY(knn_device(d_pts.as<A>(), nq, ft.dpad, (uint32_t)k, oi, od, st, true));
         if (!dev) {
-            CU(cudaMemcpyAsync(idx, oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(distv, od, (size_t)nq * k * sizeof(A), cudaMemcpyDeviceToHost, st));
+            if ((is_pageable(idx) || is_pageable(distv)) && (size_t)nq * k * 8 >= ((size_t)4 << 20)) {
+                TRY(copy_out_bytes(idx, oi, (size_t)nq * k * 8, st));
+                TRY(copy_out_bytes(distv, od, (size_t)nq * k * sizeof(A), st));
+            } else {
+                CU(cudaMemcpyAsync(idx, oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(distv, od, (size_t)nq * k * sizeof(A), cudaMemcpyDeviceToHost, st));
+            }
             counters.d2h_bytes = (uint64_t)nq * k * (8 + sizeof(A));
         }
         CU(cudaEventRecord(ev[1], st));

@@ -38,6 +38,7 @@ extern "C" {
     pub fn pn_vptree_create_f64(p: *const f64, n: usize, d: usize, row_stride: usize, col_stride: usize,
                                 opts: *const pn_build_opts, out: *mut *mut pn_tree) -> i32;
     pub fn pn_tree_destroy(t: *mut pn_tree) -> i32;
+    pub fn pn_tree_session(t: *mut pn_tree, out: *mut *mut pn_tree) -> i32;
     pub fn pn_balltree_query_f32(t: *mut pn_tree, q: *const f32, nq: usize, q_row_stride: usize, k: usize,
                                  idx: *mut u64, dist: *mut f32) -> i32;
     pub fn pn_balltree_query_f64(t: *mut pn_tree, q: *const f64, nq: usize, q_row_stride: usize, k: usize,

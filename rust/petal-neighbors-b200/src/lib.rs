@@ -206,6 +206,15 @@ impl<'a, A: Element> BallTree<'a, A, Euclidean> {
     pub fn num_points(&self) -> usize {
         self.n
     }
+
+    /// A second handle onto the same device-resident tree with its own stream and workspaces (`pn_tree_session`):
+    /// queries through `&self` from several threads are legal but serialise inside the library; give every thread
+    /// its own session and they overlap on the GPU.  Nothing of the tree is copied.
+    pub fn session(&self) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ffi::pn_tree_session(self.handle.0, &mut h) });
+        Self { handle: Handle(h), n: self.n, d: self.d, metric: Euclidean::default(), _p: PhantomData }
+    }
 }
 
 /// Vantage-point tree (reference src/vantage_point_tree.rs).

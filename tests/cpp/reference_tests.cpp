@@ -103,6 +103,8 @@ static void vp_euclidian() {  // src/vantage_point_tree.rs:220-233
     CHECK(kq.first == kb.first && kq.second == kb.second);
     CHECK(vp.query({0.95, 1.96}, 9).first.size() == 6);
     CHECK(vp.query_radius({0.95, 1.96}, 0.3) == bt.query_radius({0.95, 1.96}, 0.3));
+    auto s2 = bt.session();   // a second handle onto the same tree
+    CHECK(s2.query({0.95, 1.96}, 4).first == kb.first && s2.num_points() == 6);
 }
 static void ball_tree_query_property() {  // src/ball_tree.rs:742-765: tree distances == naive distances
     const size_t N = 40, D = 3;
