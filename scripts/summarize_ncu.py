@@ -20,7 +20,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 WHAT = {"c2": ("knn_filter", "BASELINE config 2 at the bench's own launch size: 1M x 16 f32 points, 1 000 000 queries, k = 10 (`scripts/ncu_targets.py c2`; seeded dense plan: main launch of 13 whole waves = 985 088 queries, then the tail launch)"),
         "t128": ("knn_filter", "north-star shape 10M x 128 f32, 75 776 queries = two whole waves of 148 CTAs x 256 queries, k = 10 (`scripts/ncu_targets.py t128`)"),
         "c3": ("knn_filter", "VantagePointTree 1M x 64 f32 mixture, 303 104 queries, query_nearest: the seeded tensor scan on the ball partition (`scripts/ncu_targets.py c3`)"),
-        "c4": ("radius", "BallTree::query_radius 10M x 3 f32, r = 0.01, 262 144 queries in one chunk (`scripts/ncu_targets.py c4`)")}
+        "c4": ("radius", "BallTree::query_radius 10M x 3 f32, r = 0.01, 262 144 queries in one chunk (`scripts/ncu_targets.py c4`)"),
+        "c4knn": ("knn_warp", "BallTree::query 10M x 3 f32, 1 000 000 device-resident queries, k = 10: the warp-per-query scan (`scripts/ncu_targets.py c4knn`)"),
+        "c1": ("knn_warp", "BASELINE config 1: BallTree 10k x 3 f64, every point a query (query_self), k = 10 (`scripts/ncu_targets.py c1`)")}
 for w, (kern, desc) in WHAT.items():
     path = os.path.join(G, f"r02_full_{w}_raw.csv")
     if not os.path.exists(path):
@@ -40,7 +42,7 @@ for w, (kern, desc) in WHAT.items():
         out.append("")
     open(os.path.join(P, f"r02_ncu_full_{kern}_{w}.md"), "w").write("\n".join(out) + "\n")
     print("wrote", f"r02_ncu_full_{kern}_{w}.md")
-for w in ("c2", "c3", "c4"):
+for w in ("c2", "c3", "c4", "c4knn", "c1"):
     path = os.path.join(G, f"r02_launches_{w}.csv")
     if not os.path.exists(path):
         continue
