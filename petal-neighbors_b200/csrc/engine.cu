@@ -103,6 +103,8 @@ struct PeerShared {
     void fail() { std::lock_guard<std::mutex> lk(mu); failed = true; cv.notify_all(); }
 };
 
+static std::mutex g_life;   // lifetime bookkeeping of trees and their sessions (pn_tree_destroy, pn_tree_session)
+
 // The opaque handle.
 struct pn_tree {
     virtual ~pn_tree() {}
@@ -1765,7 +1767,10 @@ struct Engine final : pn_tree {
             TRY(e->attach(*this));
         }
         e->owner = root;
-        root->n_sessions.fetch_add(1);
+        {
+            std::lock_guard<std::mutex> lk(g_life);
+            root->n_sessions.fetch_add(1);
+        }
         *out = e.release();
         return PN_OK;
     }
@@ -2037,10 +2042,16 @@ int32_t pn_balltree_create_dev_f64(const double* p, size_t n, size_t d, size_t r
 int32_t pn_tree_destroy(pn_tree* t) {
     GUARD_BEGIN
     if (!t) return PN_OK;
-    if (t->n_sessions.load() > 0) { t->zombie = true; return PN_OK; }   // its sessions still read its arrays: freed with the last one
-    pn_tree* owner = t->owner;
+    pn_tree* owner = nullptr;
+    bool free_owner = false;
+    {
+        std::lock_guard<std::mutex> lk(g_life);   // destroys of a tree and of its sessions may race
+        if (t->n_sessions.load() > 0) { t->zombie = true; return PN_OK; }   // its sessions still read its arrays: freed with the last one
+        owner = t->owner;
+        if (owner) free_owner = owner->n_sessions.fetch_sub(1) == 1 && owner->zombie;
+    }
     delete t;
-    if (owner && owner->n_sessions.fetch_sub(1) == 1 && owner->zombie) delete owner;
+    if (free_owner) delete owner;
     return PN_OK;
     GUARD_END
 }
