@@ -627,8 +627,7 @@ struct Engine final : pn_tree {
             }
             TRY(w_seed.ensure((size_t)nq * 4));
             const DevTree<float>& dtf = *reinterpret_cast<DevTree<float>*>(&dt);
-            if (k == 1) tc::seed_bound_kernel<1><<<(nq + 127) / 128, 128, 0, st>>>(dtf, *qsorted, *order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
-            else tc::seed_bound_kernel<16><<<(nq + 127) / 128, 128, 0, st>>>(dtf, *qsorted, *order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
+            tc::seed_bound_kernel<<<(nq + 7) / 8, 256, 0, st>>>(dtf, *qsorted, *order, w_home.as<uint32_t>(), nq, k, w_seed.as<float>());
             CU(cudaGetLastError());
             ++counters.kernel_launches;
             return PN_OK;
