@@ -70,6 +70,16 @@ typedef enum pn_builder { PN_BUILDER_AUTO = 0, PN_BUILDER_HOST = 1, PN_BUILDER_D
  * skips the set-up passes.  Results are identical either way. */
 typedef enum pn_prune { PN_PRUNE_AUTO = 0, PN_PRUNE_ON = 1, PN_PRUNE_OFF = 2 } pn_prune;
 
+/* Which partition of the points the tensor path scans (k-NN batches of f32 trees with d >= 16).  Exact results do not depend
+ * on it; what the tile bitmaps of the pruned scan can skip does.  REFERENCE: the tree's own stored order (the reference's
+ * split: median of the widest coordinate, src/ball_tree.rs:577-613).  TWO_MEANS: the handle also keeps a second ball tree
+ * over the same rows whose splits follow the line through the two centroids of a 2-means clustering of each node -- buckets
+ * follow clusters instead of cutting through them -- and answers k-NN batches from it.  AUTO builds it where the build-time
+ * estimates say seeding pays but the reference partition's tile balls are too loose, and keeps it when its own estimates
+ * turn the tile bitmaps on (clustered data in d >= 32, e.g. BASELINE config 3); uniform data never pays for it.  The
+ * layout accessors, self-queries and radius queries of a ball handle always use the reference partition. */
+typedef enum pn_partition { PN_PARTITION_AUTO = 0, PN_PARTITION_REFERENCE = 1, PN_PARTITION_TWO_MEANS = 2 } pn_partition;
+
 #define PN_FLAG_HOST_ONLY 1u /* build + flatten on the host only (no device; queries fail with
                                 PN_CUDA).  For builder tests on machines without a GPU. */
 
@@ -88,7 +98,8 @@ typedef struct pn_build_opts {
     uint32_t shard_index;
     uint32_t builder;     /* pn_builder: where the partition is computed */
     uint32_t prune;       /* pn_prune: triangle-inequality pruning in front of the tensor filter */
-    uint32_t reserved[6];
+    uint32_t partition;   /* pn_partition: the partition the tensor path scans */
+    uint32_t reserved[5];
 } pn_build_opts;
 
 typedef struct pn_tree pn_tree; /* opaque: flattened, device-resident tree */
@@ -111,6 +122,8 @@ typedef struct pn_tree_info {
     double est_seed_candidates; /* candidates a query still reranks when it starts from its seed */
     double est_tile_frac;       /* share of tile balls beyond a single query's seed */
     double est_group_tile_frac; /* share of tile balls out of reach of a whole tile of queries */
+    uint32_t tensor_partition;  /* the partition the estimates above describe and k-NN batches scan: 0 reference, 1 two-means */
+    uint32_t reserved0;
 } pn_tree_info;
 
 /* Work counters of the most recent query call. */

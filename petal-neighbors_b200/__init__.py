@@ -26,10 +26,12 @@ import numpy as np
 from . import _ffi
 from . import distance
 from ._ffi import (PN_ALGO_AUTO, PN_ALGO_SIMT, PN_ALGO_TENSOR, PN_BUILDER_AUTO, PN_BUILDER_HOST, PN_BUILDER_DEVICE,
-                   PN_PRUNE_AUTO, PN_PRUNE_ON, PN_PRUNE_OFF)
+                   PN_PRUNE_AUTO, PN_PRUNE_ON, PN_PRUNE_OFF,
+                   PN_PARTITION_AUTO, PN_PARTITION_REFERENCE, PN_PARTITION_TWO_MEANS)
 
 __all__ = ["BallTree", "VantagePointTree", "ArrayError", "EngineError", "distance", "merge_topk_dev",
-           "PN_ALGO_AUTO", "PN_ALGO_SIMT", "PN_ALGO_TENSOR", "PN_BUILDER_AUTO", "PN_BUILDER_HOST", "PN_BUILDER_DEVICE", "PN_PRUNE_AUTO", "PN_PRUNE_ON", "PN_PRUNE_OFF"]
+           "PN_ALGO_AUTO", "PN_ALGO_SIMT", "PN_ALGO_TENSOR", "PN_BUILDER_AUTO", "PN_BUILDER_HOST", "PN_BUILDER_DEVICE", "PN_PRUNE_AUTO", "PN_PRUNE_ON", "PN_PRUNE_OFF",
+           "PN_PARTITION_AUTO", "PN_PARTITION_REFERENCE", "PN_PARTITION_TWO_MEANS"]
 
 
 class ArrayError(Exception):
@@ -79,7 +81,8 @@ class _Tree:
     _kind = "balltree"
 
     def __init__(self, points, metric=None, *, device=-1, bucket_size=0, algo=PN_ALGO_AUTO, host_threads=0,
-                 host_only=False, shard_depth=0, shard_index=0, builder=PN_BUILDER_AUTO, prune=PN_PRUNE_AUTO):
+                 host_only=False, shard_depth=0, shard_index=0, builder=PN_BUILDER_AUTO, prune=PN_PRUNE_AUTO,
+                 partition=PN_PARTITION_AUTO):
         if metric is not None and not isinstance(metric, distance.Euclidean):
             raise TypeError("only distance.Euclidean is offered by the B200 engine (Cosine is not a metric; "
                             "there is no CPU fallback)")
@@ -94,6 +97,7 @@ class _Tree:
         opts.shard_index = shard_index
         opts.builder = builder
         opts.prune = prune
+        opts.partition = partition
         self._h = C.c_void_p()
         self.metric = metric if metric is not None else distance.Euclidean()
         if hasattr(points, "data_ptr") and getattr(points, "is_cuda", False):

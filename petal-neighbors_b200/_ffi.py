@@ -15,6 +15,7 @@ PN_ALGO_AUTO, PN_ALGO_SIMT, PN_ALGO_TENSOR = 0, 1, 2
 PN_FLAG_HOST_ONLY = 1
 PN_BUILDER_AUTO, PN_BUILDER_HOST, PN_BUILDER_DEVICE = 0, 1, 2
 PN_PRUNE_AUTO, PN_PRUNE_ON, PN_PRUNE_OFF = 0, 1, 2
+PN_PARTITION_AUTO, PN_PARTITION_REFERENCE, PN_PARTITION_TWO_MEANS = 0, 1, 2
 
 # every symbol include/petal_b200.h declares
 EXPORTS = [
@@ -49,7 +50,7 @@ class BuildOpts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("bucket_size", C.c_uint32),
                 ("algo", C.c_uint32), ("host_threads", C.c_uint32), ("flags", C.c_uint32),
                 ("shard_depth", C.c_uint32), ("shard_index", C.c_uint32), ("builder", C.c_uint32),
-                ("prune", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+                ("prune", C.c_uint32), ("partition", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
 class TreeInfo(C.Structure):
@@ -59,7 +60,8 @@ class TreeInfo(C.Structure):
                 ("bucket_size_max", C.c_uint32), ("device", C.c_int32), ("algo", C.c_uint32),
                 ("device_bytes", C.c_uint64), ("build_seconds", C.c_double),
                 ("prune_seeded", C.c_uint32), ("prune_tiles", C.c_uint32), ("est_seed_candidates", C.c_double),
-                ("est_tile_frac", C.c_double), ("est_group_tile_frac", C.c_double)]
+                ("est_tile_frac", C.c_double), ("est_group_tile_frac", C.c_double),
+                ("tensor_partition", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -70,7 +72,7 @@ class Counters(C.Structure):
 
 
 def _struct_dict(s):
-    return {f: getattr(s, f) for f, _ in s._fields_ if f != "reserved"}
+    return {f: getattr(s, f) for f, _ in s._fields_ if not f.startswith("reserved")}
 
 
 _lib = None

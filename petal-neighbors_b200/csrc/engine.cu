@@ -142,7 +142,7 @@ struct Engine final : pn_tree {
     int n_sms = 148;
     cudaStream_t stream = nullptr, last_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    DevBuf d_pts, d_ids, d_blo, d_bhi, d_centers, d_radii, d_vpids;
+    DevBuf d_pts, d_ids, d_blo, d_bhi, d_centers, d_radii, d_vpids, d_plane_w, d_plane_t;
     DevBuf w_qraw, w_q, w_home, w_hist, w_cursor, w_order, w_part_d, w_part_i, w_floor_d, w_floor_i,
         w_counters, w_out_i, w_out_d, w_counts, w_offsets, w_hits;
     DevTree<A> dt{};
@@ -163,6 +163,7 @@ struct Engine final : pn_tree {
     bool tensor_ready = false, last_used_tensor = false;
     // pruned tensor scan (tc_prune.cuh): tile balls, the build-time estimate of what pruning can do, per-call workspaces
     DevBuf d_tcen, d_trad, w_qs, w_seed, w_bits, w_tcnt;
+    DevBuf w_bcen, w_brad, w_bmu, w_qth, w_bbits, w_bcnt, w_wslot, w_wlist, w_wbits, w_nwide;   // tile-bitmap pass: query balls, their bitmaps, wide balls
     double prune_frac = 0.0;      // estimated fraction of (query group, tile) pairs that are out of reach
     double seed_candidates = 0.0; // estimated candidates per query that survive a seed threshold
     double tile_frac = 0.0;       // estimated share of tiles beyond a single query's seed
@@ -174,6 +175,14 @@ struct Engine final : pn_tree {
     // exact 1-NN does not depend on the partition; the VP arrays serve the pruned SIMT traversal (PN_ALGO_SIMT), the layout
     // accessors and trees the tensor path does not take (f64, d < 16).
     std::unique_ptr<Engine<A>> aux;
+    // Ball handles (and the ball partition of a VP handle) on CLUSTERED data: the reference's split -- the median of the
+    // widest coordinate -- cuts through clusters, so in d >= 32 most 128-row tiles of the stored order mix fragments of
+    // several clusters and no ball bounds them tightly (BASELINE config 3: 88 % of all (query group, tile) pairs stay).
+    // Such a handle keeps a second ball tree over the same rows, partitioned by the TWO-MEANS rule of gpu_build.cu
+    // (partition_rule 1), and answers its k-NN batches from it: exact results do not depend on the partition, the tile
+    // bitmaps of tc_prune.cuh do.  two_means_partition() decides from the build-time estimates of both partitions.
+    uint32_t partition_rule = 0;  // gb::build_ball_tree rule of THIS engine's arrays
+    static constexpr uint32_t TWO_MEANS_ORDER_LEVELS = 1;
     bool gpu_built = false;  // the tree arrays were produced on the device (gpu_build.cu); host copies are fetched on demand
     uint32_t kp = 0;       // padded K of the augmented operands (multiple of 32)
     float pmax = 0.f;      // max |s (p - center)|
@@ -183,10 +192,11 @@ struct Engine final : pn_tree {
     ~Engine() override {
         if (!host_only) {
             DeviceGuard g(device);
-            for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &w_qraw, &w_q, &w_home,
+            for (DevBuf* b : {&d_pts, &d_ids, &d_blo, &d_bhi, &d_centers, &d_radii, &d_vpids, &d_plane_w, &d_plane_t, &w_qraw, &w_q, &w_home,
                               &w_hist, &w_cursor, &w_order, &w_part_d, &w_part_i, &w_floor_d, &w_floor_i, &w_counters,
                               &w_out_i, &w_out_d, &w_counts, &w_offsets, &w_hits, &d_baug, &d_center, &w_aaug, &w_qmargin, &w_trace, &w_gbound,
-                              &d_tcen, &d_trad, &w_qs, &w_seed, &w_bits, &w_tcnt})
+                              &d_tcen, &d_trad, &w_qs, &w_seed, &w_bits, &w_tcnt,
+                              &w_bcen, &w_brad, &w_bmu, &w_qth, &w_bbits, &w_bcnt, &w_wslot, &w_wlist, &w_wbits, &w_nwide})
                 b->release();
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             for (int i = 0; i < 2; ++i) {
@@ -231,6 +241,10 @@ struct Engine final : pn_tree {
             return o;
         o.pts = e->d_pts.template as<A>(); o.ids = e->d_ids.template as<uint32_t>();
         o.centers = e->d_centers.template as<A>(); o.radii = e->d_radii.template as<A>();
+        if (e->partition_rule == 1 && t.n_internal &&
+            e->d_plane_w.ensure((size_t)t.n_internal * t.dpad * sizeof(A)) == PN_OK && e->d_plane_t.ensure((size_t)t.n_internal * sizeof(A)) == PN_OK) {
+            o.plane_w = e->d_plane_w.template as<A>(); o.plane_t = e->d_plane_t.template as<A>();
+        }
         return o;
     }
     static gb::VpOut<A> alloc_vp_arrays(void* ctx, uint64_t n, const gb::VpShape& shape) {
@@ -272,16 +286,20 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 
-    int build_on_device(const A* raw_dev, size_t n_all, size_t d, size_t stride, uint32_t bucket, uint32_t shard_depth, uint32_t shard_index) {
+    int build_on_device(const A* raw_dev, size_t n_all, size_t d, size_t stride, uint32_t bucket, uint32_t shard_depth, uint32_t shard_index,
+                        uint32_t rule = 0) {
         DeviceGuard g(device);
         if (!g.ok) return fail(PN_CUDA, "no usable CUDA device (there is no CPU fallback)");
         TRY(open_device());
         ft.d = (uint32_t)d; ft.n_total = n_all;
+        partition_rule = rule;
         gb::TreeShape shape;
         uint64_t n = 0;
         std::string err;
+        // two-means partition: the rows of a bucket follow one more level of the split (a bucket is about two tiles of the
+        // tensor path's point image)
         const int rc = gb::build_ball_tree<A>(raw_dev, n_all, (uint32_t)d, stride, bucket, shard_depth, shard_index, shape, &n,
-                                              &Engine::alloc_tree_arrays, this, stream, err);
+                                              &Engine::alloc_tree_arrays, this, stream, err, rule, rule == 1 ? TWO_MEANS_ORDER_LEVELS : 0u);
         if (rc) return fail(rc == (int)cudaErrorMemoryAllocation ? PN_OOM : PN_CUDA, "device tree build: " + err);
         if (n == 0) return fail(PN_EMPTY, "shard holds no points");
         gpu_built = true;
@@ -290,7 +308,7 @@ struct Engine final : pn_tree {
         TRY(d_vpids.ensure(16));
         CU(cudaMemcpy(d_blo.p, ft.bucket_lo.data(), ft.bucket_lo.size() * 4, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d_bhi.p, ft.bucket_hi.data(), ft.bucket_hi.size() * 4, cudaMemcpyHostToDevice));
-        info.device_bytes = d_pts.cap + d_ids.cap + d_blo.cap + d_bhi.cap + d_centers.cap + d_radii.cap + d_vpids.cap;
+        info.device_bytes = d_pts.cap + d_ids.cap + d_blo.cap + d_bhi.cap + d_centers.cap + d_radii.cap + d_vpids.cap + d_plane_w.cap + d_plane_t.cap;
         fill_dev_tree();
         TRY(prepare_tensor());
         return PN_OK;
@@ -326,6 +344,8 @@ struct Engine final : pn_tree {
         dt.n = (uint32_t)ft.n; dt.d = ft.d; dt.dpad = ft.dpad; dt.dv = ft.dpad / VT<A>::N;
         dt.L = ft.L; dt.n_internal = ft.n_internal; dt.n_buckets = ft.n_buckets; dt.n_nodes = ft.n_nodes;
         dt.kind = ft.kind;
+        dt.plane_w = partition_rule == 1 && d_plane_w.p && d_plane_t.p ? d_plane_w.as<A>() : nullptr;
+        dt.plane_t = dt.plane_w ? d_plane_t.as<A>() : nullptr;
         const double u = sizeof(A) == 4 ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
         dt.slack = (A)((2.0 * ft.d + 8.0) * u);
     }
@@ -650,7 +670,12 @@ struct Engine final : pn_tree {
             const float4* qsorted;
             const uint32_t* order = nullptr;
             CU(cudaEventRecord(ev[2], st));   // scan_ms covers the whole scan: sort + seeds, bitmaps, filter, merge
+            // PN_STAGE_TIMING=1 (diagnostic): the stages of this call timed one by one, to stderr
+            static const bool stage_timing = getenv("PN_STAGE_TIMING") != nullptr;
+            cudaEvent_t se[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            if (stage_timing) { for (auto& e : se) CU(cudaEventCreate(&e)); CU(cudaEventRecord(se[0], st)); }
             TRY(sort_and_seed(qraw, nq, stride, k, st, self_query, &qsorted, &order));
+            if (stage_timing) CU(cudaEventRecord(se[1], st));
             TRY(w_aaug.ensure((size_t)nq * kp * 2));
             TRY(w_qmargin.ensure((size_t)nq * 4));
             TRY(w_bits.ensure((size_t)n_qt * words * 4));
@@ -661,11 +686,40 @@ struct Engine final : pn_tree {
             tc::build_aaug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(qsorted), d_center.as<float>(), tscale, nq, ft.d, ft.dpad,
                                                                     kp, pmax, w_aaug.as<__half>(), w_qmargin.as<float>());
             CU(cudaGetLastError());
-            tc::tile_bitmap_kernel<<<n_qt, 256, (size_t)(QT / 32) * dt.dv * 16, st>>>(
-                qsorted, w_seed.as<float>(), nq, QT, d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
-                w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>(), w_counters.as<unsigned long long>() + 3);
-            CU(cudaGetLastError());
+            {
+                // tile bitmaps (tc_prune.cuh): balls of 32 sorted queries against the tile balls, wide balls refined query by query
+                const uint32_t n_sub = QT / 32, n_warps = n_qt * n_sub, n_balls = 2 * n_warps, wide_cap = std::max<uint32_t>(1u, n_warps / 4);
+                const size_t smem = (size_t)32 * dt.dv * 16;
+                TRY(w_bcen.ensure((size_t)n_balls * ft.dpad * 4)); TRY(w_brad.ensure((size_t)n_balls * 4)); TRY(w_bmu.ensure((size_t)n_balls * 4));
+                TRY(w_qth.ensure((size_t)n_warps * 32 * 4)); TRY(w_bbits.ensure((size_t)n_balls * words * 4)); TRY(w_bcnt.ensure((size_t)n_balls * 4));
+                TRY(w_wslot.ensure((size_t)n_warps * 4)); TRY(w_wlist.ensure((size_t)wide_cap * 4)); TRY(w_wbits.ensure((size_t)wide_cap * words * 4));
+                TRY(w_nwide.ensure(4));
+                if (smem > 48u * 1024u) {
+                    CU(cudaFuncSetAttribute(tc::ball_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    CU(cudaFuncSetAttribute(tc::ball_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                }
+                CU(cudaMemsetAsync(w_nwide.p, 0, 4, st));
+                tc::warp_balls_kernel<<<(n_warps + 7) / 8, 256, 0, st>>>(qsorted, w_seed.as<float>(), nq, n_warps, dt.dv, w_bcen.as<float4>(), w_brad.as<float>(),
+                                                                         w_bmu.as<float>(), w_qth.as<float>());
+                CU(cudaGetLastError());
+                tc::ball_tile_kernel<false><<<(n_balls + 31) / 32, 256, smem, st>>>(w_bcen.as<float4>(), w_brad.as<float>(), w_bmu.as<float>(), n_balls, nullptr, nullptr, 0u,
+                                                                                   d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
+                                                                                   w_bbits.as<uint32_t>(), w_bcnt.as<uint32_t>());
+                CU(cudaGetLastError());
+                tc::wide_select_kernel<<<(n_qt + 127) / 128, 128, 0, st>>>(w_bcnt.as<uint32_t>(), w_bmu.as<float>(), n_qt, n_sub, wide_cap, w_wslot.as<uint32_t>(),
+                                                                          w_wlist.as<uint32_t>(), w_nwide.as<uint32_t>());
+                CU(cudaGetLastError());
+                tc::ball_tile_kernel<true><<<wide_cap, 256, smem, st>>>(qsorted, nullptr, w_qth.as<float>(), nq, w_wlist.as<uint32_t>(), w_nwide.as<uint32_t>(), wide_cap,
+                                                                       d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
+                                                                       w_wbits.as<uint32_t>(), nullptr);
+                CU(cudaGetLastError());
+                tc::group_bits_kernel<<<n_qt, 256, 0, st>>>(w_bbits.as<uint32_t>(), w_wbits.as<uint32_t>(), w_wslot.as<uint32_t>(), nq, QT, n_sub, words,
+                                                            w_bits.as<uint32_t>(), w_tcnt.as<uint32_t>(), w_counters.as<unsigned long long>() + 3);
+                CU(cudaGetLastError());
+                counters.kernel_launches += 4;
+            }
             counters.kernel_launches += 2;
+            if (stage_timing) CU(cudaEventRecord(se[2], st));
             alignas(64) CUtensorMap map_a;
             TRY(make_map(&map_a, w_aaug.p, nq, tc::BM));
             tc::FilterArgs fa{};
@@ -680,10 +734,20 @@ struct Engine final : pn_tree {
             fa.row0 = 0; fa.nq = nq; fa.g_bound = nullptr;
             fa.tile_bits = w_bits.as<uint32_t>(); fa.tile_cnt = w_tcnt.as<uint32_t>(); fa.tile_words = words; fa.seed_t2 = w_seed.as<float>();
             TRY(k1 ? launch_filter_k<1>(map_a, fa, st) : launch_filter_k<16>(map_a, fa, st));
+            if (stage_timing) CU(cudaEventRecord(se[3], st));
             // results of sorted slot i belong to query order[i] (self query: to the original row of stored point i)
             CU(merge_lists<A, uint32_t>(st, w_part_d.as<A>(), w_part_i.as<uint32_t>(), 1, nq, k, idx_out, dist_out, kstride,
                                                                             0, nullptr, nullptr, self_query ? d_ids.as<uint32_t>() : order));
             CU(cudaGetLastError());
+            if (stage_timing) {
+                CU(cudaEventRecord(se[4], st));
+                CU(cudaEventSynchronize(se[4]));
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < 4; ++i) (void)cudaEventElapsedTime(&t[i], se[i], se[i + 1]);
+                fprintf(stderr, "[pn stage timing] pruned scan, %u queries, k %u: sort + seeds %.2f ms | operands + tile bitmaps %.2f ms | filter %.2f ms | merge %.2f ms\n",
+                        nq, k, t[0], t[1], t[2], t[3]);
+                for (auto& e : se) cudaEventDestroy(e);
+            }
             counters.kernel_launches += 2;
             counters.filter_pairs += (uint64_t)ft.n * nq;  // replaced by the device-side count of scanned pairs in fetch_counters
             CU(cudaEventRecord(ev[3], st));
@@ -918,6 +982,32 @@ struct Engine final : pn_tree {
         return PN_OK;
     }
 
+    // A second ball tree over this engine's stored rows, split by the two-means rule, when that pays (see `aux`):
+    // AUTO tries it where seeding already pays and the tile balls of the reference partition leave a single query more than
+    // a tenth of the tiles, and keeps it when its own estimates turn the bitmaps on and a single query can skip at least a
+    // tenth of all tiles more; PN_PARTITION_TWO_MEANS keeps it regardless.  Returns the new
+    // engine in `out` (null: stay with this partition); a failure on the way only loses the speed-up.
+    int two_means_partition(uint32_t partition_opt, uint32_t bucket, std::unique_ptr<Engine<A>>& out) {
+        out.reset();
+        if constexpr (sizeof(A) == 4) {
+            if (partition_opt == PN_PARTITION_REFERENCE || host_only || ft.kind != 0 || !tensor_ready || ft.n != ft.n_total) return PN_OK;
+            const bool forced = partition_opt == PN_PARTITION_TWO_MEANS;
+            // AUTO: seeding pays (clustered data), a single query could skip some tiles but not nearly all of them
+            if (forced ? ft.n < 1024 : !(ft.n >= 32768 && prune_opt == PN_PRUNE_AUTO && prune_on && tile_frac >= 0.1 && tile_frac < 0.9)) return PN_OK;
+            DeviceGuard g(device);
+            if (!g.ok) return PN_OK;
+            std::unique_ptr<Engine<A>> ax(new Engine<A>());
+            ax->device = device; ax->algo = algo; ax->prune_opt = prune_opt;
+            if (cudaStreamSynchronize(stream) != cudaSuccess) { (void)cudaGetLastError(); return PN_OK; }
+            if (ax->build_on_device(d_pts.as<A>(), ft.n, ft.d, ft.dpad, bucket, 0, 0, 1) != PN_OK || !ax->tensor_ready) { (void)cudaGetLastError(); return PN_OK; }
+            translate_ids_kernel<<<(unsigned)((ft.n + 255) / 256), 256, 0, ax->stream>>>(ax->d_ids.template as<uint32_t>(), d_ids.as<uint32_t>(), (uint32_t)ft.n);
+            if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ax->stream) != cudaSuccess) { (void)cudaGetLastError(); return PN_OK; }
+            ax->ft.n_total = ft.n_total;
+            if (forced || (ax->tiles_on && ax->tile_frac >= tile_frac + 0.1)) out = std::move(ax);
+        }
+        return PN_OK;
+    }
+
     // A vantage-point handle's ball partition of the same points (Engine::aux).  Tensor-eligible trees get it when they are
     // created; the others on the first query the VP arrays do not serve (radius search): built on the device from the
     // stored rows, then its ids (positions in this tree's stored order) are translated to the original point indices.
@@ -946,6 +1036,7 @@ struct Engine final : pn_tree {
             TRY(aux->w_counters.ensure(256));
             CU(cudaMemsetAsync(aux->w_counters.p, 0, 256, st));
             aux->counters = pn_counters{};
+            aux->aux_used = false;
         }
         aux_used = false;
         return PN_OK;
@@ -1666,6 +1757,10 @@ struct Engine final : pn_tree {
             {&d_pts, (size_t)ft.n * ft.dpad * sizeof(A)}, {&d_ids, (size_t)ft.n * 4}, {&d_blo, (size_t)ft.n_buckets * 4}, {&d_bhi, (size_t)ft.n_buckets * 4},
             {&d_centers, (size_t)std::max<uint32_t>(ft.n_nodes, 1) * ft.dpad * sizeof(A)}, {&d_radii, (size_t)std::max<uint32_t>(ft.n_nodes, 1) * sizeof(A)},
             {&d_vpids, ft.kind == 1 ? (size_t)std::max<uint32_t>(ft.n_nodes, 1) * 4 : 16}};
+        if (partition_rule == 1 && ft.n_internal) {   // (never replicated: a handle's second partition stays on its device; sessions alias it)
+            v.push_back({&d_plane_w, (size_t)ft.n_internal * ft.dpad * sizeof(A)});
+            v.push_back({&d_plane_t, (size_t)ft.n_internal * sizeof(A)});
+        }
         if (tensor_ready) {
             v.push_back({&d_center, (size_t)ft.dpad * 4});
             v.push_back({&d_baug, (ft.n + tc::BN - 1) / tc::BN * tc::BN * (size_t)kp * 2});
@@ -1741,7 +1836,7 @@ struct Engine final : pn_tree {
         ft.bucket_max = src.ft.bucket_max; ft.kind = src.ft.kind;
         ft.bucket_lo = src.ft.bucket_lo; ft.bucket_hi = src.ft.bucket_hi; ft.vp_ids = src.ft.vp_ids;
         kp = src.kp; algo = src.algo; tensor_ready = src.tensor_ready; pmax = src.pmax; tscale = src.tscale;
-        prune_on = src.prune_on; tiles_on = src.tiles_on; prune_opt = src.prune_opt;
+        prune_on = src.prune_on; tiles_on = src.tiles_on; prune_opt = src.prune_opt; partition_rule = src.partition_rule;
         prune_frac = src.prune_frac; seed_candidates = src.seed_candidates; tile_frac = src.tile_frac;
         gpu_built = true;   // no host copies: layout() reads the device arrays
         auto mine = replica_arrays();
@@ -1801,6 +1896,19 @@ struct Engine final : pn_tree {
 template <typename A>
 static int finish_create(int kind, std::unique_ptr<Engine<A>>& e, const pn_build_opts& o, std::chrono::steady_clock::time_point t0, pn_tree** out);
 
+// a ball handle's two-means partition of the same rows (Engine::aux), when Engine::two_means_partition keeps one
+template <typename A>
+static int attach_two_means(Engine<A>& e, const pn_build_opts& o, uint32_t bucket) {
+    if (e.host_only || o.shard_depth) return PN_OK;
+    std::unique_ptr<Engine<A>> tm;
+    TRY(e.two_means_partition(o.partition, bucket, tm));
+    if (tm) {
+        e.info.device_bytes += tm->info.device_bytes;
+        e.aux = std::move(tm);
+    }
+    return PN_OK;
+}
+
 template <typename A>
 static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row_stride, size_t col_stride,
                        const pn_build_opts* opts_in, pn_tree** out) {
@@ -1825,6 +1933,7 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
     const bool host_only = (o.flags & PN_FLAG_HOST_ONLY) != 0;
     if (o.builder > PN_BUILDER_DEVICE) return fail(PN_BAD_ARG, "bad builder");
     if (o.prune > PN_PRUNE_OFF) return fail(PN_BAD_ARG, "bad prune option");
+    if (o.partition > PN_PARTITION_TWO_MEANS) return fail(PN_BAD_ARG, "bad partition option");
     if (o.shard_depth && (kind != PN_KIND_BALL || o.shard_depth > 16 || o.shard_index >= (1u << o.shard_depth)))
         return fail(PN_BAD_ARG, kind != PN_KIND_BALL ? "subtree sharding is a ball-tree option" : "bad shard_depth / shard_index");
     // ball trees with a device are built there from 32768 points up (bit-identical layout, tests/test_gpu_build.py)
@@ -1882,12 +1991,18 @@ static int create_tree(int kind, const A* points, size_t n, size_t d, size_t row
         if (g.ok && raw.ensure(n * d * sizeof(A)) == PN_OK &&
             cudaMemcpy2D(raw.p, d * sizeof(A), points, std::max(row_stride, d) * sizeof(A), d * sizeof(A), n, cudaMemcpyHostToDevice) == cudaSuccess &&
             ax->build_on_device(raw.as<A>(), n, d, d, bucket, 0, 0) == PN_OK && ax->tensor_ready) {
+            raw.release();
+            // clustered points: the two-means partition of the same rows instead, when its tile bounds are the tighter ones
+            std::unique_ptr<Engine<A>> tm;
+            ax->two_means_partition(o.partition, bucket, tm);
+            if (tm) ax = std::move(tm);
             e->info.device_bytes += ax->info.device_bytes;
             e->aux = std::move(ax);
         }
         (void)cudaGetLastError();
         raw.release();
     }
+    if (kind == PN_KIND_BALL) TRY(attach_two_means(*e, o, bucket));
     return finish_create(kind, e, o, t0, out);
 }
 
@@ -1906,6 +2021,7 @@ static int finish_create(int kind, std::unique_ptr<Engine<A>>& e, const pn_build
         const Engine<A>* pe = e->aux ? e->aux.get() : e.get();   // a VP handle reports the ball partition its tensor path uses
         inf.prune_seeded = pe->prune_on ? 1u : 0u; inf.prune_tiles = pe->tiles_on ? 1u : 0u;
         inf.est_seed_candidates = pe->seed_candidates; inf.est_tile_frac = pe->tile_frac; inf.est_group_tile_frac = pe->prune_frac;
+        inf.tensor_partition = pe->partition_rule;
     }
     inf.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     *out = e.release();
@@ -1927,6 +2043,8 @@ static int create_tree_dev(const A* points_dev, size_t n, size_t d, size_t row_s
     else o.device = -1;
     if (o.flags & PN_FLAG_HOST_ONLY) return fail(PN_BAD_ARG, "device-resident points cannot build a host-only tree");
     if (o.builder == PN_BUILDER_HOST) return fail(PN_BAD_ARG, "device-resident points are built on the device");
+    if (o.prune > PN_PRUNE_OFF) return fail(PN_BAD_ARG, "bad prune option");
+    if (o.partition > PN_PARTITION_TWO_MEANS) return fail(PN_BAD_ARG, "bad partition option");
     if (o.shard_depth && (o.shard_depth > 16 || o.shard_index >= (1u << o.shard_depth))) return fail(PN_BAD_ARG, "bad shard_depth / shard_index");
     uint32_t bucket = o.bucket_size ? o.bucket_size : 256;
     if (bucket < 8) bucket = 8;
@@ -1943,6 +2061,7 @@ static int create_tree_dev(const A* points_dev, size_t n, size_t d, size_t row_s
     } catch (const std::bad_alloc&) {
         return fail(PN_OOM, "host allocation failed while building the tree");
     }
+    TRY(attach_two_means(*e, o, bucket));
     return finish_create(PN_KIND_BALL, e, o, t0, out);
 }
 

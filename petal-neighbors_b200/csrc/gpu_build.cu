@@ -21,6 +21,7 @@ namespace gb {
     } while (0)
 
 constexpr int BT = 256;     // threads per block of every builder kernel
+constexpr uint32_t TILE_ROWS = 128;  // rows per tile of the tensor path's point image (tc::BN)
 constexpr int ROWS = 1024;  // consecutive positions of ONE segment handled by a block (blocks never straddle segments)
 
 template <typename A> struct KeyT;
@@ -107,6 +108,119 @@ __global__ void choose_kernel(const typename KeyT<A>::U* __restrict__ mn, const 
     col[s] = best_c;
 }
 
+// ---- 1b. the TWO-MEANS split rule (rule 1; not the reference's): the split direction of a segment is the line through
+// the two centroids of a 2-means clustering of a sample of its points, the key of a point its projection on that line.
+// The median cut, the stable partition and everything after stay as they are, so the result is a ball tree of the same
+// shape with correct centroids and radii -- every query path is exact on it -- whose buckets follow clusters instead of
+// cutting through them along coordinate axes (what the tile bounds of the pruned tensor scan need, tc_prune.cuh).
+// One block per segment: up to `m_max` evenly spaced points of the segment in shared memory, two far-apart seeds (the
+// point farthest from the first sample, then the point farthest from that one), four Lloyd iterations, all reductions in
+// a fixed order (the layout is reproducible run to run).
+template <typename A>
+__global__ void __launch_bounds__(BT) two_means_dir_kernel(const A* __restrict__ raw, uint64_t stride, uint32_t d, const uint32_t* __restrict__ idx,
+                                                           const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t m_max,
+                                                           A* __restrict__ wdir) {
+    extern __shared__ __align__(16) unsigned char dir_smem[];
+    const uint32_t ds = d | 1u;                                // odd row stride: lane i reads row i without bank conflicts
+    float* S = reinterpret_cast<float*>(dir_smem);             // [m_max][ds]
+    float* c1 = S + (size_t)m_max * ds;                        // [d]
+    float* c2 = c1 + d;                                        // [d]
+    __shared__ float s_val[BT];
+    __shared__ uint32_t s_idx[BT];
+    __shared__ uint32_t s_grp[BT];
+    __shared__ uint32_t s_n1;
+    const uint32_t seg = blockIdx.x;
+    const uint32_t lo = seg_l[seg], len = seg_h[seg] - lo;
+    A* w = wdir + (uint64_t)seg * d;
+    if (len < 2) {   // nothing to split
+        for (uint32_t j = threadIdx.x; j < d; j += BT) w[j] = A(0);
+        return;
+    }
+    const uint32_t m = min(len, m_max);
+    for (uint32_t e = threadIdx.x; e < m * d; e += BT) {
+        const uint32_t i = e / d, j = e % d;
+        const uint32_t pos = (uint32_t)(((uint64_t)i * len) / m);
+        S[(size_t)i * ds + j] = (float)raw[(uint64_t)idx[lo + pos] * stride + j];
+    }
+    __syncthreads();
+    // sample farthest from row `from` (ties: the lower sample), by a fixed-order tree reduction
+    auto farthest = [&](const float* from) -> uint32_t {
+        float v = -1.f;
+        if (threadIdx.x < m) {
+            v = 0.f;
+            const float* r = S + (size_t)threadIdx.x * ds;
+            for (uint32_t j = 0; j < d; ++j) { const float t = r[j] - from[j]; v += t * t; }
+        }
+        s_val[threadIdx.x] = v; s_idx[threadIdx.x] = threadIdx.x;
+        __syncthreads();
+        for (uint32_t o = BT / 2; o; o >>= 1) {
+            if (threadIdx.x < o) {
+                const float a = s_val[threadIdx.x], b = s_val[threadIdx.x + o];
+                if (b > a) { s_val[threadIdx.x] = b; s_idx[threadIdx.x] = s_idx[threadIdx.x + o]; }
+            }
+            __syncthreads();
+        }
+        const uint32_t best = s_idx[0];
+        __syncthreads();
+        return best;
+    };
+    const uint32_t ib = farthest(S);
+    for (uint32_t j = threadIdx.x; j < d; j += BT) c1[j] = S[(size_t)ib * ds + j];
+    __syncthreads();
+    const uint32_t ic = farthest(c1);
+    for (uint32_t j = threadIdx.x; j < d; j += BT) c2[j] = S[(size_t)ic * ds + j];
+    __syncthreads();
+    for (int it = 0; it < 4; ++it) {
+        if (threadIdx.x == 0) s_n1 = 0;
+        __syncthreads();
+        uint32_t g = 2;   // 0: nearer c1, 1: nearer c2, 2: no such sample
+        if (threadIdx.x < m) {
+            const float* r = S + (size_t)threadIdx.x * ds;
+            float d1 = 0.f, d2 = 0.f;
+            for (uint32_t j = 0; j < d; ++j) {
+                const float t1 = r[j] - c1[j], t2 = r[j] - c2[j];
+                d1 += t1 * t1; d2 += t2 * t2;
+            }
+            g = d1 <= d2 ? 0u : 1u;
+            if (g == 0) atomicAdd(&s_n1, 1u);   // an integer count: order-independent
+        }
+        s_grp[threadIdx.x] = g;
+        __syncthreads();
+        const uint32_t n1 = s_n1, n2 = m - n1;
+        if (n1 == 0 || n2 == 0) break;          // block-uniform: one side is empty (identical samples), keep the centroids
+        for (uint32_t j = threadIdx.x; j < d; j += BT) {
+            float a1 = 0.f, a2 = 0.f;
+            for (uint32_t i = 0; i < m; ++i) {
+                const float v = S[(size_t)i * ds + j];
+                if (s_grp[i] == 0) a1 += v; else a2 += v;
+            }
+            c1[j] = a1 / (float)n1; c2[j] = a2 / (float)n2;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < d; j += BT) w[j] = (A)(c2[j] - c1[j]);
+}
+
+// key of a point = its projection on the direction of its segment: a warp per row, the lanes over the columns, partial
+// sums combined in a fixed butterfly order
+template <typename A>
+__global__ void __launch_bounds__(BT) proj_keys_kernel(const A* __restrict__ raw, uint64_t stride, uint32_t d, const uint32_t* __restrict__ idx,
+                                                       const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t cps,
+                                                       const A* __restrict__ wdir, typename KeyT<A>::U* __restrict__ kv) {
+    const Span sp = block_span(seg_l, seg_h, cps);
+    if (sp.cnt == 0) return;
+    const A* w = wdir + (uint64_t)sp.seg * d;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t r = warp; r < sp.cnt; r += BT / 32) {
+        const A* row = raw + (uint64_t)idx[sp.lo + r] * stride;
+        A acc = A(0);
+        for (uint32_t j = lane; j < d; j += 32) acc += row[j] * w[j];
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) kv[sp.lo + r] = ord_key(acc);
+    }
+}
+
 // ---- 2. median of each segment on the (value of the split column, original index) key: MSB-first radix select -------
 template <typename A>
 __global__ void __launch_bounds__(BT) keys_kernel(const A* __restrict__ raw, uint64_t stride, const uint32_t* __restrict__ idx,
@@ -127,11 +241,12 @@ __device__ __forceinline__ uint32_t select_rank(uint32_t len, int mode) {
 }
 template <typename U>
 __global__ void init_state_kernel(const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, uint32_t n_seg, int mode,
-                                  SelState<U>* __restrict__ st) {
+                                  SelState<U>* __restrict__ st, const uint32_t* __restrict__ seg_next = nullptr) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const uint32_t len = seg_h[s] - seg_l[s];
-    st[s].pv = 0; st[s].pi = 0; st[s].m = len ? select_rank(len, mode) : 0;
+    // seg_next: the split position is whatever the shape says (tile-aligned shapes), boundary 2s+1 of the next level
+    st[s].pv = 0; st[s].pi = 0; st[s].m = len ? (seg_next ? seg_next[2 * s + 1] - seg_l[s] : select_rank(len, mode)) : 0;
 }
 
 template <typename U, int VB>
@@ -195,14 +310,14 @@ constexpr uint32_t SMALL_MAX = 4096;
 template <typename A>
 __global__ void __launch_bounds__(BT) select_small_kernel(const typename KeyT<A>::U* __restrict__ kv, const uint32_t* __restrict__ idx,
                                                           const uint32_t* __restrict__ seg_l, const uint32_t* __restrict__ seg_h, int mode,
-                                                          SelState<typename KeyT<A>::U>* __restrict__ st) {
+                                                          SelState<typename KeyT<A>::U>* __restrict__ st, const uint32_t* __restrict__ seg_next = nullptr) {
     using U = typename KeyT<A>::U;
     constexpr int VB = KeyT<A>::VB;
     __shared__ uint32_t sh[256];
     __shared__ SelState<U> s;
     const uint32_t seg = blockIdx.x, lo = seg_l[seg], cnt = seg_h[seg] - lo;
     if (cnt == 0) return;
-    if (threadIdx.x == 0) { s.pv = 0; s.pi = 0; s.m = select_rank(cnt, mode); }
+    if (threadIdx.x == 0) { s.pv = 0; s.pi = 0; s.m = seg_next ? seg_next[2 * seg + 1] - lo : select_rank(cnt, mode); }
     for (int pass = 0; pass < VB + 4; ++pass) {
         sh[threadIdx.x] = 0;
         __syncthreads();
@@ -231,6 +346,20 @@ __global__ void __launch_bounds__(BT) select_small_kernel(const typename KeyT<A>
         __syncthreads();
     }
     if (threadIdx.x == 0) st[seg] = s;
+}
+
+// the cut of every node of a level, for routing queries the way the points were split (home_bucket_planes_kernel):
+// direction (zero padded to dpad) and the key of the pivot -- keys below it went to the left child
+template <typename A>
+__global__ void save_planes_kernel(const A* __restrict__ wdir, const SelState<typename KeyT<A>::U>* __restrict__ st, const uint32_t* __restrict__ seg_l,
+                                   const uint32_t* __restrict__ seg_h, uint32_t n_seg, uint32_t first, uint32_t d, uint32_t dpad,
+                                   A* __restrict__ plane_w, A* __restrict__ plane_t) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_seg * dpad) return;
+    const uint32_t s = e / dpad, j = e % dpad;
+    const bool live = seg_h[s] - seg_l[s] >= 2;   // shorter segments were not split: everything "goes right" of -inf, harmlessly
+    plane_w[(uint64_t)(first + s) * dpad + j] = live && j < d ? wdir[(uint64_t)s * d + j] : A(0);
+    if (j == 0) plane_t[first + s] = live ? ord_val(st[s].pv) : A(0);
 }
 
 // ---- 3. stable partition around the pivot: keys below it go to the left child, order (ascending original index) kept --
@@ -417,28 +546,41 @@ static uint32_t choose_levels(uint64_t n, uint32_t bucket_size) {
 // the level-by-level partition of idx[0, n) (ascending on entry) for levels [0, levels) of `shape`; idx ends in idx_a
 template <typename A>
 static int partition_levels(const A* raw, uint64_t stride, uint32_t d, const TreeShape& shape, uint32_t levels, uint32_t* idx_a, uint32_t* idx_b,
-                            const uint32_t* const* seg_dev, Scratch& sc, cudaStream_t st, std::string& err, uint32_t** idx_final) {
+                            const uint32_t* const* seg_dev, Scratch& sc, cudaStream_t st, std::string& err, uint32_t** idx_final,
+                            uint32_t rule = 0, A* plane_w = nullptr, A* plane_t = nullptr, uint32_t plane_levels = 0, uint32_t dpad = 0) {
     using U = typename KeyT<A>::U;
     constexpr int VB = KeyT<A>::VB;
     const uint64_t n = shape.n;
     if (levels == 0) { *idx_final = idx_a; return 0; }
     const uint32_t max_seg = 1u << (levels - 1);
-    auto blocks_per_seg = [&](uint32_t l) {
-        const uint64_t maxlen = (n + ((uint64_t(1) << l) - 1)) >> l;  // ceil(n / 2^l) bounds every level-l segment
-        return (uint32_t)std::max<uint64_t>(1, (maxlen + ROWS - 1) / ROWS);
-    };
+    // the longest segment of every level (the plain shape: ceil(n / 2^l); tile-aligned shapes split less evenly)
+    std::vector<uint64_t> longest(levels, 0);
+    for (uint32_t l = 0; l < levels; ++l)
+        for (size_t s2 = 0; s2 + 1 < shape.seg[l].size(); ++s2) longest[l] = std::max<uint64_t>(longest[l], shape.seg[l][s2 + 1] - shape.seg[l][s2]);
+    auto blocks_per_seg = [&](uint32_t l) { return (uint32_t)std::max<uint64_t>(1, (longest[l] + ROWS - 1) / ROWS); };
     size_t max_blocks = 0, max_big_seg = 0;
     for (uint32_t l = 0; l < levels; ++l) {
         max_blocks = std::max<size_t>(max_blocks, (size_t)blocks_per_seg(l) << l);
-        if (((n + ((uint64_t(1) << l) - 1)) >> l) > SMALL_MAX) max_big_seg = size_t(1) << l;
+        if (longest[l] > SMALL_MAX) max_big_seg = size_t(1) << l;
     }
     U *kv = nullptr, *mn = nullptr, *mx = nullptr;
     uint32_t *col = nullptr, *hist = nullptr, *csum = nullptr, *cex = nullptr;
     SelState<U>* state = nullptr;
     GB_CU(sc.get(&kv, n));
-    GB_CU(sc.get(&mn, (size_t)max_seg * d));
-    GB_CU(sc.get(&mx, (size_t)max_seg * d));
-    GB_CU(sc.get(&col, max_seg));
+    A* wdir = nullptr;
+    // two-means rule: samples per segment bounded by 160 KB of shared memory
+    const uint32_t ds = d | 1u;
+    const uint32_t m_max = (uint32_t)std::min<uint64_t>(BT, std::max<uint64_t>(8, (160u * 1024u / 4u - 2u * d) / ds));
+    const size_t dir_smem = ((size_t)m_max * ds + 2u * d) * sizeof(float);
+    if (rule == 1) {
+        GB_CU(sc.get(&wdir, (size_t)max_seg * d));
+        if (dir_smem > 200u * 1024u) { err = "rows too wide for the two-means split rule"; return (int)cudaErrorInvalidValue; }
+        GB_CU(cudaFuncSetAttribute(two_means_dir_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dir_smem));
+    } else {
+        GB_CU(sc.get(&mn, (size_t)max_seg * d));
+        GB_CU(sc.get(&mx, (size_t)max_seg * d));
+        GB_CU(sc.get(&col, max_seg));
+    }
     GB_CU(sc.get(&state, max_seg));
     GB_CU(sc.get(&hist, std::max<size_t>(1, max_big_seg) * 256));
     GB_CU(sc.get(&csum, max_blocks));
@@ -450,20 +592,27 @@ static int partition_levels(const A* raw, uint64_t stride, uint32_t d, const Tre
         const uint32_t* seg_l = seg_dev[l];
         const uint32_t* seg_h = seg_dev[l] + 1;   // contiguous boundaries: the end of segment s is the start of s + 1
         const uint32_t* seg_n = seg_dev[l + 1];
-        GB_CU(cudaMemsetAsync(mn, 0xff, (size_t)n_seg * d * sizeof(U), st));
-        GB_CU(cudaMemsetAsync(mx, 0x00, (size_t)n_seg * d * sizeof(U), st));
-        minmax_kernel<A><<<nb, BT, 0, st>>>(raw, stride, d, cur, seg_l, seg_h, cps, mn, mx);
-        choose_kernel<A><<<(n_seg + 127) / 128, 128, 0, st>>>(mn, mx, d, n_seg, seg_l, seg_h, col);
-        keys_kernel<A><<<nb, BT, 0, st>>>(raw, stride, cur, seg_l, seg_h, cps, col, kv);
-        if (((n + ((uint64_t(1) << l) - 1)) >> l) > SMALL_MAX) {
-            init_state_kernel<U><<<(n_seg + 127) / 128, 128, 0, st>>>(seg_l, seg_h, n_seg, 0, state);
+        if (rule == 1) {
+            two_means_dir_kernel<A><<<n_seg, BT, dir_smem, st>>>(raw, stride, d, cur, seg_l, seg_h, m_max, wdir);
+            proj_keys_kernel<A><<<nb, BT, 0, st>>>(raw, stride, d, cur, seg_l, seg_h, cps, wdir, kv);
+        } else {
+            GB_CU(cudaMemsetAsync(mn, 0xff, (size_t)n_seg * d * sizeof(U), st));
+            GB_CU(cudaMemsetAsync(mx, 0x00, (size_t)n_seg * d * sizeof(U), st));
+            minmax_kernel<A><<<nb, BT, 0, st>>>(raw, stride, d, cur, seg_l, seg_h, cps, mn, mx);
+            choose_kernel<A><<<(n_seg + 127) / 128, 128, 0, st>>>(mn, mx, d, n_seg, seg_l, seg_h, col);
+            keys_kernel<A><<<nb, BT, 0, st>>>(raw, stride, cur, seg_l, seg_h, cps, col, kv);
+        }
+        if (longest[l] > SMALL_MAX) {
+            init_state_kernel<U><<<(n_seg + 127) / 128, 128, 0, st>>>(seg_l, seg_h, n_seg, 0, state, rule == 1 ? seg_n : nullptr);
             for (int pass = 0; pass < VB + 4; ++pass) {
                 hist_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, seg_h, cps, state, pass, hist);
                 pick_kernel<U, VB><<<(n_seg + 127) / 128, 128, 0, st>>>(hist, state, seg_l, seg_h, n_seg, pass);
             }
         } else {
-            select_small_kernel<A><<<n_seg, BT, 0, st>>>(kv, cur, seg_l, seg_h, 0, state);
+            select_small_kernel<A><<<n_seg, BT, 0, st>>>(kv, cur, seg_l, seg_h, 0, state, rule == 1 ? seg_n : nullptr);
         }
+        if (rule == 1 && plane_w && l < plane_levels)
+            save_planes_kernel<A><<<(n_seg * dpad + 255) / 256, 256, 0, st>>>(wdir, state, seg_l, seg_h, n_seg, n_seg - 1, d, dpad, plane_w, plane_t);
         count_left_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, seg_h, cps, state, csum);
         scan_blocks_kernel<<<1, 1024, 0, st>>>(csum, cex, nb);
         scatter_kernel<A><<<nb, BT, 0, st>>>(kv, cur, seg_l, seg_h, seg_n, cps, state, cex, nxt);
@@ -486,7 +635,7 @@ static int upload_shape(const TreeShape& shape, Scratch& sc, std::vector<uint32_
 template <typename A>
 int build_ball_tree(const A* raw, uint64_t n_all, uint32_t d, uint64_t stride, uint32_t bucket_size, uint32_t shard_depth, uint32_t shard_index,
                     TreeShape& shape, uint64_t* n_out, BallOut<A> (*alloc_out)(void* ctx, uint64_t n, const TreeShape& shape), void* ctx,
-                    cudaStream_t st, std::string& err) {
+                    cudaStream_t st, std::string& err, uint32_t rule, uint32_t order_levels) {
     Scratch sc;
     uint32_t *idx_a = nullptr, *idx_b = nullptr;
     GB_CU(sc.get(&idx_a, n_all));
@@ -515,18 +664,45 @@ int build_ball_tree(const A* raw, uint64_t n_all, uint32_t d, uint64_t stride, u
     if (lo) GB_CU(cudaMemcpyAsync(other, idx + lo, n * 4, cudaMemcpyDeviceToDevice, st));
     uint32_t* work_a = lo ? other : idx;
     uint32_t* work_b = lo ? idx : other;  // stream order: the copy above has read idx before the partition overwrites it
+    if (rule == 1 && bucket_size >= TILE_ROWS && n >= 4 * TILE_ROWS) {
+        // tile-aligned shape: every node of the tree starts on a multiple of 128 rows, so that a 128-row tile of the tensor
+        // path's point image never straddles two buckets (a straddling tile mixes two clusters and no ball bounds it)
+        uint32_t L = 0;
+        for (;; ++L) {
+            shape.init(n, L, TILE_ROWS);
+            uint32_t longest = 0;
+            for (size_t s2 = 0; s2 + 1 < shape.seg[L].size(); ++s2) longest = std::max(longest, shape.seg[L][s2 + 1] - shape.seg[L][s2]);
+            if (longest <= std::max(bucket_size, 2 * TILE_ROWS) / TILE_ROWS * TILE_ROWS) break;
+        }
+    } else
     shape.init(n, choose_levels(n, bucket_size));
+    // two-means rule: the stored order may follow `order_levels` more levels of the split than the tree has nodes for
+    // (rows of a bucket grouped by the sub-clusters the next cuts would separate); the boundaries of the levels the tree
+    // does have are the same in both shapes
+    TreeShape order_shape;
+    const bool deeper = rule == 1 && order_levels > 0 && n >= 1024;
+    if (deeper) order_shape.init(n, shape.L + order_levels, shape.align);
+    const TreeShape& pshape = deeper ? order_shape : shape;
     std::vector<uint32_t*> seg_dev;
-    int rc = upload_shape(shape, sc, seg_dev, st, err);
+    int rc = upload_shape(pshape, sc, seg_dev, st, err);
     if (rc) return rc;
-    uint32_t* fin = nullptr;
-    rc = partition_levels<A>(raw, stride, d, shape, shape.L, work_a, work_b, seg_dev.data(), sc, st, err, &fin);
-    if (rc) return rc;
-
     const uint32_t L = shape.L, n_internal = (1u << L) - 1, n_buckets = 1u << L, n_nodes = (1u << (L + 1)) - 1;
     const uint32_t vecn = 16 / sizeof(A), dpad = (d + vecn - 1) / vecn * vecn;
+    A *plane_w = nullptr, *plane_t = nullptr;   // two-means rule: the cuts of the tree's internal nodes
+    if (rule == 1 && n_internal) {
+        GB_CU(sc.get(&plane_w, (size_t)n_internal * dpad));
+        GB_CU(sc.get(&plane_t, (size_t)n_internal));
+    }
+    uint32_t* fin = nullptr;
+    rc = partition_levels<A>(raw, stride, d, pshape, pshape.L, work_a, work_b, seg_dev.data(), sc, st, err, &fin, rule, plane_w, plane_t, L, dpad);
+    if (rc) return rc;
+
     BallOut<A> out = alloc_out(ctx, n, shape);
     if (!out.pts || !out.ids || !out.centers || !out.radii) { err = "allocation of the tree arrays failed"; return (int)cudaErrorMemoryAllocation; }
+    if (plane_w && out.plane_w && out.plane_t) {
+        GB_CU(cudaMemcpyAsync(out.plane_w, plane_w, (size_t)n_internal * dpad * sizeof(A), cudaMemcpyDeviceToDevice, st));
+        GB_CU(cudaMemcpyAsync(out.plane_t, plane_t, (size_t)n_internal * sizeof(A), cudaMemcpyDeviceToDevice, st));
+    }
     gather_rows_kernel<A><<<(unsigned)((n * dpad + 255) / 256), 256, 0, st>>>(raw, stride, d, dpad, fin, n, out.pts, out.ids);
     GB_CU(cudaGetLastError());
     // per-node point counts from the shape
@@ -551,9 +727,9 @@ int build_ball_tree(const A* raw, uint64_t n_all, uint32_t d, uint64_t stride, u
 }
 
 template int build_ball_tree<float>(const float*, uint64_t, uint32_t, uint64_t, uint32_t, uint32_t, uint32_t, TreeShape&, uint64_t*,
-                                    BallOut<float> (*)(void*, uint64_t, const TreeShape&), void*, cudaStream_t, std::string&);
+                                    BallOut<float> (*)(void*, uint64_t, const TreeShape&), void*, cudaStream_t, std::string&, uint32_t, uint32_t);
 template int build_ball_tree<double>(const double*, uint64_t, uint32_t, uint64_t, uint32_t, uint32_t, uint32_t, TreeShape&, uint64_t*,
-                                     BallOut<double> (*)(void*, uint64_t, const TreeShape&), void*, cudaStream_t, std::string&);
+                                     BallOut<double> (*)(void*, uint64_t, const TreeShape&), void*, cudaStream_t, std::string&, uint32_t, uint32_t);
 
 // ======================================================================================================================
 // Vantage-point tree (create_node, src/vantage_point_tree.rs:146-197) level by level on the device.  The host builder sorts

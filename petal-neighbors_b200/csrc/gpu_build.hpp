@@ -24,8 +24,10 @@ struct TreeShape {
     uint64_t n = 0;
     uint32_t L = 0;
     std::vector<std::vector<uint32_t>> seg;  // [L + 1][2^l + 1]
-    void init(uint64_t n_, uint32_t L_) {
-        n = n_; L = L_;
+    uint32_t align = 0;  // > 0 (two-means partition only): nodes of more than one `align`-row tile split between tiles,
+                         // floor(tiles / 2) of them to the left, so every node starts on a multiple of `align`
+    void init(uint64_t n_, uint32_t L_, uint32_t align_ = 0) {
+        n = n_; L = L_; align = align_;
         seg.assign(L + 1, {});
         seg[0] = {0u, (uint32_t)n};
         for (uint32_t l = 0; l < L; ++l) {
@@ -35,6 +37,10 @@ struct TreeShape {
             for (size_t s = 0; s + 1 < a.size(); ++s) {
                 b[2 * s] = a[s];
                 b[2 * s + 1] = (uint32_t)(((uint64_t)a[s] + a[s + 1]) / 2);
+                if (align) {
+                    const uint32_t tiles = (a[s + 1] - a[s] + align - 1) / align;
+                    if (tiles >= 2) b[2 * s + 1] = a[s] + align * (tiles / 2);
+                }
             }
             b[size_t(1) << (l + 1)] = (uint32_t)n;
         }
@@ -48,6 +54,8 @@ struct BallOut {
     uint32_t* ids;   // n
     A* centers;      // n_nodes x dpad
     A* radii;        // n_nodes (-1 = empty node)
+    A* plane_w = nullptr;  // two-means rule only (optional): n_internal x dpad split directions ...
+    A* plane_t = nullptr;  // ... and n_internal pivot keys: a row with  row . w < t  went to the left child
 };
 
 // raw: n_all x d rows with `stride` elements between rows, on the device.  When shard_depth > 0 the first
@@ -59,7 +67,13 @@ template <typename A>
 int build_ball_tree(const A* raw, uint64_t n_all, uint32_t d, uint64_t stride, uint32_t bucket_size, uint32_t shard_depth,
                     uint32_t shard_index, TreeShape& shape, uint64_t* n_out,
                     BallOut<A> (*alloc_out)(void* ctx, uint64_t n, const TreeShape& shape), void* ctx, cudaStream_t st,
-                    std::string& err);
+                    std::string& err, uint32_t rule = 0, uint32_t order_levels = 0);
+// rule 0: the reference's split (the first column with the greatest spread, src/ball_tree.rs:577-613) -- the layout the host
+//         builder produces, bit for bit.
+// rule 1: the TWO-MEANS split (not the reference's; an engine-internal partition for the pruned tensor scan): the key of a
+//         point is its projection on the line through the two centroids of a 2-means clustering of a sample of its
+//         segment; median cut, shape, centroids and radii as for rule 0, so every query path is exact on the result.
+//         `order_levels` more levels of the same split order the rows inside the buckets.
 
 // ---- vantage-point tree (src/vantage_point_tree.rs:146-197): ranges of the level-l slices in the stored order; the
 // vantage point of a slice [lo, hi) sits at hi - 1, near = [lo, lo + (len-1)/2), far = [lo + (len-1)/2, hi - 1)

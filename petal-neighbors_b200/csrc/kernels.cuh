@@ -104,6 +104,10 @@ struct DevTree {
     uint32_t L, n_internal, n_buckets, n_nodes;
     int kind;
     A slack;                       // (2d + 8) * unit roundoff: relative slack of a triangle bound
+    // two-means partition only (else null): the cut of every internal node -- direction (n_internal x dpad) and pivot key;
+    // a row with  row . w < t  went to the left child.  Used to route queries to their home bucket, nothing else.
+    const A* plane_w;
+    const A* plane_t;
 };
 
 // ---- per-thread running top-k in registers (Neighbor + BinaryHeap, src/ball_tree.rs:378-423,
@@ -828,6 +832,16 @@ __global__ void home_bucket_kernel(const DevTree<A> t, const typename VT<A>::V* 
             const A R1 = t.radii[c1], R2 = t.radii[c2];
             if (R1 < A(0)) { node = c2; continue; }
             if (R2 < A(0)) { node = c1; continue; }
+            if (t.plane_w) {
+                // the side of the cut the points themselves were sent to (the nearer centroid disagrees with the median cut
+                // for a few per cent of the queries, and a query in the wrong bucket gets a useless seed)
+                const A* w = t.plane_w + (size_t)node * t.dpad;
+                const A* qs = reinterpret_cast<const A*>(qr);
+                A key = A(0);
+                for (uint32_t j = 0; j < t.dpad; ++j) key += qs[j] * __ldg(w + j);
+                node = key < t.plane_t[node] ? c1 : c2;
+                continue;
+            }
             node = dist_to(t.centers + (size_t)c1 * t.dv) <= dist_to(t.centers + (size_t)c2 * t.dv) ? c1 : c2;
         } else {
             const A mu = t.radii[node];

@@ -197,104 +197,227 @@ __global__ void __launch_bounds__(256) seed_bound_kernel(const DevTree<float> t,
     if (lane == 0) seed_t2[i] = kth < pos_inf<float>() ? thresh2(xsqrt(kth)) : pos_inf<float>();
 }
 
-// One block per query group (QT = 32 * n_sub sorted queries): one bit per point tile.  Two levels: (1) the ball of each
-// 32-query warp of the group against the tile ball -- one distance per (warp, tile); (2) only where that ball test cannot
-// exclude the tile, the warp's 32 queries one by one (lane = query), each against its own seed; a tile confirmed by one
-// query is not examined further.  With dense queries (1) decides almost everything; with sparse queries, whose warps span
-// several clusters, (2) keeps the lists short.  bits[g * words + w] bit b <-> tile 32 w + b; cnt[g] = tiles to scan;
-// total[0] += pairs the group will see.
-__global__ void __launch_bounds__(256) tile_bitmap_kernel(const float4* __restrict__ qs, const float* __restrict__ seed_t2, uint32_t nq, uint32_t qt,
-                                                          const float* __restrict__ tcen, const float* __restrict__ trad, uint32_t n_tiles,
-                                                          uint32_t dv, float slack, uint32_t words, uint32_t* __restrict__ bits,
-                                                          uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total) {
-    extern __shared__ float4 sm4[];            // [n_sub][dv] warp centres
-    __shared__ float s_r[16], s_mu[16];        // warp radius; max over the warp's queries of (seed + distance to the warp centre)
-    __shared__ float s_qtheta[512];            // every query's own seed as a distance (-inf: no such query)
-    __shared__ uint32_t s_cnt;
-    const uint32_t g = blockIdx.x, n_sub = qt / 32;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    if (threadIdx.x == 0) s_cnt = 0;
-    for (uint32_t w = warp; w < n_sub; w += n_warps) {
-        const uint32_t qi = g * qt + w * 32 + lane;
-        const bool act = qi < nq;
-        const uint32_t n_act = min(32u, nq > g * qt + w * 32 ? nq - (g * qt + w * 32) : 0u);
-        const float4* qr = qs + (size_t)qi * dv;
-        for (uint32_t j = 0; j < dv; ++j) {
-            float4 v = act ? __ldg(qr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int o = 16; o; o >>= 1) {
-                v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-                v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
-            }
-            const float inv = n_act ? 1.f / (float)n_act : 0.f;
-            if (lane == 0) sm4[w * dv + j] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+// ---- tile bitmaps: one bit per (query group of a filter CTA, 128-point tile) -----------------------------------------------
+// A group is QT = 32 n_sub sorted queries.  The unit of the test is a BALL of queries (centre c, radius R, and
+// mu = max over its queries of seed_q + |q - c|): every point p of tile T has |q - p| >= |c - c_T| - |q - c| - R_T, so no
+// query of the ball needs T when  |c - c_T| - R_T - slack (|c - c_T| + R + R_T) > mu.
+//   1. warp_balls_kernel   : TWO balls for every 32 consecutive sorted queries (the warp split around two far-apart queries)
+//   2. ball_tile_kernel    : every (ball, tile) pair -- 32 balls in shared memory per block, a thread per tile with 32
+//                            accumulators, one ballot per ball gives 32 tile bits at a time -> a bitmap and a count per ball
+//   3. wide_select_kernel  : a warp whose count is more than twice the smallest count of its group (queries of three
+//                            clusters in one warp ...) is "wide": at most a quarter of the warps
+//   4. ball_tile_kernel<PER_QUERY>: the 32 queries of a wide warp as 32 balls of radius 0, each against its own seed; the
+//                            OR of the 32 answers replaces the warp's two bitmaps
+//   5. group_bits_kernel   : OR over the balls of a group, tiles to scan per group, pairs the scan will see
+// (r2, first version: one kernel per group that refined ball verdicts query by query, re-reading the 32 query rows for
+// every candidate tile -- 180 ms per million queries on the two-means partition of BASELINE config 3, where the refinement
+// does reject tiles and therefore never gave up; the filter it fed took 50 ms.)
+constexpr uint32_t PR_NONE = 0xffffffffu;
+
+// Two balls per warp of 32 sorted queries (balls 2w and 2w + 1).  Queries are sorted by home bucket only, and a bucket that
+// holds fragments of two clusters sends queries of both into one warp: one ball around them all would reach every tile.
+// The warp is therefore split around two far-apart queries (a: the query farthest from the warp's mean, b: the query
+// farthest from a; every query joins the nearer one), and each half gets its own centre, radius and bound.  A half
+// without queries has mu = -inf and needs nothing.
+__global__ void __launch_bounds__(256) warp_balls_kernel(const float4* __restrict__ qs, const float* __restrict__ seed_t2, uint32_t nq, uint32_t n_warps,
+                                                         uint32_t dv, float4* __restrict__ bcen, float* __restrict__ brad, float* __restrict__ bmu,
+                                                         float* __restrict__ qtheta) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31, w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_warps) return;
+    const uint32_t q0 = w * 32, qi = q0 + lane;
+    const bool act = qi < nq;
+    const uint32_t n_act = q0 < nq ? min(32u, nq - q0) : 0u;
+    const float4* qr = qs + (size_t)(act ? qi : 0) * dv;
+    // the seed as a DISTANCE bound: sqrt of the squared-domain threshold, rounded up
+    const float th = act ? xmul(xsqrt(seed_t2[qi]), 1.0000002f) : -pos_inf<float>();
+    qtheta[qi] = th;   // (the array is padded to whole warps)
+    float4* c0 = bcen + (size_t)(2 * w) * dv;
+    float4* c1 = c0 + dv;
+    auto sum4 = [&](float4 v) {
+        for (int o = 16; o; o >>= 1) {
+            v.x += __shfl_xor_sync(full, v.x, o); v.y += __shfl_xor_sync(full, v.y, o);
+            v.z += __shfl_xor_sync(full, v.z, o); v.w += __shfl_xor_sync(full, v.w, o);
         }
-        __syncwarp();
-        float acc = 0.f;
-        if (act) for (uint32_t j = 0; j < dv; ++j) acc = fold(acc, __ldg(qr + j), sm4[w * dv + j]);
-        float r = act ? xsqrt(acc) : 0.f;
-        // the seed as a DISTANCE bound: sqrt of the squared-domain threshold, rounded up
-        const float th = act ? xmul(xsqrt(seed_t2[qi]), 1.0000002f) : -pos_inf<float>();
-        s_qtheta[w * 32 + lane] = th;
-        // |q - p| >= |c_w - c_T| - |q - c_w| - R_T for every point p of tile T, so query q can skip T when
-        // |c_w - c_T| - R_T - slack > seed_q + |q - c_w|; the warp needs T unless that holds for its largest seed_q + |q - c_w|
-        float mu = act ? xmul(xadd(th, r), 1.0000002f) : -pos_inf<float>();
-        for (int o = 16; o; o >>= 1) { r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o)); mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o)); }
-        if (lane == 0) { s_r[w] = r; s_mu[w] = mu; }   // a warp without a live query has mu = -inf: it needs nothing
+        return v;
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // (1) the warp's mean, parked in ball 0's centre
+    const float inv = n_act ? 1.f / (float)n_act : 0.f;
+    for (uint32_t j = 0; j < dv; ++j) {
+        const float4 v = sum4(act ? __ldg(qr + j) : zero4);
+        if (lane == 0) c0[j] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    }
+    __syncwarp();
+    float acc = 0.f;
+    if (act) for (uint32_t j = 0; j < dv; ++j) acc = fold(acc, __ldg(qr + j), c0[j]);
+    // (2) a = the query farthest from the mean, b = the query farthest from a (lowest lane on ties)
+    float far = act ? acc : -1.f, best = far;
+    for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(full, best, o));
+    const int la = __ffs(__ballot_sync(full, far == best)) - 1;
+    float da = 0.f;
+    for (uint32_t j = 0; j < dv; ++j) {
+        const float4 mine = act ? __ldg(qr + j) : zero4;
+        float4 a;
+        a.x = __shfl_sync(full, mine.x, la); a.y = __shfl_sync(full, mine.y, la); a.z = __shfl_sync(full, mine.z, la); a.w = __shfl_sync(full, mine.w, la);
+        da = fold(da, mine, a);
+    }
+    far = act ? da : -1.f; best = far;
+    for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(full, best, o));
+    const int lb = __ffs(__ballot_sync(full, far == best)) - 1;
+    float db = 0.f;
+    for (uint32_t j = 0; j < dv; ++j) {
+        const float4 mine = act ? __ldg(qr + j) : zero4;
+        float4 b;
+        b.x = __shfl_sync(full, mine.x, lb); b.y = __shfl_sync(full, mine.y, lb); b.z = __shfl_sync(full, mine.z, lb); b.w = __shfl_sync(full, mine.w, lb);
+        db = fold(db, mine, b);
+    }
+    const bool g1 = act && db < da;          // nearer b: second half; everything else that is live: first half
+    const bool g0 = act && !g1;
+    const uint32_t n1 = __popc(__ballot_sync(full, g1)), n0 = n_act - n1;
+    const float inv0 = n0 ? 1.f / (float)n0 : 0.f, inv1 = n1 ? 1.f / (float)n1 : 0.f;
+    __syncwarp();
+    // (3) the centres of the two halves
+    for (uint32_t j = 0; j < dv; ++j) {
+        const float4 mine = act ? __ldg(qr + j) : zero4;
+        const float4 s0 = sum4(g0 ? mine : zero4), s1 = sum4(g1 ? mine : zero4);
+        if (lane == 0) {
+            c0[j] = make_float4(s0.x * inv0, s0.y * inv0, s0.z * inv0, s0.w * inv0);
+            c1[j] = make_float4(s1.x * inv1, s1.y * inv1, s1.z * inv1, s1.w * inv1);
+        }
+    }
+    __syncwarp();
+    // (4) radius and bound of each half: |q - p| >= |c - c_T| - |q - c| - R_T for every point p of tile T
+    const float4* cm = g1 ? c1 : c0;
+    acc = 0.f;
+    if (act) for (uint32_t j = 0; j < dv; ++j) acc = fold(acc, __ldg(qr + j), cm[j]);
+    const float r = act ? xsqrt(acc) : 0.f;
+    const float mu = act ? xmul(xadd(th, r), 1.0000002f) : -pos_inf<float>();
+    float r0 = g0 ? r : 0.f, r1 = g1 ? r : 0.f, m0 = g0 ? mu : -pos_inf<float>(), m1 = g1 ? mu : -pos_inf<float>();
+    for (int o = 16; o; o >>= 1) {
+        r0 = fmaxf(r0, __shfl_xor_sync(full, r0, o)); r1 = fmaxf(r1, __shfl_xor_sync(full, r1, o));
+        m0 = fmaxf(m0, __shfl_xor_sync(full, m0, o)); m1 = fmaxf(m1, __shfl_xor_sync(full, m1, o));
+    }
+    if (lane == 0) { brad[2 * w] = r0; brad[2 * w + 1] = r1; bmu[2 * w] = m0; bmu[2 * w + 1] = m1; }
+}
+
+// PER_QUERY = false: block b tests balls [32 b, 32 b + 32) (centres bcen, radii brad, bounds bmu); out_bits[ball][word],
+//                    out_cnt[ball] = tiles the ball needs.
+// PER_QUERY = true : block b tests the 32 queries of wide ball wlist[b] (centres = the query rows, radius 0, bound =
+//                    qtheta); out_bits[b][word] = OR over the 32 queries.
+template <bool PER_QUERY>
+__global__ void __launch_bounds__(256) ball_tile_kernel(const float4* __restrict__ cen, const float* __restrict__ brad, const float* __restrict__ bmu,
+                                                        uint32_t n_balls, const uint32_t* __restrict__ wlist, const uint32_t* __restrict__ n_wide,
+                                                        uint32_t wide_cap, const float* __restrict__ tcen, const float* __restrict__ trad,
+                                                        uint32_t n_tiles, uint32_t dv, float slack, uint32_t words, uint32_t* __restrict__ out_bits,
+                                                        uint32_t* __restrict__ out_cnt) {
+    extern __shared__ float4 sm4[];   // [32][dv] ball centres
+    __shared__ float s_r[32], s_mu[32];
+    __shared__ uint32_t s_cnt[32];
+    uint32_t ball0;
+    if (PER_QUERY) {
+        if (blockIdx.x >= min(*n_wide, wide_cap)) return;
+        ball0 = wlist[blockIdx.x] * 32;   // first query of the wide ball: centres are query rows
+    } else {
+        ball0 = blockIdx.x * 32;
+    }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (uint32_t e = threadIdx.x; e < 32 * dv; e += blockDim.x) {
+        const uint32_t b = e / dv;
+        sm4[e] = (PER_QUERY || ball0 + b < n_balls) ? __ldg(cen + (size_t)(ball0 + b) * dv + (e % dv)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (threadIdx.x < 32) {
+        const uint32_t b = ball0 + threadIdx.x;
+        s_r[threadIdx.x] = PER_QUERY ? 0.f : (b < n_balls ? brad[b] : 0.f);
+        s_mu[threadIdx.x] = (PER_QUERY || b < n_balls) ? bmu[b] : -pos_inf<float>();
+        s_cnt[threadIdx.x] = 0;
     }
     __syncthreads();
-    uint32_t mine = 0, tried = 0, rejected = 0;
+    uint32_t mine = 0;   // tiles ball `lane` needs, over this warp's share of the tiles
     for (uint32_t t0 = warp * 32; t0 < words * 32; t0 += n_warps * 32) {
         const uint32_t t = t0 + lane;
-        uint32_t wmask = 0;  // warps of the group whose ball cannot exclude tile t
-        if (t < n_tiles) {
-            const float4* ct = reinterpret_cast<const float4*>(tcen) + (size_t)t * dv;
-            const float rt = trad[t];
-            float acc[16];
+        const bool live = t < n_tiles;
+        float acc[32];
 #pragma unroll
-            for (int w = 0; w < 16; ++w) acc[w] = 0.f;
+        for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+        if (live) {
+            const float4* ct = reinterpret_cast<const float4*>(tcen) + (size_t)t * dv;
             for (uint32_t j = 0; j < dv; ++j) {
                 const float4 c = __ldg(ct + j);
 #pragma unroll
-                for (int w = 0; w < 16; ++w)
-                    if (w < (int)n_sub) acc[w] = fold(acc[w], sm4[w * dv + j], c);
+                for (int b = 0; b < 32; ++b) acc[b] = fold(acc[b], sm4[b * dv + j], c);
             }
+        }
+        const float rt = live ? trad[t] : 0.f;
+        uint32_t word = 0;
 #pragma unroll
-            for (int w = 0; w < 16; ++w) {
-                if (w < (int)n_sub) {
-                    const float cd = xsqrt(acc[w]);
-                    const float sum = xadd(xadd(cd, s_r[w]), rt);
-                    const float lb = xsub(xsub(cd, rt), xmul(slack, sum));
-                    wmask |= (lb > s_mu[w]) ? 0u : 1u << w;
-                }
-            }
+        for (int b = 0; b < 32; ++b) {
+            const float cd = xsqrt(acc[b]);
+            const float sum = xadd(xadd(cd, s_r[b]), rt);
+            const float lb = xsub(xsub(cd, rt), xmul(slack, sum));
+            const unsigned need = __ballot_sync(0xffffffffu, live && !(lb > s_mu[b]));
+            if (PER_QUERY) word |= need;
+            else if ((int)lane == b) word = need;
         }
-        // level 2: lane = query of warp w, one candidate tile at a time (warp-uniform loop).  It only pays where it rejects
-        // tiles: once 64 refinements of this warp have rejected fewer than a quarter, level 1's verdicts are taken as they are.
-        unsigned needed = 0;  // lanes (tiles) confirmed
-        for (uint32_t w = 0; w < n_sub; ++w) {
-            unsigned cand = __ballot_sync(0xffffffffu, (wmask >> w) & 1u) & ~needed;
-            if (!cand) continue;
-            if (tried >= 64 && rejected * 4 < tried) { needed |= cand; continue; }
-            const uint32_t qi = g * qt + w * 32 + lane;
-            const float4* qr = qs + (size_t)min(qi, nq - 1) * dv;
-            const float qth = s_qtheta[w * 32 + lane];
-            while (cand) {
-                const int src = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const uint32_t tt = t0 + src;
-                const float4* ct = reinterpret_cast<const float4*>(tcen) + (size_t)tt * dv;
-                const float rt = trad[tt];
-                float acc = 0.f;
-                for (uint32_t j = 0; j < dv; ++j) acc = fold(acc, __ldg(qr + j), __ldg(ct + j));
-                const float cd = xsqrt(acc);
-                const float lb = xsub(xsub(cd, rt), xmul(slack, xadd(cd, rt)));
-                ++tried;
-                if (__ballot_sync(0xffffffffu, !(lb > qth))) needed |= 1u << src; else ++rejected;
-            }
+        if (PER_QUERY) {
+            if (lane == 0) out_bits[(size_t)blockIdx.x * words + (t0 >> 5)] = word;
+        } else {
+            if (ball0 + lane < n_balls) out_bits[(size_t)(ball0 + lane) * words + (t0 >> 5)] = word;
+            mine += __popc(word);
         }
-        if (lane == 0) { bits[(size_t)g * words + (t0 >> 5)] = needed; mine += __popc(needed); }
     }
-    if (lane == 0 && mine) atomicAdd(&s_cnt, mine);
+    if (!PER_QUERY) {
+        if (mine) atomicAdd(&s_cnt[lane], mine);
+        __syncthreads();
+        if (threadIdx.x < 32 && ball0 + threadIdx.x < n_balls) out_cnt[ball0 + threadIdx.x] = s_cnt[threadIdx.x];
+    }
+}
+
+// one thread per group: its wide warps get a slot in the refinement list (wslot[warp], PR_NONE otherwise).  A warp counts
+// with the larger of its two balls' tile counts.
+__global__ void wide_select_kernel(const uint32_t* __restrict__ ball_cnt, const float* __restrict__ bmu, uint32_t n_groups, uint32_t n_sub,
+                                   uint32_t wide_cap, uint32_t* __restrict__ wslot, uint32_t* __restrict__ wlist, uint32_t* __restrict__ n_wide) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    auto live = [&](uint32_t w) { return bmu[2 * w] > -pos_inf<float>() || bmu[2 * w + 1] > -pos_inf<float>(); };
+    auto need = [&](uint32_t w) { return max(ball_cnt[2 * w], ball_cnt[2 * w + 1]); };
+    uint32_t lo = PR_NONE;
+    for (uint32_t i = 0; i < n_sub; ++i)
+        if (live(g * n_sub + i)) lo = min(lo, need(g * n_sub + i));
+    for (uint32_t i = 0; i < n_sub; ++i) {
+        const uint32_t w = g * n_sub + i;
+        uint32_t slot = PR_NONE;
+        if (lo != PR_NONE && live(w) && need(w) > 2u * lo + 16u) {
+            slot = atomicAdd(n_wide, 1u);
+            if (slot < wide_cap) wlist[slot] = w; else slot = PR_NONE;
+        }
+        wslot[w] = slot;
+    }
+}
+
+// one block per group: OR over its warps (both balls of a warp, or the refined bitmap of a wide warp), cnt[g] = tiles to
+// scan, total[0] += pairs the group will see
+__global__ void __launch_bounds__(256) group_bits_kernel(const uint32_t* __restrict__ ball_bits, const uint32_t* __restrict__ wide_bits,
+                                                         const uint32_t* __restrict__ wslot, uint32_t nq, uint32_t qt, uint32_t n_sub, uint32_t words,
+                                                         uint32_t* __restrict__ bits, uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total) {
+    __shared__ uint32_t s_cnt;
+    __shared__ uint32_t s_slot[16];
+    const uint32_t g = blockIdx.x;
+    if (threadIdx.x == 0) s_cnt = 0;
+    if (threadIdx.x < n_sub) s_slot[threadIdx.x] = wslot[g * n_sub + threadIdx.x];
+    __syncthreads();
+    uint32_t mine = 0;
+    for (uint32_t wd = threadIdx.x; wd < words; wd += blockDim.x) {
+        uint32_t v = 0;
+        for (uint32_t i = 0; i < n_sub; ++i) {
+            const uint32_t slot = s_slot[i];
+            const size_t w = (size_t)g * n_sub + i;
+            v |= slot != PR_NONE ? wide_bits[(size_t)slot * words + wd] : (ball_bits[(2 * w) * words + wd] | ball_bits[(2 * w + 1) * words + wd]);
+        }
+        bits[(size_t)g * words + wd] = v;
+        mine += __popc(v);
+    }
+    if (mine) atomicAdd(&s_cnt, mine);
     __syncthreads();
     if (threadIdx.x == 0) {
         cnt[g] = s_cnt;

@@ -24,7 +24,8 @@ pub struct pn_build_opts {
     pub shard_index: u32,
     pub builder: u32, // pn_builder: 0 auto, 1 host, 2 device
     pub prune: u32,   // pn_prune: 0 auto, 1 on, 2 off
-    pub reserved: [u32; 6],
+    pub partition: u32, // pn_partition: 0 auto, 1 reference, 2 two-means
+    pub reserved: [u32; 5],
 }
 
 extern "C" {
