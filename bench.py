@@ -322,9 +322,16 @@ def extra_c3(pn, torch, synth, stream, flush, steps):
             "pairs_over_NQ": ctr["pairs"] / (float(n) * nq), "rerank_per_query": ctr["rerank_pairs"] / nq,
             "e2e": {"value": nq / float(np.mean(wall)), "unit": UNIT, "h2d_bytes_per_step": int(ctr_host["h2d_bytes"]),
                     "d2h_bytes_per_step": int(ctr_host["d2h_bytes"]), "matches_device_path": same},
-            "build_seconds": info["build_seconds"], "build": "on the host (VP trees)",
+            "build_seconds": info["build_seconds"],
+            "build": "VP arrays on the host; the ball partitions the tensor path scans (reference rule, then two-means) on the device",
+            "tensor_partition": "two-means" if info["tensor_partition"] == 1 else "reference", "seeded_scan": bool(info["prune_seeded"]),
+            "tile_bitmaps": bool(info["prune_tiles"]), "est_tile_frac": info["est_tile_frac"],
             "roofline": {"bound": "tensor", "achieved": rl["tensor"]["useful_tflops"], "peak": rl["tensor"]["peak_burst_tflops"], "unit": "TFLOP/s",
-                         "frac": rl["tensor"]["frac_of_burst"], "detail": rl}}
+                         "frac": rl["tensor"]["frac_of_burst"],
+                         "note": "flops of the (query, point) pairs the pruned scan really evaluates, over the whole scan time (sort, seeds, tile "
+                                 "bitmaps, filter); dense_equivalent_tflops = 2 d N Q / the same time, what a scan without pruning would need to do",
+                         "dense_equivalent_tflops": 2.0 * d * float(n) * nq / (ctr["scan_ms"] * 1e-3) / 1e12 if ctr["scan_ms"] else None,
+                         "detail": rl}}
 
 
 def extra_c4(pn, torch, synth, steps):

@@ -92,18 +92,21 @@ def test_pruning_with_ties_far_queries_and_self_query(pn, oracle):
 
 
 def test_c3_full_size_seeded(pn, oracle):
-    """BASELINE config 3 at full size in AUTO: the build-time estimates turn the SEEDED scan on for this mixture (every query
-    starts from the k-th distance within its home bucket, so the exact reranks fall from ~290 to ~20 per query at k = 1),
-    while tile skipping stays off -- in d = 64 the buckets mix neighbouring clusters and only ~13 % of the pairs could be
-    skipped.  Exact on samples, VP handle and ball handle."""
+    """BASELINE config 3 at full size in AUTO.  The build-time estimates turn the SEEDED scan on for this mixture (every query
+    starts from the k-th distance within its home bucket: exact reranks fall from ~290 to ~10 per query at k = 1).  With the
+    reference partition tile skipping would stay off -- in d = 64 its buckets mix neighbouring clusters and only ~10 % of the
+    pairs could be skipped -- so the handle builds the two-means partition of the same points, whose estimates turn the tile
+    bitmaps on: well under 60 % of the pairs are scanned.  Exact on samples, VP handle and ball handle."""
     from petal_neighbors_b200 import synth
     n = nq = 1_000_000
     pts = synth.fast_gaussian_mixture(n, 64, 5, n_centers=1024, sigma=0.05, center_seed=4)
     Q = synth.fast_gaussian_mixture(nq, 64, 6, n_centers=1024, sigma=0.05, center_seed=4)
     vp = pn.VantagePointTree.euclidean(pts)
+    inf = vp.info()
+    assert inf["tensor_partition"] == 1 and inf["prune_seeded"] == 1 and inf["prune_tiles"] == 1, inf
     vi, vd = vp.query_nearest_batch(Q)
     c = vp.counters()
-    assert 0 < c["pairs"] <= float(n) * nq
+    assert 0 < c["pairs"] < 0.6 * float(n) * nq, c["pairs"] / (float(n) * nq)
     assert c["rerank_pairs"] / nq < 100, c["rerank_pairs"] / nq
     sample = np.arange(0, nq, nq // 400)[:400]
     oi, od = oracle.brute_knn(pts, Q[sample], 1)
@@ -114,4 +117,9 @@ def test_c3_full_size_seeded(pn, oracle):
     assert c["pairs"] < float(n) * 300_000
     s2 = sample[sample < 300_000]
     oi, od = oracle.brute_knn(pts, Q[s2], 10)
+    assert np.array_equal(idx[s2], oi.astype(np.uint64)) and np.array_equal(bits(dist[s2]), bits(od))
+    auto = pn.BallTree.euclidean(pts)                                  # a ball handle in AUTO keeps the two-means partition as well
+    assert auto.info()["tensor_partition"] == 1
+    idx, dist = auto.query_batch(Q[:300_000], 10)
+    assert auto.counters()["pairs"] < 0.75 * float(n) * 300_000
     assert np.array_equal(idx[s2], oi.astype(np.uint64)) and np.array_equal(bits(dist[s2]), bits(od))
