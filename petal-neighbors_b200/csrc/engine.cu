@@ -688,7 +688,10 @@ struct Engine final : pn_tree {
             CU(cudaGetLastError());
             {
                 // tile bitmaps (tc_prune.cuh): balls of 32 sorted queries against the tile balls, wide balls refined query by query
-                const uint32_t n_sub = QT / 32, n_warps = n_qt * n_sub, n_balls = 2 * n_warps, wide_cap = std::max<uint32_t>(1u, n_warps / 4);
+                // PN_WIDE_DIV (diagnostic): the share of warps that may be refined query by query is 1 / PN_WIDE_DIV (0: none)
+                static const int wide_div = getenv("PN_WIDE_DIV") ? atoi(getenv("PN_WIDE_DIV")) : 4;
+                const uint32_t n_sub = QT / 32, n_warps = n_qt * n_sub, n_balls = 2 * n_warps;
+                const uint32_t wide_cap = wide_div > 0 ? std::max<uint32_t>(1u, n_warps / (uint32_t)wide_div) : 1u;
                 const size_t smem = (size_t)32 * dt.dv * 16;
                 TRY(w_bcen.ensure((size_t)n_balls * ft.dpad * 4)); TRY(w_brad.ensure((size_t)n_balls * 4)); TRY(w_bmu.ensure((size_t)n_balls * 4));
                 TRY(w_qth.ensure((size_t)n_warps * 32 * 4)); TRY(w_bbits.ensure((size_t)n_balls * words * 4)); TRY(w_bcnt.ensure((size_t)n_balls * 4));
@@ -706,10 +709,10 @@ struct Engine final : pn_tree {
                                                                                    d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
                                                                                    w_bbits.as<uint32_t>(), w_bcnt.as<uint32_t>());
                 CU(cudaGetLastError());
-                tc::wide_select_kernel<<<(n_qt + 127) / 128, 128, 0, st>>>(w_bcnt.as<uint32_t>(), w_bmu.as<float>(), n_qt, n_sub, wide_cap, w_wslot.as<uint32_t>(),
+                tc::wide_select_kernel<<<(n_qt + 127) / 128, 128, 0, st>>>(w_bcnt.as<uint32_t>(), w_bmu.as<float>(), n_qt, n_sub, wide_div > 0 ? wide_cap : 0u, w_wslot.as<uint32_t>(),
                                                                           w_wlist.as<uint32_t>(), w_nwide.as<uint32_t>());
                 CU(cudaGetLastError());
-                tc::ball_tile_kernel<true><<<wide_cap, 256, smem, st>>>(qsorted, nullptr, w_qth.as<float>(), nq, w_wlist.as<uint32_t>(), w_nwide.as<uint32_t>(), wide_cap,
+                tc::ball_tile_kernel<true><<<wide_cap, 256, smem, st>>>(qsorted, nullptr, w_qth.as<float>(), nq, w_wlist.as<uint32_t>(), w_nwide.as<uint32_t>(), wide_div > 0 ? wide_cap : 0u,
                                                                        d_tcen.as<float>(), d_trad.as<float>(), n_tiles, dt.dv, (float)dt.slack, words,
                                                                        w_wbits.as<uint32_t>(), nullptr);
                 CU(cudaGetLastError());

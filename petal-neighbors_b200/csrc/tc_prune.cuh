@@ -173,25 +173,38 @@ __global__ void __launch_bounds__(256) seed_bound_kernel(const DevTree<float> t,
     const float4* qr = qs + (size_t)i * t.dv;
     float ks = pos_inf<float>();    // this lane's entry of the sorted list
     float kth = pos_inf<float>();   // entry k-1 (warp-uniform)
-    for (uint32_t base = lo; base < hi; base += 32) {
-        const uint32_t p = base + lane;
-        float acc = pos_inf<float>();
-        if (p < hi) {
-            const float4* pr = t.pts + (size_t)p * t.dv;
-            acc = 0.f;
-            for (uint32_t j = 0; j < t.dv; ++j) acc = fold(acc, __ldg(qr + j), __ldg(pr + j));
+    // NP points per lane and round: NP independent fold chains keep NP L2 round trips in flight (one chain per lane left the
+    // kernel latency-bound: 16 % of the issue slots at 92 % occupancy, profiles/r02_ncu_full_pruned_scan_c3p.md)
+    constexpr int NP = 4;
+    for (uint32_t base = lo; base < hi; base += 32 * NP) {
+        float acc[NP];
+        const float4* pr[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const uint32_t p = base + u * 32 + lane;
+            pr[u] = t.pts + (size_t)min(p, hi - 1) * t.dv;
+            acc[u] = 0.f;
         }
-        unsigned mask = __ballot_sync(full, acc < kth);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float c = __shfl_sync(full, acc, src);
-            const uint32_t pos = __popc(__ballot_sync(full, ks <= c));   // entries not larger than the candidate: a prefix
-            if (pos >= k) continue;
-            const float up = __shfl_up_sync(full, ks, 1);
-            if ((uint32_t)lane > pos) ks = up;
-            else if ((uint32_t)lane == pos) ks = c;
-            kth = __shfl_sync(full, ks, (int)k - 1);
+        for (uint32_t j = 0; j < t.dv; ++j) {
+            const float4 qv = __ldg(qr + j);
+#pragma unroll
+            for (int u = 0; u < NP; ++u) acc[u] = fold(acc[u], qv, __ldg(pr[u] + j));
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const float cand = base + u * 32 + lane < hi ? acc[u] : pos_inf<float>();
+            unsigned mask = __ballot_sync(full, cand < kth);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float c = __shfl_sync(full, cand, src);
+                const uint32_t pos = __popc(__ballot_sync(full, ks <= c));   // entries not larger than the candidate: a prefix
+                if (pos >= k) continue;
+                const float up = __shfl_up_sync(full, ks, 1);
+                if ((uint32_t)lane > pos) ks = up;
+                else if ((uint32_t)lane == pos) ks = c;
+                kth = __shfl_sync(full, ks, (int)k - 1);
+            }
         }
     }
     if (lane == 0) seed_t2[i] = kth < pos_inf<float>() ? thresh2(xsqrt(kth)) : pos_inf<float>();

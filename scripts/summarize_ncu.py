@@ -20,6 +20,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 WHAT = {"c2": ("knn_filter", "BASELINE config 2 at the bench's own launch size: 1M x 16 f32 points, 1 000 000 queries, k = 10 (`scripts/ncu_targets.py c2`; seeded dense plan: main launch of 13 whole waves = 985 088 queries, then the tail launch)"),
         "t128": ("knn_filter", "north-star shape 10M x 128 f32, 75 776 queries = two whole waves of 148 CTAs x 256 queries, k = 10 (`scripts/ncu_targets.py t128`)"),
         "c3": ("knn_filter", "VantagePointTree 1M x 64 f32 mixture, 303 104 queries, query_nearest: the seeded tensor scan on the ball partition (`scripts/ncu_targets.py c3`)"),
+        "c3p": ("pruned_scan", "VantagePointTree 1M x 64 f32 mixture, 303 104 queries, query_nearest: the PRUNED tensor scan on the two-means partition -- seeds, tile bitmaps (ball_tile_kernel: the balls of all warps, then the queries of the wide warps), filter over the tiles the bitmaps leave (`scripts/ncu_targets.py c3`)"),
         "c4": ("radius", "BallTree::query_radius 10M x 3 f32, r = 0.01, 262 144 queries in one chunk (`scripts/ncu_targets.py c4`)"),
         "c4knn": ("knn_warp", "BallTree::query 10M x 3 f32, 1 000 000 device-resident queries, k = 10: the warp-per-query scan (`scripts/ncu_targets.py c4knn`)"),
         "c1": ("knn_warp", "BASELINE config 1: BallTree 10k x 3 f64, every point a query (query_self), k = 10 (`scripts/ncu_targets.py c1`)")}
@@ -42,7 +43,7 @@ for w, (kern, desc) in WHAT.items():
         out.append("")
     open(os.path.join(P, f"r02_ncu_full_{kern}_{w}.md"), "w").write("\n".join(out) + "\n")
     print("wrote", f"r02_ncu_full_{kern}_{w}.md")
-for w in ("c2", "c3", "c4", "c4knn", "c1"):
+for w in ("c2", "c3", "c3p", "c4", "c4knn", "c1"):
     path = os.path.join(G, f"r02_launches_{w}.csv")
     if not os.path.exists(path):
         continue
@@ -63,7 +64,7 @@ for w in ("c2", "c3", "c4", "c4knn", "c1"):
         agg[name][1] += v
     mine = {k: v for k, v in agg.items() if not k.startswith("at::")}
     tot = sum(v for _, v in mine.values())
-    out = [f"# Round 2 -- launch list of `python scripts/ncu_targets.py {w}` (`ncu --metrics gpu__time_duration.sum --clock-control none`)", "",
+    out = [f"# Round 2 -- launch list of `python scripts/ncu_targets.py {w.replace('c3p', 'c3')}` (`ncu --metrics gpu__time_duration.sum --clock-control none`)", "",
            f"{WHAT[w][1]}.  Two calls plus the tree build; per-launch times are cold-cache and serialised, so only the SHARES matter.",
            f"Library kernels only ({len(mine)} kernels, {sum(c for c, _ in mine.values())} launches, {tot:.2f} ms); "
            f"torch's generator kernels of the synthetic inputs ({sum(c for k, (c, _) in agg.items() if k.startswith('at::'))} launches) are left out.", "",
